@@ -1,0 +1,99 @@
+"""GPU parity of ergm_gemm_bf16 (tcgen05) against a plain fp32 torch matmul of the
+bf16-rounded operands (the operation Conv1D/addmm performs at model.py:222,244,263,265,698)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(a, b, a_mn, b_mn):
+    A = a.float().t() if a_mn else a.float()
+    B = b.float() if b_mn else b.float().t()
+    return A @ B
+
+
+def _run(M, N, K, a_mn, b_mn, block_n=0, out_dtype=torch.float32, split_k=1, atomic=False, seed=0):
+    from ergm_b200 import ops, _lib as L
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    a = torch.randn((K, M) if a_mn else (M, K), device="cuda", generator=g).bfloat16()
+    b = torch.randn((K, N) if b_mn else (N, K), device="cuda", generator=g).bfloat16()
+    ldd = (N + 7) // 8 * 8
+    d = torch.zeros(M, ldd, device="cuda", dtype=out_dtype)
+    ops.gemm(a, b, d, M=M, N=N, K=K, a_major=int(a_mn), b_major=int(b_mn), block_n=block_n,
+             split_k=split_k, epilogue=L.EPI_ATOMIC if atomic else 0)
+    torch.cuda.synchronize()
+    ref = _ref(a, b, a_mn, b_mn)
+    got = d[:, :N].float()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    return err, scale, d
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize("block_n", [64, 128, 256])
+def test_gemm_majors(cuda_device, a_mn, b_mn, block_n):
+    err, scale, _ = _run(256, 512, 320, a_mn, b_mn, block_n)
+    assert err <= 2e-3 * scale, (err, scale)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (8192, 2304, 768), (100, 72, 200), (1, 8, 8),
+                                   (333, 50260, 768), (4096, 768, 3072), (77, 1000, 1024)])
+def test_gemm_shapes_fwd_layout(cuda_device, M, N, K):
+    err, scale, d = _run(M, N, K, 0, 1)
+    assert err <= 2e-3 * scale, (err, scale)
+    # padding columns must stay untouched
+    assert d[:, N:].abs().max().item() == 0 if d.shape[1] > N else True
+
+
+def test_gemm_bf16_out(cuda_device):
+    err, scale, _ = _run(512, 768, 768, 0, 1, out_dtype=torch.bfloat16)
+    assert err <= 1e-2 * scale
+
+
+@pytest.mark.parametrize("split_k", [1, 2, 5])
+def test_gemm_wgrad_splitk(cuda_device, split_k):
+    err, scale, _ = _run(768, 768, 4096, 1, 1, split_k=split_k, atomic=True)
+    assert err <= 2e-3 * scale, (err, scale)
+
+
+def test_gemm_epilogues(cuda_device):
+    from ergm_b200 import ops, _lib as L
+    M, N, K = 300, 3072, 768
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(K, N, device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g)
+    pre_ref = a.float() @ w.float() + bias
+    # bias + gelu (+ preact)
+    d = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    pre = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, d, M=M, N=N, K=K, bias=bias, preact=pre, epilogue=L.EPI_GELU)
+    gel = torch.nn.functional.gelu(pre_ref, approximate="tanh")
+    assert (pre.float() - pre_ref).abs().max().item() < 2e-2
+    assert (d.float() - gel).abs().max().item() < 2e-2
+    # exact gelu, fp32 out
+    d32 = torch.empty(M, N, device="cuda")
+    ops.gemm(a, w, d32, M=M, N=N, K=K, bias=bias, epilogue=L.EPI_GELU | L.EPI_EXACT)
+    assert (d32 - gel).abs().max().item() < 1e-4
+    # bias + residual, fp32 out, in place on the residual
+    out = res.clone()
+    ops.gemm(a, w, out, M=M, N=N, K=K, bias=bias, residual=out)
+    assert (out - (pre_ref + res)).abs().max().item() < 1e-4
+
+
+def test_gemm_dropout_epilogue(cuda_device):
+    from ergm_b200 import ops
+    M, N, K = 512, 768, 64
+    a = torch.ones(M, K, device="cuda").bfloat16()
+    w = torch.ones(K, N, device="cuda").bfloat16()
+    d = torch.empty(M, N, device="cuda")
+    ops.gemm(a, w, d, M=M, N=N, K=K, dropout_p=0.25, seed=1234, offset=7)
+    keep = (d != 0).float().mean().item()
+    assert abs(keep - 0.75) < 0.01
+    assert torch.allclose(d[d != 0], torch.full_like(d[d != 0], 64 / 0.75))
+    d2 = torch.empty(M, N, device="cuda")
+    ops.gemm(a, w, d2, M=M, N=N, K=K, dropout_p=0.25, seed=1234, offset=7)
+    assert torch.equal(d, d2)
+    ops.gemm(a, w, d2, M=M, N=N, K=K, dropout_p=0.25, seed=1234, offset=8)
+    assert not torch.equal(d, d2)
