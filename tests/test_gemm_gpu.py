@@ -16,7 +16,10 @@ def _run(M, N, K, a_mn, b_mn, block_n=0, out_dtype=torch.float32, split_k=1, ato
     from ergm_b200 import ops, _lib as L
     g = torch.Generator(device="cuda").manual_seed(seed)
     a = torch.randn((K, M) if a_mn else (M, K), device="cuda", generator=g).bfloat16()
-    b = torch.randn((K, N) if b_mn else (N, K), device="cuda", generator=g).bfloat16()
+    if b_mn:  # rows of a TMA operand must be 16-byte aligned: pad the leading dimension
+        b = torch.randn(K, (N + 7) // 8 * 8, device="cuda", generator=g).bfloat16()[:, :N]
+    else:
+        b = torch.randn(N, K, device="cuda", generator=g).bfloat16()
     ldd = (N + 7) // 8 * 8
     d = torch.zeros(M, ldd, device="cuda", dtype=out_dtype)
     ops.gemm(a, b, d, M=M, N=N, K=K, a_major=int(a_mn), b_major=int(b_mn), block_n=block_n,
