@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libergm_b200.so")
 
 ERGM_MAJOR_K, ERGM_MAJOR_MN = 0, 1
-EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_ATOMIC, EPI_DROPOUT, EPI_PREACT, EPI_EXACT = 1, 2, 4, 8, 16, 32, 64
+EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_ATOMIC, EPI_DROPOUT, EPI_PREACT, EPI_EXACT, EPI_GELU_GRAD = 1, 2, 4, 8, 16, 32, 64, 128
 DT_BF16, DT_F32 = 0, 1
 
 
@@ -47,11 +47,39 @@ def lib():
     return _lib
 
 
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "ergm_b200.h")
+
+_CTYPES = {"int": ctypes.c_int, "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64,
+           "uint64_t": ctypes.c_uint64, "float": ctypes.c_float}
+
+
+def header_prototypes(path=HEADER_PATH):
+    """Parses `int ergm_*(...)` prototypes out of include/ergm_b200.h ->
+    {name: [ctypes argtypes]} so the binding can never drift from the header."""
+    import re
+    src = open(path).read()
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\bint\s+(ergm_\w+)\s*\(([^)]*)\)\s*;", src):
+        name, args = m.group(1), m.group(2).strip()
+        types = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                if "*" in a:
+                    types.append(ctypes.c_void_p)
+                else:
+                    base = a.replace("const", "").split()[0]
+                    types.append(_CTYPES[base])
+        protos[name] = types
+    return protos
+
+
 def _declare(L):
-    L.ergm_abi_version.restype = ctypes.c_int
-    L.ergm_device_sm_count.restype = ctypes.c_int
-    L.ergm_gemm_bf16.restype = ctypes.c_int
-    L.ergm_gemm_bf16.argtypes = [ctypes.POINTER(GemmArgs), ctypes.c_void_p]
+    for name, argtypes in header_prototypes().items():
+        fn = getattr(L, name)  # AttributeError here = header declares a symbol the .so lacks
+        fn.restype = ctypes.c_int
+        fn.argtypes = argtypes
 
 
 def check(rc, what):

@@ -1,0 +1,506 @@
+// HBM-bound row kernels of the ERGM path: embedding + multimodal fusion (model.py:458-507),
+// LayerNorm forward / backward fused with the residual-gradient add (model.py:298,318,332,578),
+// column sums for bias gradients, dtype casts.  One warp owns one row; every global access is a
+// 16-byte vector, rows are contiguous so each warp request covers whole 512-byte spans.
+#include "../../include/ergm_b200.h"
+#include "common.cuh"
+#include "dropout.cuh"
+
+namespace ergm {
+
+constexpr int ROW_WARPS = 8;  // warps (rows in flight) per CTA
+
+// ------------------------------------------------------------------------------------------
+// embed_fuse_fwd:  h[b,t] = ((wte[id] (+img_b if t==0) (+aud_b if t==1)) + wpe[pos]) + wte[tt]
+// ------------------------------------------------------------------------------------------
+struct EmbedFwdParams {
+  const int64_t* ids;
+  const int64_t* tts;       // nullable
+  const int64_t* pos_ids;   // nullable, [T] (shared by the batch) when given
+  const float* wte;
+  const float* wpe;
+  const float* imgs;        // nullable, [B, ld_img]
+  const float* auds;        // nullable, [B, ld_aud]
+  float* out;               // [B*T, H]
+  int64_t ld_img, ld_aud;
+  int B, T, H, past_len, vocab, n_pos;
+  DropoutSite drop;
+  int do_drop;
+  int* err_flag;            // set to 1 on an out-of-range id (device-side assert replacement)
+};
+
+__global__ void __launch_bounds__(ROW_WARPS * 32) embed_fuse_fwd_kernel(const EmbedFwdParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows = p.B * p.T;
+  const float keep_scale = p.do_drop ? 1.f / (1.f - p.drop.p) : 1.f;
+  for (int row = blockIdx.x * ROW_WARPS + warp; row < rows; row += gridDim.x * ROW_WARPS) {
+    const int b = row / p.T, t = row - b * p.T;
+    const int64_t id = p.ids[row];
+    const int64_t tt = p.tts ? p.tts[row] : -1;
+    const int64_t pos = p.pos_ids ? p.pos_ids[t] : (int64_t)(p.past_len + t);
+    if (id < 0 || id >= p.vocab || pos < 0 || pos >= p.n_pos || (p.tts && (tt < 0 || tt >= p.vocab))) {
+      if (lane == 0) *p.err_flag = 1;
+      continue;
+    }
+    const float4* we = reinterpret_cast<const float4*>(p.wte + id * p.H);
+    const float4* wp = reinterpret_cast<const float4*>(p.wpe + pos * p.H);
+    const float4* wt = p.tts ? reinterpret_cast<const float4*>(p.wte + tt * p.H) : nullptr;
+    const float4* fz = nullptr;
+    if (p.imgs && t == 0) fz = reinterpret_cast<const float4*>(p.imgs + (int64_t)b * p.ld_img);
+    if (p.auds && t == 1) fz = reinterpret_cast<const float4*>(p.auds + (int64_t)b * p.ld_aud);
+    float4* o = reinterpret_cast<float4*>(p.out + (int64_t)row * p.H);
+    for (int c = lane; c < p.H / 4; c += 32) {
+      float4 e = __ldg(we + c);
+      if (fz) { const float4 f = __ldg(fz + c); e.x += f.x; e.y += f.y; e.z += f.z; e.w += f.w; }
+      const float4 q = __ldg(wp + c);
+      e.x += q.x; e.y += q.y; e.z += q.z; e.w += q.w;
+      if (wt) { const float4 s = __ldg(wt + c); e.x += s.x; e.y += s.y; e.z += s.z; e.w += s.w; }
+      if (p.do_drop) {
+        const uint32_t k = p.drop.keep4((uint32_t)row, (uint32_t)c);
+        e.x = (k & 1u) ? e.x * keep_scale : 0.f; e.y = (k & 2u) ? e.y * keep_scale : 0.f;
+        e.z = (k & 4u) ? e.z * keep_scale : 0.f; e.w = (k & 8u) ? e.w * keep_scale : 0.f;
+      }
+      o[c] = e;
+    }
+  }
+}
+
+// gather rows of an fp32 table into a bf16 matrix (caption embeddings, model.py:460-463)
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+gather_rows_bf16_kernel(const int64_t* ids, const float* table, __nv_bfloat16* out, int rows, int H,
+                        int vocab, int* err_flag) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int row = blockIdx.x * ROW_WARPS + warp; row < rows; row += gridDim.x * ROW_WARPS) {
+    const int64_t id = ids[row];
+    if (id < 0 || id >= vocab) { if (lane == 0) *err_flag = 1; continue; }
+    const float4* src = reinterpret_cast<const float4*>(table + id * H);
+    uint2* dst = reinterpret_cast<uint2*>(out + (int64_t)row * H);
+    for (int c = lane; c < H / 4; c += 32) {
+      const float4 e = __ldg(src + c);
+      dst[c] = make_uint2(pack_bf16x2(e.x, e.y), pack_bf16x2(e.z, e.w));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// embed_bwd: scatter-add of dh rows into dwte (by input id and by token-type id) and dwpe.
+// A CTA walks `rows_per_cta` consecutive rows; each thread owns 4 columns and keeps a running
+// sum per index stream, flushing with one red.add.v4 whenever the index changes (token-type
+// ids come in long runs, so their heavy contention collapses to one atomic per run).
+// ------------------------------------------------------------------------------------------
+struct EmbedBwdParams {
+  const float* dh;          // [rows, H]
+  const int64_t* ids;       // nullable
+  const int64_t* tts;       // nullable
+  const int64_t* pos_ids;   // nullable ([T]); positions used only when dwpe != null
+  float* dwte;
+  float* dwpe;              // nullable
+  float* dimgs;             // nullable [B, H]  (+= dh[b,0])
+  float* dauds;             // nullable [B, H]  (+= dh[b,1])
+  int rows, T, H, past_len, rows_per_cta;
+  DropoutSite drop;
+  int do_drop;
+};
+
+ERGM_DEVINL void red_add4(float* addr, const float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+__global__ void embed_bwd_kernel(const EmbedBwdParams p) {
+  const int c = threadIdx.x;  // float4 column
+  if (c >= p.H / 4) return;
+  const int r0 = blockIdx.x * p.rows_per_cta;
+  const int r1 = min(r0 + p.rows_per_cta, p.rows);
+  const float keep_scale = p.do_drop ? 1.f / (1.f - p.drop.p) : 1.f;
+  int64_t cur[3] = {-1, -1, -1};
+  float4 acc[3];
+#pragma unroll
+  for (int s = 0; s < 3; ++s) acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float* tables[3] = {p.ids ? p.dwte : nullptr, p.tts ? p.dwte : nullptr, p.dwpe};
+  for (int row = r0; row < r1; ++row) {
+    float4 g = __ldg(reinterpret_cast<const float4*>(p.dh + (int64_t)row * p.H) + c);
+    if (p.do_drop) {
+      const uint32_t k = p.drop.keep4((uint32_t)row, (uint32_t)c);
+      g.x = (k & 1u) ? g.x * keep_scale : 0.f; g.y = (k & 2u) ? g.y * keep_scale : 0.f;
+      g.z = (k & 4u) ? g.z * keep_scale : 0.f; g.w = (k & 8u) ? g.w * keep_scale : 0.f;
+    }
+    const int t = row % p.T;
+    int64_t idx[3];
+    idx[0] = p.ids ? p.ids[row] : -1;
+    idx[1] = p.tts ? p.tts[row] : -1;
+    idx[2] = p.dwpe ? (p.pos_ids ? p.pos_ids[t] : (int64_t)(p.past_len + t)) : -1;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      if (!tables[s]) continue;
+      if (idx[s] != cur[s]) {
+        if (cur[s] >= 0) red_add4(tables[s] + cur[s] * p.H + 4 * c, acc[s]);
+        cur[s] = idx[s];
+        acc[s] = g;
+      } else {
+        acc[s].x += g.x; acc[s].y += g.y; acc[s].z += g.z; acc[s].w += g.w;
+      }
+    }
+    if (p.dimgs && t == 0) red_add4(p.dimgs + (int64_t)(row / p.T) * p.H + 4 * c, g);
+    if (p.dauds && t == 1) red_add4(p.dauds + (int64_t)(row / p.T) * p.H + 4 * c, g);
+  }
+#pragma unroll
+  for (int s = 0; s < 3; ++s)
+    if (tables[s] && cur[s] >= 0) red_add4(tables[s] + cur[s] * p.H + 4 * c, acc[s]);
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm forward: y = (x - mean) * rstd * gamma + beta, biased variance, eps inside sqrt
+// ------------------------------------------------------------------------------------------
+template <int NV>  // NV = H / 128 float4 per lane
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+              const float* __restrict__ beta, __nv_bfloat16* __restrict__ y_bf16,
+              float* __restrict__ y_f32, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+              int rows, float eps) {
+  constexpr int H = NV * 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 g[NV], bt[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
+    bt[i] = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * i);
+  }
+  for (int row = blockIdx.x * ROW_WARPS + warp; row < rows; row += gridDim.x * ROW_WARPS) {
+    const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)row * H);
+    float4 v[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      v[i] = xr[lane + 32 * i];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) * (1.f / H);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      ss += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(ss) * (1.f / H) + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g[i].x + bt[i].x;
+      o.y = (v[i].y - mean) * rstd * g[i].y + bt[i].y;
+      o.z = (v[i].z - mean) * rstd * g[i].z + bt[i].z;
+      o.w = (v[i].w - mean) * rstd * g[i].w + bt[i].w;
+      if (y_bf16)
+        reinterpret_cast<uint2*>(y_bf16 + (int64_t)row * H)[lane + 32 * i] =
+            make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+      if (y_f32) reinterpret_cast<float4*>(y_f32 + (int64_t)row * H)[lane + 32 * i] = o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm backward fused with the residual-stream gradient:
+//   dx_out = dres_in + LN'(dy)           (fp32)
+//   dx_bf16 = bf16(dropmask(dx_out))     (operand of the next dgrad / wgrad GEMMs)
+//   dgamma += sum_rows dy * xhat, dbeta += sum_rows dy, dbias_next += sum_rows dx_bf16
+// ------------------------------------------------------------------------------------------
+struct LnBwdParams {
+  const void* dy;        // bf16 or fp32 [rows, H]
+  const float* x;
+  const float* mean;
+  const float* rstd;
+  const float* gamma;
+  const float* dres_in;  // nullable
+  float* dx_out;         // nullable (may alias dres_in)
+  __nv_bfloat16* dx_bf16;  // nullable
+  float* dgamma;
+  float* dbeta;
+  float* dbias_next;     // nullable, colsum of dx_bf16 (as rounded)
+  int rows;
+  int dy_f32;
+  DropoutSite drop;      // mask applied to the bf16 copy only
+  int do_drop;
+};
+
+template <int NV>
+__global__ void __launch_bounds__(ROW_WARPS * 32) ln_bwd_kernel(const LnBwdParams p) {
+  constexpr int H = NV * 128;
+  __shared__ float red[ROW_WARPS][H];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float keep_scale = p.do_drop ? 1.f / (1.f - p.drop.p) : 1.f;
+  float4 gm[NV], ag[NV], ab[NV], an[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    gm[i] = __ldg(reinterpret_cast<const float4*>(p.gamma) + lane + 32 * i);
+    ag[i] = ab[i] = an[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int row = blockIdx.x * ROW_WARPS + warp; row < p.rows; row += gridDim.x * ROW_WARPS) {
+    const float mean = p.mean[row], rstd = p.rstd[row];
+    float4 dy[NV], xh[NV];
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (p.dy_f32) {
+        dy[i] = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.dy) + (int64_t)row * H)[lane + 32 * i];
+      } else {
+        const uint2 u = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.dy) + (int64_t)row * H)[lane + 32 * i];
+        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+        dy[i] = make_float4(a.x, a.y, b.x, b.y);
+      }
+      const float4 xv = reinterpret_cast<const float4*>(p.x + (int64_t)row * H)[lane + 32 * i];
+      xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+      const float gx = dy[i].x * gm[i].x, gy = dy[i].y * gm[i].y, gz = dy[i].z * gm[i].z, gw = dy[i].w * gm[i].w;
+      c1 += (gx + gy) + (gz + gw);
+      c2 += (gx * xh[i].x + gy * xh[i].y) + (gz * xh[i].z + gw * xh[i].w);
+      ag[i].x += dy[i].x * xh[i].x; ag[i].y += dy[i].y * xh[i].y; ag[i].z += dy[i].z * xh[i].z; ag[i].w += dy[i].w * xh[i].w;
+      ab[i].x += dy[i].x; ab[i].y += dy[i].y; ab[i].z += dy[i].z; ab[i].w += dy[i].w;
+    }
+    c1 = warp_sum(c1) * (1.f / H);
+    c2 = warp_sum(c2) * (1.f / H);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float4 dx;
+      dx.x = rstd * (dy[i].x * gm[i].x - c1 - xh[i].x * c2);
+      dx.y = rstd * (dy[i].y * gm[i].y - c1 - xh[i].y * c2);
+      dx.z = rstd * (dy[i].z * gm[i].z - c1 - xh[i].z * c2);
+      dx.w = rstd * (dy[i].w * gm[i].w - c1 - xh[i].w * c2);
+      if (p.dres_in) {
+        const float4 r = reinterpret_cast<const float4*>(p.dres_in + (int64_t)row * H)[lane + 32 * i];
+        dx.x += r.x; dx.y += r.y; dx.z += r.z; dx.w += r.w;
+      }
+      if (p.dx_out) reinterpret_cast<float4*>(p.dx_out + (int64_t)row * H)[lane + 32 * i] = dx;
+      if (p.dx_bf16) {
+        if (p.do_drop) {
+          const uint32_t k = p.drop.keep4((uint32_t)row, (uint32_t)(lane + 32 * i));
+          dx.x = (k & 1u) ? dx.x * keep_scale : 0.f; dx.y = (k & 2u) ? dx.y * keep_scale : 0.f;
+          dx.z = (k & 4u) ? dx.z * keep_scale : 0.f; dx.w = (k & 8u) ? dx.w * keep_scale : 0.f;
+        }
+        const uint2 u = make_uint2(pack_bf16x2(dx.x, dx.y), pack_bf16x2(dx.z, dx.w));
+        reinterpret_cast<uint2*>(p.dx_bf16 + (int64_t)row * H)[lane + 32 * i] = u;
+        if (p.dbias_next) {
+          const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+          an[i].x += a.x; an[i].y += a.y; an[i].z += b.x; an[i].w += b.y;
+        }
+      }
+    }
+  }
+  // cross-warp reduction of the three column sums, one quantity at a time through smem
+  float* outs[3] = {p.dgamma, p.dbeta, p.dbias_next};
+#pragma unroll
+  for (int qn = 0; qn < 3; ++qn) {
+    if (!outs[qn]) continue;  // uniform
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 v = qn == 0 ? ag[i] : (qn == 1 ? ab[i] : an[i]);
+      reinterpret_cast<float4*>(&red[warp][0])[lane + 32 * i] = v;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < H; c += ROW_WARPS * 32) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < ROW_WARPS; ++w) s += red[w][c];
+      atomicAdd(outs[qn] + c, s);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// colsum: out[N] += sum_rows src[rows, N]  (bf16 source; bias gradients)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const __nv_bfloat16* __restrict__ src, int64_t ld, int rows, int N,
+                   float* __restrict__ out, int rows_per_cta) {
+  __shared__ float red[8][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col0 = blockIdx.x * 256 + lane * 8;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(r0 + rows_per_cta, rows);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col0 < N) {
+    for (int r = r0 + warp; r < r1; r += 8) {
+      const uint4 u = *reinterpret_cast<const uint4*>(src + (int64_t)r * ld + col0);
+      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+      acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = acc[i];
+  __syncthreads();
+  const int c = threadIdx.x;
+  if (blockIdx.x * 256 + c < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][c];
+    atomicAdd(out + blockIdx.x * 256 + c, s);
+  }
+}
+
+// cast fp32 [rows, N] (ld_src) -> bf16 [rows, N] (ld_dst), optional fused column sum of the
+// rounded values (used for dQ: fp32 atomic accumulator -> bf16 operand + bias gradient)
+__global__ void __launch_bounds__(256)
+cast_f32_bf16_2d_kernel(const float* __restrict__ src, int64_t ld_src, __nv_bfloat16* __restrict__ dst,
+                        int64_t ld_dst, int rows, int N, float* __restrict__ colsum, int rows_per_cta) {
+  __shared__ float red[8][128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col0 = blockIdx.x * 128 + lane * 4;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(r0 + rows_per_cta, rows);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col0 < N) {
+    for (int r = r0 + warp; r < r1; r += 8) {
+      const float4 v = *reinterpret_cast<const float4*>(src + (int64_t)r * ld_src + col0);
+      const uint2 u = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+      *reinterpret_cast<uint2*>(dst + (int64_t)r * ld_dst + col0) = u;
+      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+      acc.x += a.x; acc.y += a.y; acc.z += b.x; acc.w += b.y;
+    }
+  }
+  if (!colsum) return;
+  reinterpret_cast<float4*>(&red[warp][0])[lane] = acc;
+  __syncthreads();
+  const int c = threadIdx.x;
+  if (c < 128 && blockIdx.x * 128 + c < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][c];
+    atomicAdd(colsum + blockIdx.x * 128 + c, s);
+  }
+}
+
+// flat fp32 -> bf16 cast (weight shadow refresh)
+__global__ void __launch_bounds__(256)
+cast_f32_bf16_flat_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    reinterpret_cast<uint2*>(dst)[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
+template <typename F>
+static int dispatch_nv(int H, F&& f) {
+  switch (H / 128) {
+    case 1: return f(std::integral_constant<int, 1>{});
+    case 2: return f(std::integral_constant<int, 2>{});
+    case 3: return f(std::integral_constant<int, 3>{});
+    case 4: return f(std::integral_constant<int, 4>{});
+    case 6: return f(std::integral_constant<int, 6>{});
+    case 8: return f(std::integral_constant<int, 8>{});
+    case 10: return f(std::integral_constant<int, 10>{});
+    default: return ERGM_ERR_UNSUPPORTED;
+  }
+}
+
+static int row_grid(int rows) {
+  const int need = (rows + ROW_WARPS - 1) / ROW_WARPS;
+  const int cap = num_sms() * 8;
+  return need < cap ? (need > 0 ? need : 1) : cap;
+}
+
+}  // namespace ergm
+
+using namespace ergm;
+
+extern "C" int ergm_embed_fuse_fwd(const int64_t* ids, const int64_t* token_type_ids,
+                                   const int64_t* position_ids, const float* wte, const float* wpe,
+                                   const float* imgs, int64_t ld_img, const float* auds,
+                                   int64_t ld_aud, float* out, int B, int T, int H, int past_len,
+                                   int vocab, int n_pos, float dropout_p, uint64_t seed,
+                                   uint64_t offset, int* err_flag, void* stream) {
+  if (!ids || !wte || !wpe || !out || !err_flag || B <= 0 || T <= 0 || H % 128) return ERGM_ERR_ARG;
+  if ((imgs && ld_img % 4) || (auds && ld_aud % 4)) return ERGM_ERR_ARG;
+  EmbedFwdParams p{ids, token_type_ids, position_ids, wte, wpe, imgs, auds, out, ld_img, ld_aud,
+                   B, T, H, past_len, vocab, n_pos,
+                   DropoutSite{seed, offset, dropout_p, (uint32_t)(H / 4)}, dropout_p > 0.f, err_flag};
+  embed_fuse_fwd_kernel<<<row_grid(B * T), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int ergm_gather_rows_bf16(const int64_t* ids, const float* table, void* out_bf16,
+                                     int rows, int H, int vocab, int* err_flag, void* stream) {
+  if (!ids || !table || !out_bf16 || !err_flag || rows <= 0 || H % 128) return ERGM_ERR_ARG;
+  gather_rows_bf16_kernel<<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      ids, table, reinterpret_cast<__nv_bfloat16*>(out_bf16), rows, H, vocab, err_flag);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int ergm_embed_bwd(const float* dh, const int64_t* ids, const int64_t* token_type_ids,
+                              const int64_t* position_ids, float* dwte, float* dwpe, float* dimgs,
+                              float* dauds, int rows, int T, int H, int past_len, float dropout_p,
+                              uint64_t seed, uint64_t offset, void* stream) {
+  if (!dh || rows <= 0 || T <= 0 || H % 128 || H / 4 > 1024) return ERGM_ERR_ARG;
+  if ((ids || token_type_ids) && !dwte) return ERGM_ERR_ARG;
+  EmbedBwdParams p{dh, ids, token_type_ids, position_ids, dwte, dwpe, dimgs, dauds, rows, T, H,
+                   past_len, 32, DropoutSite{seed, offset, dropout_p, (uint32_t)(H / 4)},
+                   dropout_p > 0.f};
+  const int threads = ((H / 4 + 31) / 32) * 32;
+  embed_bwd_kernel<<<(rows + 31) / 32, threads, 0, (cudaStream_t)stream>>>(p);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int ergm_ln_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16,
+                           float* y_f32, float* mean, float* rstd, int rows, int H, float eps,
+                           void* stream) {
+  if (!x || !gamma || !beta || rows <= 0 || H % 128) return ERGM_ERR_ARG;
+  return dispatch_nv(H, [&](auto nv) {
+    ln_fwd_kernel<decltype(nv)::value><<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd, rows, eps);
+    return (int)cudaGetLastError();
+  });
+}
+
+extern "C" int ergm_ln_bwd(const void* dy, int dy_is_f32, const float* x, const float* mean,
+                           const float* rstd, const float* gamma, const float* dres_in,
+                           float* dx_out, void* dx_bf16, float* dgamma, float* dbeta,
+                           float* dbias_next, int rows, int H, float dropout_p, uint64_t seed,
+                           uint64_t offset, void* stream) {
+  if (!dy || !x || !mean || !rstd || !gamma || !dgamma || !dbeta || rows <= 0 || H % 128)
+    return ERGM_ERR_ARG;
+  LnBwdParams p{dy, x, mean, rstd, gamma, dres_in, dx_out, reinterpret_cast<__nv_bfloat16*>(dx_bf16),
+                dgamma, dbeta, dbias_next, rows, dy_is_f32,
+                DropoutSite{seed, offset, dropout_p, (uint32_t)(H / 4)}, dropout_p > 0.f};
+  return dispatch_nv(H, [&](auto nv) {
+    const int need = (rows + ROW_WARPS - 1) / ROW_WARPS;
+    const int grid = need < 2 * num_sms() ? need : 2 * num_sms();
+    ln_bwd_kernel<decltype(nv)::value><<<grid, ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
+    return (int)cudaGetLastError();
+  });
+}
+
+extern "C" int ergm_colsum_bf16(const void* src, int64_t ld, int rows, int N, float* out,
+                                void* stream) {
+  if (!src || !out || rows <= 0 || N <= 0 || N % 8 || ld % 8) return ERGM_ERR_ARG;
+  const int col_ctas = (N + 255) / 256;
+  int row_splits = (2 * num_sms() + col_ctas - 1) / col_ctas;
+  if (row_splits > (rows + 63) / 64) row_splits = (rows + 63) / 64;
+  const int rpc = (rows + row_splits - 1) / row_splits;
+  colsum_bf16_kernel<<<dim3(col_ctas, (rows + rpc - 1) / rpc), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), ld, rows, N, out, rpc);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int ergm_cast_f32_bf16_2d(const float* src, int64_t ld_src, void* dst, int64_t ld_dst,
+                                     int rows, int N, float* colsum, void* stream) {
+  if (!src || !dst || rows <= 0 || N <= 0 || N % 4 || ld_src % 4 || ld_dst % 4) return ERGM_ERR_ARG;
+  const int col_ctas = (N + 127) / 128;
+  int row_splits = (2 * num_sms() + col_ctas - 1) / col_ctas;
+  if (row_splits > (rows + 63) / 64) row_splits = (rows + 63) / 64;
+  const int rpc = (rows + row_splits - 1) / row_splits;
+  cast_f32_bf16_2d_kernel<<<dim3(col_ctas, (rows + rpc - 1) / rpc), 256, 0, (cudaStream_t)stream>>>(
+      src, ld_src, reinterpret_cast<__nv_bfloat16*>(dst), ld_dst, rows, N, colsum, rpc);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int ergm_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  if (!src || !dst || n <= 0 || n % 4) return ERGM_ERR_ARG;
+  const int64_t n4 = n / 4;
+  int64_t blocks = (n4 + 255) / 256;
+  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+  cast_f32_bf16_flat_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+      src, reinterpret_cast<__nv_bfloat16*>(dst), n4);
+  return (int)cudaGetLastError();
+}

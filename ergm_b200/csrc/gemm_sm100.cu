@@ -184,6 +184,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const bool do_drop = (p.epi & ERGM_EPI_DROPOUT) != 0;
     const bool do_pre = (p.epi & ERGM_EPI_PREACT) != 0;
     const bool exact = (p.epi & ERGM_EPI_EXACT) != 0;
+    const bool do_gelu_grad = (p.epi & ERGM_EPI_GELU_GRAD) != 0;
     const float keep_scale = do_drop ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
     const DropoutSite site{p.seed, p.offset, p.dropout_p, (uint32_t)((p.N + 3) >> 2)};
     int acc = 0;
@@ -236,6 +237,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
               for (int i = 0; i < 32; ++i)
                 if (col0 + i < p.N) pp[i] = __float2bfloat16_rn(v[i]);
+            }
+          }
+          if (do_gelu_grad) {
+            // v *= gelu_new'(u), u = saved pre-activation (bf16 [M, ldd]) -> dU of model.py:264
+            const __nv_bfloat16* up =
+                reinterpret_cast<const __nv_bfloat16*>(p.preact) + (int64_t)row * p.ldd + col0;
+            if (full) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                const uint4 u4 = *reinterpret_cast<const uint4*>(up + i);
+                const uint32_t uu[4] = {u4.x, u4.y, u4.z, u4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = unpack_bf16x2(uu[j]);
+                  v[i + 2 * j] *= exact ? gelu_new_grad<true>(f.x) : gelu_new_grad<false>(f.x);
+                  v[i + 2 * j + 1] *= exact ? gelu_new_grad<true>(f.y) : gelu_new_grad<false>(f.y);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.N) v[i] *= gelu_new_grad<true>(__bfloat162float(up[i]));
             }
           }
           if (do_gelu) {
@@ -377,7 +400,9 @@ extern "C" int ergm_gemm_bf16(const ergm_gemm_args* a, void* stream) {
   if (a->M <= 0 || a->N <= 0 || a->K <= 0) return ERGM_ERR_ARG;
   if ((a->epilogue & ERGM_EPI_BIAS) && !a->bias) return ERGM_ERR_ARG;
   if ((a->epilogue & ERGM_EPI_RESIDUAL) && !a->residual) return ERGM_ERR_ARG;
-  if ((a->epilogue & ERGM_EPI_PREACT) && !a->preact) return ERGM_ERR_ARG;
+  if ((a->epilogue & (ERGM_EPI_PREACT | ERGM_EPI_GELU_GRAD)) && !a->preact) return ERGM_ERR_ARG;
+  if ((a->epilogue & ERGM_EPI_PREACT) && (a->epilogue & ERGM_EPI_GELU_GRAD)) return ERGM_ERR_ARG;
+  if ((a->epilogue & ERGM_EPI_GELU_GRAD) && a->d_dtype != ERGM_DT_BF16) return ERGM_ERR_ARG;
   if ((a->epilogue & ERGM_EPI_ATOMIC) && a->d_dtype != ERGM_DT_F32) return ERGM_ERR_ARG;
   if (a->split_k > 1 && !(a->epilogue & ERGM_EPI_ATOMIC)) return ERGM_ERR_ARG;
   if ((a->epilogue & ERGM_EPI_DROPOUT) && !(a->dropout_p >= 0.f && a->dropout_p < 1.f))

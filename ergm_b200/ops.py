@@ -49,3 +49,127 @@ def gemm(a, b, d, *, M, N, K, a_major=L.ERGM_MAJOR_K, b_major=L.ERGM_MAJOR_MN, l
     args.dropout_p = dropout_p
     args.seed, args.offset = seed, offset
     L.check(L.lib().ergm_gemm_bf16(ctypes.byref(args), _stream()), "ergm_gemm_bf16")
+
+
+def _call(name, *args):
+    fn = getattr(L.lib(), name)
+    L.check(fn(*args, torch.cuda.current_stream().cuda_stream), name)
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+_err_flags = {}
+
+
+def err_flag(device):
+    """Per-device int32 flag the kernels raise on out-of-range indices (checked lazily)."""
+    key = (device.type, device.index)
+    if key not in _err_flags:
+        _err_flags[key] = torch.zeros(1, dtype=torch.int32, device=device)
+    return _err_flags[key]
+
+
+def check_err_flag(device):
+    f = err_flag(device)
+    if int(f.item()) != 0:
+        f.zero_()
+        raise IndexError("ergm_b200: index out of range in input_ids / token_type_ids / labels")
+
+
+def embed_fuse_fwd(ids, tts, pos_ids, wte, wpe, imgs, auds, out, *, past_len=0, dropout_p=0.0, seed=0, offset=0):
+    B, T = ids.shape
+    H = wte.shape[1]
+    _call("ergm_embed_fuse_fwd", ids.data_ptr(), _p(tts), _p(pos_ids), wte.data_ptr(), wpe.data_ptr(),
+          _p(imgs), imgs.stride(0) if imgs is not None else 0, _p(auds), auds.stride(0) if auds is not None else 0,
+          out.data_ptr(), B, T, H, past_len, wte.shape[0], wpe.shape[0], dropout_p, seed, offset,
+          err_flag(ids.device).data_ptr())
+
+
+def gather_rows_bf16(ids, table, out):
+    _call("ergm_gather_rows_bf16", ids.data_ptr(), table.data_ptr(), out.data_ptr(), ids.numel(), table.shape[1],
+          table.shape[0], err_flag(ids.device).data_ptr())
+
+
+def embed_bwd(dh, ids, tts, pos_ids, dwte, dwpe, *, T, past_len=0, dimgs=None, dauds=None, dropout_p=0.0, seed=0, offset=0):
+    rows, H = dh.shape
+    _call("ergm_embed_bwd", dh.data_ptr(), _p(ids), _p(tts), _p(pos_ids), _p(dwte), _p(dwpe), _p(dimgs), _p(dauds),
+          rows, T, H, past_len, dropout_p, seed, offset)
+
+
+def ln_fwd(x, gamma, beta, y_bf16, y_f32, mean, rstd, eps):
+    rows, H = x.shape
+    _call("ergm_ln_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _p(y_bf16), _p(y_f32), _p(mean), _p(rstd),
+          rows, H, eps)
+
+
+def ln_bwd(dy, x, mean, rstd, gamma, dres_in, dx_out, dx_bf16, dgamma, dbeta, dbias_next=None, *, dropout_p=0.0,
+           seed=0, offset=0):
+    rows, H = x.shape
+    _call("ergm_ln_bwd", dy.data_ptr(), int(dy.dtype == torch.float32), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+          gamma.data_ptr(), _p(dres_in), _p(dx_out), _p(dx_bf16), dgamma.data_ptr(), dbeta.data_ptr(), _p(dbias_next),
+          rows, H, dropout_p, seed, offset)
+
+
+def colsum_bf16(src, out, *, rows=None, N=None, ld=None):
+    rows = src.shape[0] if rows is None else rows
+    N = src.shape[1] if N is None else N
+    _call("ergm_colsum_bf16", src.data_ptr(), src.stride(0) if ld is None else ld, rows, N, out.data_ptr())
+
+
+def cast_f32_bf16_2d(src, dst, colsum=None):
+    rows, N = src.shape
+    _call("ergm_cast_f32_bf16_2d", src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), rows, N, _p(colsum))
+
+
+def cast_f32_bf16(src, dst):
+    _call("ergm_cast_f32_bf16", src.data_ptr(), dst.data_ptr(), src.numel())
+
+
+def attn_fwd(q, k, v, out, lse, *, B, nh, Tq, Tk, q_col0=0, k_col0=0, v_col0=0, causal=True, causal_off=None,
+             kv_lens=None, dropout_p=0.0, seed=0, offset=0):
+    """q/k/v: bf16 2-D matrices [B*T, ld] (may be the same tensor with different col0)."""
+    if causal_off is None:
+        causal_off = Tk - Tq
+    _call("ergm_attn_fwd", q.data_ptr(), q.stride(0), q_col0, k.data_ptr(), k.stride(0), k_col0, v.data_ptr(),
+          v.stride(0), v_col0, out.data_ptr(), out.stride(0), _p(lse), _p(kv_lens), B, nh, Tq, Tk, 64, int(causal),
+          causal_off, dropout_p, seed, offset)
+
+
+def ce_fwd(logits, labels, lse, row_loss, sums, *, T, V):
+    rows = logits.shape[0]
+    _call("ergm_ce_fwd", logits.data_ptr(), int(logits.dtype == torch.float32), logits.stride(0), labels.data_ptr(),
+          rows, T, V, lse.data_ptr(), row_loss.data_ptr(), sums.data_ptr(), err_flag(logits.device).data_ptr())
+
+
+def ce_bwd(logits, labels, lse, scale, dlogits, *, T, V):
+    rows = logits.shape[0]
+    _call("ergm_ce_bwd", logits.data_ptr(), int(logits.dtype == torch.float32), logits.stride(0), labels.data_ptr(),
+          rows, T, V, lse.data_ptr(), scale.data_ptr(), dlogits.data_ptr(), dlogits.stride(0))
+
+
+def emotion_head_fwd(x_final, mean, rstd, gamma, beta, w_emo, emo_labels, hlast, logits, dlogits, sums, *, B, T):
+    H = x_final.shape[1]
+    _call("ergm_emotion_head_fwd", x_final.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+          beta.data_ptr(), w_emo.data_ptr(), _p(emo_labels), B, T, H, hlast.data_ptr(), logits.data_ptr(),
+          _p(dlogits), _p(sums), err_flag(x_final.device).data_ptr())
+
+
+def emotion_head_bwd(dlogits, hlast, w_emo, scale, dw_emo, dyf, *, B, T):
+    H = hlast.shape[1]
+    _call("ergm_emotion_head_bwd", dlogits.data_ptr(), hlast.data_ptr(), w_emo.data_ptr(), scale.data_ptr(), B, T, H,
+          _p(dw_emo), _p(dyf))
+
+
+def loss_finalize(sums, has_lm, has_emo, out):
+    _call("ergm_loss_finalize", sums.data_ptr(), int(has_lm), int(has_emo), out.data_ptr())
+
+
+def scalar_mul(a, b, dst):
+    _call("ergm_scalar_mul", a.data_ptr(), b.data_ptr(), dst.data_ptr())
+
+
+def adamw_flat(p, g, m, v, shadow, hyper, grad_scale=None):
+    _call("ergm_adamw_flat", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _p(shadow), p.numel(),
+          hyper.data_ptr(), _p(grad_scale))

@@ -48,7 +48,9 @@ enum {
   ERGM_EPI_ATOMIC = 8,     /* D += result via red.add.f32 (wgrad accumulate)    */
   ERGM_EPI_DROPOUT = 16,   /* inverted dropout on (acc+bias) before residual    */
   ERGM_EPI_PREACT = 32,    /* also store (acc+bias) before GELU to `preact`     */
-  ERGM_EPI_EXACT = 64      /* exact tanhf instead of tanh.approx in GELU        */
+  ERGM_EPI_EXACT = 64,     /* exact tanhf instead of tanh.approx in GELU        */
+  ERGM_EPI_GELU_GRAD = 128 /* result *= gelu_new'(preact[M,ldd]) (bf16 D only; MLP
+                              backward of model.py:264; `preact` is an INPUT)   */
 };
 enum { ERGM_DT_BF16 = 0, ERGM_DT_F32 = 1 };
 
@@ -71,6 +73,92 @@ typedef struct ergm_gemm_args {
 } ergm_gemm_args;
 
 int ergm_gemm_bf16(const ergm_gemm_args* args, void* stream);
+
+
+/* ------------------------------------------------------------------------ */
+/* Embedding + multimodal fusion (model.py:458-507):                          */
+/*   h[b,t] = ((wte[id] (+imgs[b] if t==0) (+auds[b] if t==1)) + wpe[pos]) + wte[type]
+ * then embd dropout.  pos = past_len + t unless position_ids[T] is given.   */
+/* imgs / auds: fp32 [B, ld] (the pooled vectors model.py:497-498 adds) or    */
+/* NULL.  err_flag (device int) is set to 1 on an out-of-range index.         */
+int ergm_embed_fuse_fwd(const int64_t* ids, const int64_t* token_type_ids,
+                        const int64_t* position_ids, const float* wte, const float* wpe,
+                        const float* imgs, int64_t ld_img, const float* auds, int64_t ld_aud,
+                        float* out, int B, int T, int H, int past_len, int vocab, int n_pos,
+                        float dropout_p, uint64_t seed, uint64_t offset, int* err_flag,
+                        void* stream);
+/* caption embeddings enc = wte[caption_ids] (model.py:460-463), bf16 output  */
+int ergm_gather_rows_bf16(const int64_t* ids, const float* table, void* out_bf16, int rows,
+                          int H, int vocab, int* err_flag, void* stream);
+/* backward of the embedding stage: scatter-add dh rows into dwte (by id and  */
+/* by token type), dwpe, and optionally the fused-feature gradients.          */
+int ergm_embed_bwd(const float* dh, const int64_t* ids, const int64_t* token_type_ids,
+                   const int64_t* position_ids, float* dwte, float* dwpe, float* dimgs,
+                   float* dauds, int rows, int T, int H, int past_len, float dropout_p,
+                   uint64_t seed, uint64_t offset, void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* LayerNorm (model.py:298,318,332,578; eps inside the sqrt, biased variance) */
+/* fwd writes bf16 and/or fp32 outputs and the row statistics.                */
+int ergm_ln_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16,
+                float* y_f32, float* mean, float* rstd, int rows, int H, float eps,
+                void* stream);
+/* bwd fused with the residual-gradient add: dx_out = dres_in + LN'(dy);      */
+/* dx_bf16 = bf16(dropout_mask(dx_out)) feeds the next dgrad/wgrad GEMMs;     */
+/* dgamma/dbeta/dbias_next are accumulated (+=).                              */
+int ergm_ln_bwd(const void* dy, int dy_is_f32, const float* x, const float* mean,
+                const float* rstd, const float* gamma, const float* dres_in, float* dx_out,
+                void* dx_bf16, float* dgamma, float* dbeta, float* dbias_next, int rows, int H,
+                float dropout_p, uint64_t seed, uint64_t offset, void* stream);
+/* out[N] += column sums of a bf16 [rows, N] matrix (Conv1D bias gradients)   */
+int ergm_colsum_bf16(const void* src, int64_t ld, int rows, int N, float* out, void* stream);
+int ergm_cast_f32_bf16_2d(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int rows,
+                          int N, float* colsum, void* stream);
+int ergm_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* Fused attention, head_dim 64 (GPT2Attention._attn, model.py:119-148, and   */
+/* the head split / merge permutes :190-198).  q/k/v are bf16 matrices        */
+/* [B*T, ld] whose head h occupies columns [col0 + 64h, col0 + 64h + 64);     */
+/* out is [B*Tq, ld_out] merged heads; lse is [B, nh, Tq] (natural log).      */
+/* causal: query i sees key j iff j <= i + causal_off (self-attention);       */
+/* kv_lens (nullable, int32 [B]) masks right-padded keys.                     */
+int ergm_attn_fwd(const void* q, int64_t ld_q, int q_col0, const void* k, int64_t ld_k,
+                  int k_col0, const void* v, int64_t ld_v, int v_col0, void* out, int64_t ld_out,
+                  float* lse, const int* kv_lens, int B, int nh, int Tq, int Tk, int head_dim,
+                  int causal, int causal_off, float dropout_p, uint64_t seed, uint64_t offset,
+                  void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* Token cross-entropy over LM-head logits with the reference's shift and     */
+/* ignore_index=-100 (model.py:705-708): row (b,t) is scored against          */
+/* labels[b,t+1].  sums[0] += sum of row losses, sums[1] += valid rows.       */
+int ergm_ce_fwd(const void* logits, int logits_is_f32, int64_t ldl, const int64_t* labels,
+                int rows, int T, int V, float* lse, float* row_loss, float* sums, int* err_flag,
+                void* stream);
+/* dlogits = (softmax - onehot) * (*scale_ptr), zero for ignored rows (bf16)   */
+int ergm_ce_bwd(const void* logits, int logits_is_f32, int64_t ldl, const int64_t* labels,
+                int rows, int T, int V, const float* lse, const float* scale_ptr,
+                void* dlogits_bf16, int64_t ldd, void* stream);
+/* Emotion head on the last position + 7-way CE (model.py:700-701,710-711).   */
+/* sums[2] += sum of sample losses, sums[3] += samples.                       */
+int ergm_emotion_head_fwd(const float* x_final, const float* mean, const float* rstd,
+                          const float* gamma, const float* beta, const float* w_emo,
+                          const int64_t* emotion_labels, int B, int T, int H, float* hlast,
+                          float* logits, float* dlogits, float* sums, int* err_flag, void* stream);
+int ergm_emotion_head_bwd(const float* dlogits, const float* hlast, const float* w_emo,
+                          const float* scale_ptr, int B, int T, int H, float* dw_emo, float* dyf,
+                          void* stream);
+/* out = [loss, lm_loss, emo_loss, 1/lm_valid, 1/emo_count] (model.py:713)    */
+int ergm_loss_finalize(const float* sums, int has_lm, int has_emotion, float* out, void* stream);
+int ergm_scalar_mul(const float* a, const float* b, float* dst, void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* Flat AdamW, torch.optim.AdamW arithmetic (main.py:68,155).  hyper (device) */
+/* = [lr, beta1, beta2, eps, weight_decay, 1-beta1^t, 1-beta2^t]; also writes */
+/* the bf16 weight shadow consumed by the GEMMs.                              */
+int ergm_adamw_flat(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n,
+                    const float* hyper, const float* grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

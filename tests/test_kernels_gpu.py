@@ -1,0 +1,281 @@
+"""GPU unit parity of the row / loss / attention kernels against plain fp32 PyTorch
+restatements of the cited model.py lines (kernel-level oracle; the model-level oracle is
+oracle/ergm_oracle.py, see tests/test_model_gpu.py)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _g(seed=0):
+    return torch.Generator(device="cuda").manual_seed(seed)
+
+
+@pytest.mark.parametrize("H", [128, 768, 1024])
+def test_ln_fwd_bwd(cuda_device, H):
+    from ergm_b200 import ops
+    rows = 333
+    g = _g(1)
+    x = torch.randn(rows, H, device="cuda", generator=g) * 2 + 0.5
+    gamma = 1 + 0.1 * torch.randn(H, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(H, device="cuda", generator=g)
+    yb = torch.empty(rows, H, device="cuda", dtype=torch.bfloat16)
+    y32 = torch.empty(rows, H, device="cuda")
+    mean = torch.empty(rows, device="cuda")
+    rstd = torch.empty(rows, device="cuda")
+    ops.ln_fwd(x, gamma, beta, yb, y32, mean, rstd, 1e-5)
+    ref = F.layer_norm(x, (H,), gamma, beta, 1e-5)
+    assert (y32 - ref).abs().max().item() < 2e-5
+    assert (yb.float() - ref).abs().max().item() < 3e-2
+    # backward
+    dy = torch.randn(rows, H, device="cuda", generator=g)
+    dres = torch.randn(rows, H, device="cuda", generator=g)
+    xr = x.clone().requires_grad_(True)
+    gr = gamma.clone().requires_grad_(True)
+    br = beta.clone().requires_grad_(True)
+    F.layer_norm(xr, (H,), gr, br, 1e-5).backward(dy)
+    for dyt in (dy, dy.bfloat16()):
+        dyf = dyt.float()
+        xr.grad = gr.grad = br.grad = None
+        F.layer_norm(xr, (H,), gr, br, 1e-5).backward(dyf)
+        dx = torch.empty(rows, H, device="cuda")
+        dxb = torch.empty(rows, H, device="cuda", dtype=torch.bfloat16)
+        dgam = torch.zeros(H, device="cuda")
+        dbet = torch.zeros(H, device="cuda")
+        dbn = torch.zeros(H, device="cuda")
+        ops.ln_bwd(dyt, x, mean, rstd, gamma, dres, dx, dxb, dgam, dbet, dbn)
+        assert (dx - (xr.grad + dres)).abs().max().item() < 1e-4
+        assert (dgam - gr.grad).abs().max().item() < 2e-3
+        assert (dbet - br.grad).abs().max().item() < 2e-3
+        assert (dbn - dxb.float().sum(0)).abs().max().item() < 2e-3
+        assert (dxb.float() - dx).abs().max().item() < 5e-2
+
+
+def test_embed_fwd_bwd(cuda_device):
+    from ergm_b200 import ops
+    B, T, H, V, P = 3, 40, 128, 1024, 256
+    g = _g(2)
+    wte = torch.randn(V, H, device="cuda", generator=g)
+    wpe = torch.randn(P, H, device="cuda", generator=g)
+    ids = torch.randint(0, V, (B, T), device="cuda", generator=g)
+    tts = torch.randint(V - 2, V, (B, 1), device="cuda", generator=g).expand(B, T).contiguous()
+    imgs = torch.randn(B, 1, H, device="cuda", generator=g)
+    auds = torch.randn(B, H, device="cuda", generator=g)
+    out = torch.empty(B * T, H, device="cuda")
+    ops.embed_fuse_fwd(ids, tts, None, wte, wpe, imgs[:, 0], auds, out, past_len=5)
+    e = wte[ids].clone()
+    e[:, 0] = e[:, 0] + imgs[:, 0]
+    e[:, 1] = e[:, 1] + auds
+    ref = e + wpe[torch.arange(5, 5 + T, device="cuda")][None] + wte[tts]
+    assert torch.equal(out.view(B, T, H), ref)  # same fp32 adds in the same order
+    enc = torch.empty(B * T, H, device="cuda", dtype=torch.bfloat16)
+    ops.gather_rows_bf16(ids, wte, enc)
+    assert torch.equal(enc.view(B, T, H), wte[ids].bfloat16())
+    ops.check_err_flag(ids.device)
+    # backward
+    dh = torch.randn(B * T, H, device="cuda", generator=g)
+    dwte = torch.zeros_like(wte)
+    dwpe = torch.zeros_like(wpe)
+    dimg = torch.zeros(B, H, device="cuda")
+    daud = torch.zeros(B, H, device="cuda")
+    ops.embed_bwd(dh, ids, tts, None, dwte, dwpe, T=T, past_len=5, dimgs=dimg, dauds=daud)
+    rw = torch.zeros_like(wte)
+    rw.index_add_(0, ids.view(-1), dh)
+    rw.index_add_(0, tts.view(-1), dh)
+    rp = torch.zeros_like(wpe)
+    rp.index_add_(0, torch.arange(5, 5 + T, device="cuda").repeat(B), dh)
+    assert (dwte - rw).abs().max().item() < 1e-4
+    assert (dwpe - rp).abs().max().item() < 1e-4
+    assert torch.allclose(dimg, dh.view(B, T, H)[:, 0]) and torch.allclose(daud, dh.view(B, T, H)[:, 1])
+    # out-of-range id raises
+    bad = ids.clone()
+    bad[0, 0] = V
+    ops.embed_fuse_fwd(bad, tts, None, wte, wpe, None, None, out)
+    with pytest.raises(IndexError):
+        ops.check_err_flag(ids.device)
+
+
+def test_embed_dropout_consistency(cuda_device):
+    from ergm_b200 import ops
+    B, T, H, V = 2, 64, 256, 512
+    g = _g(3)
+    wte = torch.ones(V, H, device="cuda")
+    wpe = torch.zeros(T, H, device="cuda")
+    ids = torch.randint(0, V, (B, T), device="cuda", generator=g)
+    out = torch.empty(B * T, H, device="cuda")
+    ops.embed_fuse_fwd(ids, None, None, wte, wpe, None, None, out, dropout_p=0.1, seed=5, offset=9)
+    keep = out != 0
+    assert abs(keep.float().mean().item() - 0.9) < 0.02
+    dh = torch.ones(B * T, H, device="cuda")
+    dwpe = torch.zeros(T, H, device="cuda")
+    dwte = torch.zeros(V, H, device="cuda")
+    ops.embed_bwd(dh, ids, None, None, dwte, dwpe, T=T, dropout_p=0.1, seed=5, offset=9)
+    ref = (keep.float() / 0.9).view(B, T, H).sum(0)
+    assert torch.allclose(dwpe, ref, atol=1e-5)
+
+
+def test_colsum_and_casts(cuda_device):
+    from ergm_b200 import ops
+    g = _g(4)
+    src = torch.randn(1000, 2304, device="cuda", generator=g).bfloat16()
+    out = torch.zeros(2304, device="cuda")
+    ops.colsum_bf16(src, out)
+    assert (out - src.float().sum(0)).abs().max().item() < 1e-2
+    s32 = torch.randn(777, 768, device="cuda", generator=g)
+    dst = torch.zeros(777, 2304, device="cuda", dtype=torch.bfloat16)
+    cs = torch.zeros(768, device="cuda")
+    ops.cast_f32_bf16_2d(s32, dst[:, 768:1536], cs)
+    assert torch.equal(dst[:, 768:1536], s32.bfloat16()) and dst[:, :768].abs().max().item() == 0
+    assert (cs - s32.bfloat16().float().sum(0)).abs().max().item() < 1e-2
+    flat = torch.randn(4096 * 3, device="cuda", generator=g)
+    fb = torch.empty(4096 * 3, device="cuda", dtype=torch.bfloat16)
+    ops.cast_f32_bf16(flat, fb)
+    assert torch.equal(fb, flat.bfloat16())
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_ce_fwd_bwd(cuda_device, dtype):
+    from ergm_b200 import ops
+    B, T, V = 3, 17, 50260
+    ld = 50304
+    g = _g(5)
+    logits = torch.zeros(B * T, ld, device="cuda", dtype=dtype)
+    logits[:, :V] = (torch.randn(B * T, V, device="cuda", generator=g) * 2).to(dtype)
+    labels = torch.randint(0, V, (B, T), device="cuda", generator=g)
+    labels[:, :6] = -100
+    labels[1, 9] = -100
+    lse = torch.empty(B * T, device="cuda")
+    rl = torch.empty(B * T, device="cuda")
+    sums = torch.zeros(4, device="cuda")
+    ops.ce_fwd(logits, labels, lse, rl, sums, T=T, V=V)
+    lf = logits[:, :V].float().view(B, T, V)
+    ref = F.cross_entropy(lf[:, :-1].reshape(-1, V), labels[:, 1:].reshape(-1), reduction="sum")
+    nvalid = (labels[:, 1:] != -100).sum().item()
+    assert abs(sums[1].item() - nvalid) == 0
+    assert abs(sums[0].item() - ref.item()) < 1e-3 * nvalid
+    # backward
+    scale = torch.full((1,), 1.0 / nvalid, device="cuda")
+    dl = torch.full((B * T, ld), 7.0, device="cuda", dtype=torch.bfloat16)
+    ops.ce_bwd(logits, labels, lse, scale, dl, T=T, V=V)
+    lr = lf.clone().requires_grad_(True)
+    F.cross_entropy(lr[:, :-1].reshape(-1, V), labels[:, 1:].reshape(-1)).backward()
+    assert (dl[:, :V].float().view(B, T, V) - lr.grad).abs().max().item() < 2e-3 / nvalid * 10
+    assert dl[:, V:].abs().max().item() == 0
+    ops.check_err_flag(logits.device)
+
+
+def test_emotion_head(cuda_device):
+    from ergm_b200 import ops
+    B, T, H = 5, 9, 768
+    g = _g(6)
+    x = torch.randn(B * T, H, device="cuda", generator=g)
+    gamma = 1 + 0.1 * torch.randn(H, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(H, device="cuda", generator=g)
+    w = torch.randn(7, H, device="cuda", generator=g) * 0.02
+    lab = torch.randint(0, 7, (B,), device="cuda", generator=g)
+    mean = x.mean(1)
+    rstd = (x.var(1, unbiased=False) + 1e-5).rsqrt()
+    hlast = torch.empty(B, H, device="cuda")
+    lg = torch.empty(B, 7, device="cuda")
+    dlg = torch.empty(B, 7, device="cuda")
+    sums = torch.zeros(4, device="cuda")
+    ops.emotion_head_fwd(x, mean, rstd, gamma, beta, w, lab, hlast, lg, dlg, sums, B=B, T=T)
+    wr = w.clone().requires_grad_(True)
+    hr = F.layer_norm(x, (H,), gamma, beta, 1e-5).view(B, T, H)[:, -1].clone().requires_grad_(True)
+    lr = F.linear(hr, wr)
+    loss = F.cross_entropy(lr, lab)
+    loss.backward()
+    assert (lg - lr).abs().max().item() < 1e-4
+    assert abs(sums[2].item() / sums[3].item() - loss.item()) < 1e-5
+    out = torch.zeros(5, device="cuda")
+    ops.loss_finalize(sums, False, True, out)
+    assert abs(out[0].item() - loss.item()) < 1e-5 and abs(out[4].item() - 1.0 / B) < 1e-7
+    dw = torch.zeros(7, H, device="cuda")
+    dyf = torch.zeros(B * T, H, device="cuda")
+    ops.emotion_head_bwd(dlg, hlast, w, out[4:5], dw, dyf, B=B, T=T)
+    assert (dw - wr.grad).abs().max().item() < 1e-5
+    assert (dyf.view(B, T, H)[:, -1] - hr.grad).abs().max().item() < 1e-6
+    assert dyf.view(B, T, H)[:, :-1].abs().max().item() == 0
+
+
+def test_adamw_flat(cuda_device):
+    from ergm_b200 import ops
+    n = 4096 * 5
+    g = _g(7)
+    p0 = torch.randn(n, device="cuda", generator=g)
+    pt = p0.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([pt], lr=2e-5)
+    p = p0.clone()
+    m = torch.zeros(n, device="cuda")
+    v = torch.zeros(n, device="cuda")
+    sh = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    for step in range(1, 4):
+        gr = torch.randn(n, device="cuda", generator=g)
+        pt.grad = gr.clone()
+        opt.step()
+        hyper = torch.tensor([2e-5, 0.9, 0.999, 1e-8, 0.01, 1 - 0.9 ** step, 1 - 0.999 ** step], device="cuda")
+        ops.adamw_flat(p, gr, m, v, sh, hyper)
+    assert (p - pt.detach()).abs().max().item() < 1e-6
+    assert torch.equal(sh, p.bfloat16())
+
+
+def _attn_ref(q, k, v, causal, off, kv_lens=None):
+    # q [B,nh,Tq,64] etc, fp32: model.py:119-148
+    w = q @ k.transpose(-1, -2) / 8.0
+    Tq, Tk = q.shape[-2], k.shape[-2]
+    if causal:
+        mask = (torch.arange(Tk, device=q.device)[None, :] <= torch.arange(Tq, device=q.device)[:, None] + off)
+        w = torch.where(mask, w, torch.full([], torch.finfo(w.dtype).min, device=q.device))
+    if kv_lens is not None:
+        km = torch.arange(Tk, device=q.device)[None, :] < kv_lens[:, None]
+        w = w.masked_fill(~km[:, None, None, :], torch.finfo(w.dtype).min)
+    p = torch.softmax(w, -1)
+    return p @ v, torch.logsumexp(w, -1)
+
+
+@pytest.mark.parametrize("B,nh,Tq,Tk,causal", [(2, 2, 48, 48, True), (2, 12, 256, 256, True), (1, 3, 200, 200, True),
+                                                (2, 2, 48, 40, False), (2, 4, 256, 256, False), (1, 2, 130, 300, False),
+                                                (2, 2, 17, 145, True), (1, 16, 512, 512, True)])
+def test_attn_fwd(cuda_device, B, nh, Tq, Tk, causal):
+    from ergm_b200 import ops
+    H = nh * 64
+    g = _g(8)
+    if Tq == Tk and causal:  # fused qkv layout, as the self-attention path uses it
+        qkv = torch.randn(B * Tq, 3 * H, device="cuda", generator=g).bfloat16()
+        qm, km, vm, qc, kc, vc = qkv, qkv, qkv, 0, H, 2 * H
+    else:
+        qm = torch.randn(B * Tq, H, device="cuda", generator=g).bfloat16()
+        kvm = torch.randn(B * Tk, 2 * H, device="cuda", generator=g).bfloat16()
+        km, vm, qc, kc, vc = kvm, kvm, 0, 0, H
+    out = torch.zeros(B * Tq, H, device="cuda", dtype=torch.bfloat16)
+    lse = torch.zeros(B, nh, Tq, device="cuda")
+    ops.attn_fwd(qm, km, vm, out, lse, B=B, nh=nh, Tq=Tq, Tk=Tk, q_col0=qc, k_col0=kc, v_col0=vc, causal=causal)
+    q = qm[:, qc:qc + H].float().view(B, Tq, nh, 64).permute(0, 2, 1, 3)
+    k = km[:, kc:kc + H].float().view(B, Tk, nh, 64).permute(0, 2, 1, 3)
+    v = vm[:, vc:vc + H].float().view(B, Tk, nh, 64).permute(0, 2, 1, 3)
+    ro, rl = _attn_ref(q, k, v, causal, Tk - Tq)
+    ro = ro.permute(0, 2, 1, 3).reshape(B * Tq, H)
+    err = (out.float() - ro).abs().max().item()
+    assert err < 2e-2, err
+    assert (lse - rl).abs().max().item() < 2e-3
+
+
+def test_attn_fwd_kv_lens(cuda_device):
+    from ergm_b200 import ops
+    B, nh, Tq, Tk = 3, 2, 64, 160
+    H = nh * 64
+    g = _g(9)
+    qm = torch.randn(B * Tq, H, device="cuda", generator=g).bfloat16()
+    kvm = torch.randn(B * Tk, 2 * H, device="cuda", generator=g).bfloat16()
+    lens = torch.tensor([160, 33, 128], device="cuda", dtype=torch.int32)
+    out = torch.zeros(B * Tq, H, device="cuda", dtype=torch.bfloat16)
+    lse = torch.zeros(B, nh, Tq, device="cuda")
+    ops.attn_fwd(qm, kvm, kvm, out, lse, B=B, nh=nh, Tq=Tq, Tk=Tk, k_col0=0, v_col0=H, causal=False, kv_lens=lens)
+    q = qm.float().view(B, Tq, nh, 64).permute(0, 2, 1, 3)
+    k = kvm[:, :H].float().view(B, Tk, nh, 64).permute(0, 2, 1, 3)
+    v = kvm[:, H:].float().view(B, Tk, nh, 64).permute(0, 2, 1, 3)
+    ro, _ = _attn_ref(q, k, v, False, 0, lens)
+    assert (out.float() - ro.permute(0, 2, 1, 3).reshape(B * Tq, H)).abs().max().item() < 2e-2
