@@ -1,0 +1,369 @@
+// ergm_attn_bwd — fused attention backward on tcgen05 / TMEM, head_dim 64.
+//
+// Gradient of GPT2Attention._attn (/root/reference/src/model.py:119-148) w.r.t. Q, K, V given
+// dO, recomputing the probabilities from the saved log-sum-exp instead of storing the
+// [B,nh,T,T] score / probability tensors the reference keeps for autograd.
+//
+// One CTA = one (batch, head, 128-key block j); it loops over the query blocks i that can see
+// those keys.  Everything is computed TRANSPOSED (keys on TMEM lanes, queries on columns) so
+// that P^T and dS^T come out of the softmax warps exactly in the layout the next MMAs need:
+//   S^T  = K_j Q_i^T                      SS MMA  M128(kv) N128(q) K64      -> TMEM [0,128)
+//   dP^T = V_j dO_i^T                     SS MMA                            -> TMEM [128,256)
+//   P^T  = exp2(S^T c - lse_i log2e),  dS^T = P^T (dP^T - delta_i) scale    (8 compute warps)
+//   dV_j += P^T dO_i                      SS MMA  M128(kv) N64 K128(q)      -> TMEM [256,320)
+//   dK_j += dS^T Q_i                      SS MMA                            -> TMEM [320,384)
+//   dQ_i  = dS K_j                        SS MMA  M128(q)  N64 K128(kv)     -> TMEM [384,448)
+// The smem tile holding dS^T ([kv rows][q contiguous], 128B swizzle) is at the same time the
+// K-major A operand of the dK product and the MN-major A operand of the dQ product, and the
+// TMA tiles of Q_i / dO_i / K_j serve as K-major and MN-major B operands without any copy.
+// dQ is accumulated across key blocks with red.global.add.v4.f32 into an fp32 buffer.
+#include "../../include/ergm_b200.h"
+#include "common.cuh"
+#include "dropout.cuh"
+
+namespace ergm {
+
+constexpr int AB_THREADS = 384;
+constexpr int AB_TILE = 128 * 64 * 2;  // 16 KB
+// K, V, 2x(Q,dO), PT (2 tiles), dST (2 tiles), lse/delta (2 stages x 2 x 128 floats)
+constexpr int AB_SMEM = 2 * AB_TILE + 4 * AB_TILE + 2 * AB_TILE + 2 * AB_TILE + 2048 + 1024 + 256;
+
+struct AttnBwdParams {
+  const float* lse;     // [B, nh, Tq]
+  const float* delta;   // [B, nh, Tq]
+  float* dq_accum;      // fp32 [B*Tq, ld_dq], head h at columns [h*64, ...)
+  __nv_bfloat16* dk;    // [B*Tk, ld_dk], head h at columns [dk_col0 + h*64, ...)
+  __nv_bfloat16* dv;
+  const int* kv_lens;
+  int64_t ld_dq, ld_dk, ld_dv;
+  int dk_col0, dv_col0;
+  int Tq, Tk, nh;
+  int q_col0, k_col0, v_col0;
+  int causal_off;
+  float scale;
+  DropoutSite drop;
+  int do_drop;
+};
+
+template <bool CAUSAL>
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
+                const AttnBwdParams p_in) {
+  extern __shared__ uint8_t smem_raw[];
+  AttnBwdParams p = p_in;
+  p.drop = p_in.drop.resolved();
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sK = base, sV = base + AB_TILE;
+  const uint32_t sQ = base + 2 * AB_TILE;    // 2 stages
+  const uint32_t sDO = base + 4 * AB_TILE;   // 2 stages
+  const uint32_t sPT = base + 6 * AB_TILE;   // 2 tiles (q chunks)
+  const uint32_t sDS = base + 8 * AB_TILE;   // 2 tiles
+  const uint32_t sStat = base + 10 * AB_TILE;  // [2 stages][lse 128 | delta 128] floats
+  const uint32_t bars = sStat + 2048;
+  const uint32_t bar_kv = bars, bar_sdp = bars + 8, bar_pds = bars + 16, bar_dq = bars + 24;
+  auto qdo_full = [&](int s) { return bars + 32 + 8u * s; };
+  auto qdo_empty = [&](int s) { return bars + 48 + 8u * s; };
+  const uint32_t tmem_slot = bars + 64;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int jb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int k0 = jb * 128;
+  int kv_len = p.Tk;
+  if (p.kv_lens) kv_len = min(kv_len, p.kv_lens[b]);
+  const int n_q = (p.Tq + 127) / 128;
+  int i_min = 0;
+  if (CAUSAL) i_min = max(0, k0 - p.causal_off) / 128;
+  const bool active = (k0 < kv_len) && (i_min < n_q);  // CTA-uniform
+  const int n_iter = active ? n_q - i_min : 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_do);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(bar_kv, 1); mbar_init(bar_sdp, 1); mbar_init(bar_pds, 256); mbar_init(bar_dq, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(qdo_full(s), 1); mbar_init(qdo_empty(s), 1); }
+    fence_mbar_init();
+  }
+  if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
+  const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem + 256, tDK = tmem + 320, tDQ = tmem + 384;
+
+  if (warp == 0) {
+    if (lane == 0 && active) {
+      mbar_expect_tx(bar_kv, 2 * AB_TILE);
+      tma_load_3d(sK, &tm_k, bar_kv, p.k_col0 + h * 64, k0, b);
+      tma_load_3d(sV, &tm_v, bar_kv, p.v_col0 + h * 64, k0, b);
+      for (int it = 0; it < n_iter; ++it) {
+        const int st = it & 1;
+        mbar_wait(qdo_empty(st), ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(qdo_full(st), 2 * AB_TILE);
+        tma_load_3d(sQ + st * AB_TILE, &tm_q, qdo_full(st), p.q_col0 + h * 64, (i_min + it) * 128, b);
+        tma_load_3d(sDO + st * AB_TILE, &tm_do, qdo_full(st), h * 64, (i_min + it) * 128, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && active) {
+      const uint32_t id_st = make_idesc_bf16(128, 128, 0, 0);   // K-major x K-major
+      const uint32_t id_dkv = make_idesc_bf16(128, 64, 0, 1);   // A K-major, B MN-major
+      const uint32_t id_dq = make_idesc_bf16(128, 64, 1, 1);    // A MN-major, B MN-major
+      mbar_wait(bar_kv, 0);
+      for (int it = 0; it < n_iter; ++it) {
+        const int st = it & 1;
+        const uint32_t q_t = sQ + st * AB_TILE, do_t = sDO + st * AB_TILE;
+        mbar_wait(qdo_full(st), (it >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_ss(tS, make_smem_desc_sw128(sK + ks * 32, 16, 1024),
+                  make_smem_desc_sw128(q_t + ks * 32, 16, 1024), id_st, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_ss(tDP, make_smem_desc_sw128(sV + ks * 32, 16, 1024),
+                  make_smem_desc_sw128(do_t + ks * 32, 16, 1024), id_st, ks > 0);
+        umma_commit(bar_sdp);
+        mbar_wait(bar_pds, it & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint32_t a_off = (ks >> 2) * AB_TILE + (ks & 3) * 32;
+          umma_ss(tDV, make_smem_desc_sw128(sPT + a_off, 16, 1024),
+                  make_smem_desc_sw128(do_t + ks * 2048, 8192, 1024), id_dkv, (it > 0 || ks > 0));
+        }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint32_t a_off = (ks >> 2) * AB_TILE + (ks & 3) * 32;
+          umma_ss(tDK, make_smem_desc_sw128(sDS + a_off, 16, 1024),
+                  make_smem_desc_sw128(q_t + ks * 2048, 8192, 1024), id_dkv, (it > 0 || ks > 0));
+        }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+          umma_ss(tDQ, make_smem_desc_sw128(sDS + ks * 2048, AB_TILE, 1024),
+                  make_smem_desc_sw128(sK + ks * 2048, 8192, 1024), id_dq, ks > 0);
+        umma_commit(bar_dq);
+        umma_commit(qdo_empty(st));
+      }
+    }
+  } else if (warp >= 4 && active) {
+    const int qr = warp & 3;             // TMEM lane quarter
+    const int half = (warp - 4) >> 2;    // column half: q columns [64*half, 64*half+64)
+    const int r = qr * 32 + lane;        // key row inside the block == TMEM lane
+    const int kj = k0 + r;
+    const bool key_ok = kj < kv_len;
+    const uint32_t lane_addr = (uint32_t)(qr * 32) << 16;
+    const float c = p.scale * 1.4426950408889634f;
+    const float keep_scale = p.do_drop ? 1.f / (1.f - p.drop.p) : 1.f;
+    const int ct = threadIdx.x - 128;    // 0..255 inside the compute group
+    for (int it = 0; it < n_iter; ++it) {
+      const int q0 = (i_min + it) * 128;
+      // stage this query block's lse / delta in smem
+      {
+        const uint32_t dst = sStat + (it & 1) * 1024 + ct * 4;
+        const int qi = q0 + (ct & 127);
+        float val = 0.f;
+        if (qi < p.Tq) {
+          const int64_t idx = ((int64_t)b * p.nh + h) * p.Tq + qi;
+          val = ct < 128 ? p.lse[idx] * 1.4426950408889634f : p.delta[idx];
+        }
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst), "f"(val) : "memory");
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mbar_wait(bar_sdp, it & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 64 * half; cc < 64 * half + 64; cc += 32) {
+        uint32_t sv[32], dv_[32];
+        tmem_ld_32x32b_x32(tS + lane_addr + cc, sv);
+        tmem_ld_32x32b_x32(tDP + lane_addr + cc, dv_);
+        tmem_ld_wait();
+        float pt[32], ds[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int qi = q0 + cc + i;
+          float lse2, dl;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(lse2) : "r"(sStat + (it & 1) * 1024 + (cc + i) * 4));
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(dl) : "r"(sStat + (it & 1) * 1024 + 512 + (cc + i) * 4));
+          bool vis = key_ok && qi < p.Tq;
+          if (CAUSAL) vis = vis && (kj <= qi + p.causal_off);
+          const float pr = vis ? exp2f(__uint_as_float(sv[i]) * c - lse2) : 0.f;
+          float dp = __uint_as_float(dv_[i]);
+          float pd = pr;
+          if (p.do_drop) {
+            const bool keep = p.drop.keep((uint32_t)((b * p.nh + h) * p.Tq + qi), (uint32_t)kj);
+            dp = keep ? dp * keep_scale : 0.f;
+            pd = keep ? pr * keep_scale : 0.f;
+          }
+          pt[i] = pd;
+          ds[i] = pr * (dp - dl) * p.scale;
+        }
+        const uint32_t rowoff = (cc >> 6) * AB_TILE + r * 128;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          const uint32_t piece = (uint32_t)(((cc & 63) + i) >> 3);
+          const uint32_t off = rowoff + ((piece ^ (uint32_t)(r & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sPT + off),
+                       "r"(pack_bf16x2(pt[i], pt[i + 1])), "r"(pack_bf16x2(pt[i + 2], pt[i + 3])),
+                       "r"(pack_bf16x2(pt[i + 4], pt[i + 5])), "r"(pack_bf16x2(pt[i + 6], pt[i + 7]))
+                       : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sDS + off),
+                       "r"(pack_bf16x2(ds[i], ds[i + 1])), "r"(pack_bf16x2(ds[i + 2], ds[i + 3])),
+                       "r"(pack_bf16x2(ds[i + 4], ds[i + 5])), "r"(pack_bf16x2(ds[i + 6], ds[i + 7]))
+                       : "memory");
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(bar_pds);
+      // dQ_i: TMEM lanes are queries here; this warp handles rows qr*32.., columns 32*half..
+      mbar_wait(bar_dq, it & 1);
+      tc_fence_after();
+      {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tDQ + lane_addr + 32 * half, v);
+        tmem_ld_wait();
+        const int qi = q0 + r;
+        if (qi < p.Tq) {
+          float* dst = p.dq_accum + ((int64_t)b * p.Tq + qi) * p.ld_dq + h * 64 + 32 * half;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i),
+                         "f"(__uint_as_float(v[i])), "f"(__uint_as_float(v[i + 1])),
+                         "f"(__uint_as_float(v[i + 2])), "f"(__uint_as_float(v[i + 3]))
+                         : "memory");
+        }
+      }
+      tc_fence_before();
+    }
+    // dK_j, dV_j: lanes are keys; this warp writes rows qr*32.., columns 32*half..+32.
+    // tcgen05.ld is warp-collective (.sync.aligned): issue it unconditionally, guard the stores.
+    {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tDK + lane_addr + 32 * half, v);
+      tmem_ld_wait();
+      if (kj < p.Tk) {
+        __nv_bfloat16* dkp = p.dk + ((int64_t)b * p.Tk + kj) * p.ld_dk + p.dk_col0 + h * 64 + 32 * half;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8)
+          *reinterpret_cast<uint4*>(dkp + i) = make_uint4(
+              pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])),
+              pack_bf16x2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])),
+              pack_bf16x2(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])),
+              pack_bf16x2(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])));
+      }
+      tmem_ld_32x32b_x32(tDV + lane_addr + 32 * half, v);
+      tmem_ld_wait();
+      if (kj < p.Tk) {
+        __nv_bfloat16* dvp = p.dv + ((int64_t)b * p.Tk + kj) * p.ld_dv + p.dv_col0 + h * 64 + 32 * half;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8)
+          *reinterpret_cast<uint4*>(dvp + i) = make_uint4(
+              pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])),
+              pack_bf16x2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])),
+              pack_bf16x2(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])),
+              pack_bf16x2(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])));
+      }
+    }
+  } else if (warp >= 4 && !active) {
+    // keys that no query sees (or beyond kv_len): zero gradients
+    const int r = (warp & 3) * 32 + lane, half = (warp - 4) >> 2;
+    const int kj = k0 + r;
+    if (kj < p.Tk) {
+      __nv_bfloat16* dkp = p.dk + ((int64_t)b * p.Tk + kj) * p.ld_dk + p.dk_col0 + h * 64 + 32 * half;
+      __nv_bfloat16* dvp = p.dv + ((int64_t)b * p.Tk + kj) * p.ld_dv + p.dv_col0 + h * 64 + 32 * half;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        *reinterpret_cast<uint4*>(dkp + i) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(dvp + i) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+// delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]   (one warp per row of the [B*Tq, nh*64] matrices)
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const __nv_bfloat16* __restrict__ dout, int64_t ld_do,
+                  const __nv_bfloat16* __restrict__ out, int64_t ld_o, float* __restrict__ delta,
+                  int rows, int Tq, int nh) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= rows) return;
+  const int b = row / Tq, q = row - b * Tq;
+  // lanes 0..15 cover one head (16 lanes x 4 elements), a warp covers 2 heads per step
+  for (int h0 = 0; h0 < nh; h0 += 2) {
+    const int h = h0 + (lane >> 4);
+    float s = 0.f;
+    if (h < nh) {
+      const int col = h * 64 + (lane & 15) * 4;
+      const uint2 a = *reinterpret_cast<const uint2*>(dout + (int64_t)row * ld_do + col);
+      const uint2 o = *reinterpret_cast<const uint2*>(out + (int64_t)row * ld_o + col);
+      const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), o0 = unpack_bf16x2(o.x), o1 = unpack_bf16x2(o.y);
+      s = a0.x * o0.x + a0.y * o0.y + a1.x * o1.x + a1.y * o1.y;
+    }
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if ((lane & 15) == 0 && h < nh) delta[((int64_t)b * nh + h) * Tq + q] = s;
+  }
+}
+
+}  // namespace ergm
+
+using namespace ergm;
+
+extern "C" int ergm_attn_bwd(const void* q, int64_t ld_q, int q_col0, const void* k, int64_t ld_k,
+                             int k_col0, const void* v, int64_t ld_v, int v_col0, const void* out,
+                             int64_t ld_out, const void* dout, int64_t ld_do, const float* lse,
+                             float* delta, float* dq_accum, int64_t ld_dq, void* dk, int64_t ld_dk,
+                             int dk_col0, void* dv, int64_t ld_dv, int dv_col0, const int* kv_lens,
+                             int B, int nh, int Tq, int Tk, int head_dim, int causal, int causal_off,
+                             float dropout_p, uint64_t seed, uint64_t offset, void* stream) {
+  if (!q || !k || !v || !out || !dout || !lse || !delta || !dq_accum || !dk || !dv) return ERGM_ERR_ARG;
+  if (B <= 0 || nh <= 0 || Tq <= 0 || Tk <= 0) return ERGM_ERR_ARG;
+  if (head_dim != 64) return ERGM_ERR_UNSUPPORTED;
+  if (ld_q % 8 || ld_k % 8 || ld_v % 8 || ld_out % 8 || ld_do % 8 || ld_dq % 4 || ld_dk % 8 || ld_dv % 8 ||
+      q_col0 % 8 || k_col0 % 8 || v_col0 % 8 || dk_col0 % 8 || dv_col0 % 8)
+    return ERGM_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  attn_delta_kernel<<<(B * Tq + 7) / 8, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dout), ld_do,
+                                                    reinterpret_cast<const __nv_bfloat16*>(out), ld_out,
+                                                    delta, B * Tq, Tq, nh);
+  CUtensorMap tq, tk, tv, tdo;
+  int rc;
+  if ((rc = encode_tmap_3d(&tq, q, 2, (uint64_t)(q_col0 + nh * 64), (uint64_t)Tq, (uint64_t)B,
+                           (uint64_t)ld_q * 2, (uint64_t)Tq * ld_q * 2, 64, 128, 1))) return rc;
+  if ((rc = encode_tmap_3d(&tk, k, 2, (uint64_t)(k_col0 + nh * 64), (uint64_t)Tk, (uint64_t)B,
+                           (uint64_t)ld_k * 2, (uint64_t)Tk * ld_k * 2, 64, 128, 1))) return rc;
+  if ((rc = encode_tmap_3d(&tv, v, 2, (uint64_t)(v_col0 + nh * 64), (uint64_t)Tk, (uint64_t)B,
+                           (uint64_t)ld_v * 2, (uint64_t)Tk * ld_v * 2, 64, 128, 1))) return rc;
+  if ((rc = encode_tmap_3d(&tdo, dout, 2, (uint64_t)(nh * 64), (uint64_t)Tq, (uint64_t)B,
+                           (uint64_t)ld_do * 2, (uint64_t)Tq * ld_do * 2, 64, 128, 1))) return rc;
+  AttnBwdParams p;
+  p.lse = lse; p.delta = delta; p.dq_accum = dq_accum;
+  p.dk = reinterpret_cast<__nv_bfloat16*>(dk); p.dv = reinterpret_cast<__nv_bfloat16*>(dv);
+  p.kv_lens = kv_lens;
+  p.ld_dq = ld_dq; p.ld_dk = ld_dk; p.ld_dv = ld_dv; p.dk_col0 = dk_col0; p.dv_col0 = dv_col0;
+  p.Tq = Tq; p.Tk = Tk; p.nh = nh;
+  p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
+  p.causal_off = causal_off;
+  p.scale = 1.0f / sqrtf((float)head_dim);
+  p.drop = make_site(seed, offset, dropout_p, (uint32_t)Tk);
+  p.do_drop = dropout_p > 0.f;
+  static bool attr = false;
+  if (!attr) {
+    ERGM_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+    ERGM_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+    attr = true;
+  }
+  dim3 grid((Tk + 127) / 128, nh, B);
+  if (causal)
+    attn_bwd_kernel<true><<<grid, AB_THREADS, AB_SMEM, s>>>(tq, tk, tv, tdo, p);
+  else
+    attn_bwd_kernel<false><<<grid, AB_THREADS, AB_SMEM, s>>>(tq, tk, tv, tdo, p);
+  return (int)cudaGetLastError();
+}

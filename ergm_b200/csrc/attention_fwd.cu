@@ -41,8 +41,10 @@ struct AttnFwdParams {
 template <bool CAUSAL>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                const __grid_constant__ CUtensorMap tm_v, const AttnFwdParams p) {
+                const __grid_constant__ CUtensorMap tm_v, const AttnFwdParams p_in) {
   extern __shared__ uint8_t smem_raw[];
+  AttnFwdParams p = p_in;
+  p.drop = p_in.drop.resolved();
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base, sK = base + AT_TILE, sV = base + 3 * AT_TILE, sP = base + 5 * AT_TILE;
   const uint32_t bars = base + 7 * AT_TILE;
@@ -245,7 +247,7 @@ extern "C" int ergm_attn_fwd(const void* q, int64_t ld_q, int q_col0, const void
   p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
   p.causal_off = causal_off;
   p.scale = 1.0f / sqrtf((float)head_dim);
-  p.drop = DropoutSite{seed, offset, dropout_p, (uint32_t)((Tk + 3) / 4)};
+  p.drop = make_site(seed, offset, dropout_p, (uint32_t)Tk);
   p.do_drop = dropout_p > 0.f;
   static bool attr = false;
   if (!attr) {

@@ -12,6 +12,17 @@ struct DropoutSite {
   uint64_t seed, offset;
   float p;
   uint32_t ncol4;  // ceil(ncols / 4)
+  // Optional device-resident step counter added to the seed, so that a CUDA-graph replay
+  // (whose kernel arguments are frozen) still draws fresh masks every step.
+  const uint64_t* step;
+
+  // call once at kernel entry: folds *step into the seed
+  ERGM_DEVINL DropoutSite resolved() const {
+    DropoutSite r = *this;
+    if (step) r.seed += __ldg(reinterpret_cast<const unsigned long long*>(step));
+    r.step = nullptr;
+    return r;
+  }
 
   // keep bits for elements (row, 4*col4 .. 4*col4+3); bit i set = keep
   ERGM_DEVINL uint32_t keep4(uint32_t row, uint32_t col4) const {
@@ -28,5 +39,11 @@ struct DropoutSite {
     return (keep4(row, col >> 2) >> (col & 3)) & 1u;
   }
 };
+
+// host side: library-global step pointer (set by ergm_set_rng_step_ptr, see api.cu)
+extern const uint64_t* g_rng_step_ptr;
+inline DropoutSite make_site(uint64_t seed, uint64_t offset, float p, uint32_t ncols) {
+  return DropoutSite{seed, offset, p, (ncols + 3) / 4, p > 0.f ? g_rng_step_ptr : nullptr};
+}
 
 }  // namespace ergm

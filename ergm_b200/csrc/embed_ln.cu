@@ -29,7 +29,9 @@ struct EmbedFwdParams {
   int* err_flag;            // set to 1 on an out-of-range id (device-side assert replacement)
 };
 
-__global__ void __launch_bounds__(ROW_WARPS * 32) embed_fuse_fwd_kernel(const EmbedFwdParams p) {
+__global__ void __launch_bounds__(ROW_WARPS * 32) embed_fuse_fwd_kernel(const EmbedFwdParams p_in) {
+  EmbedFwdParams p = p_in;
+  p.drop = p_in.drop.resolved();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rows = p.B * p.T;
   const float keep_scale = p.do_drop ? 1.f / (1.f - p.drop.p) : 1.f;
@@ -108,7 +110,9 @@ ERGM_DEVINL void red_add4(float* addr, const float4 v) {
                : "memory");
 }
 
-__global__ void embed_bwd_kernel(const EmbedBwdParams p) {
+__global__ void embed_bwd_kernel(const EmbedBwdParams p_in) {
+  EmbedBwdParams p = p_in;
+  p.drop = p_in.drop.resolved();
   const int c = threadIdx.x;  // float4 column
   if (c >= p.H / 4) return;
   const int r0 = blockIdx.x * p.rows_per_cta;
@@ -228,8 +232,10 @@ struct LnBwdParams {
 };
 
 template <int NV>
-__global__ void __launch_bounds__(ROW_WARPS * 32) ln_bwd_kernel(const LnBwdParams p) {
+__global__ void __launch_bounds__(ROW_WARPS * 32) ln_bwd_kernel(const LnBwdParams p_in) {
   constexpr int H = NV * 128;
+  LnBwdParams p = p_in;
+  p.drop = p_in.drop.resolved();
   __shared__ float red[ROW_WARPS][H];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float keep_scale = p.do_drop ? 1.f / (1.f - p.drop.p) : 1.f;
@@ -415,7 +421,7 @@ extern "C" int ergm_embed_fuse_fwd(const int64_t* ids, const int64_t* token_type
   if ((imgs && ld_img % 4) || (auds && ld_aud % 4)) return ERGM_ERR_ARG;
   EmbedFwdParams p{ids, token_type_ids, position_ids, wte, wpe, imgs, auds, out, ld_img, ld_aud,
                    B, T, H, past_len, vocab, n_pos,
-                   DropoutSite{seed, offset, dropout_p, (uint32_t)(H / 4)}, dropout_p > 0.f, err_flag};
+                   make_site(seed, offset, dropout_p, (uint32_t)H), dropout_p > 0.f, err_flag};
   embed_fuse_fwd_kernel<<<row_grid(B * T), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
   return (int)cudaGetLastError();
 }
@@ -435,7 +441,7 @@ extern "C" int ergm_embed_bwd(const float* dh, const int64_t* ids, const int64_t
   if (!dh || rows <= 0 || T <= 0 || H % 128 || H / 4 > 1024) return ERGM_ERR_ARG;
   if ((ids || token_type_ids) && !dwte) return ERGM_ERR_ARG;
   EmbedBwdParams p{dh, ids, token_type_ids, position_ids, dwte, dwpe, dimgs, dauds, rows, T, H,
-                   past_len, 32, DropoutSite{seed, offset, dropout_p, (uint32_t)(H / 4)},
+                   past_len, 32, make_site(seed, offset, dropout_p, (uint32_t)H),
                    dropout_p > 0.f};
   const int threads = ((H / 4 + 31) / 32) * 32;
   embed_bwd_kernel<<<(rows + 31) / 32, threads, 0, (cudaStream_t)stream>>>(p);
@@ -462,7 +468,7 @@ extern "C" int ergm_ln_bwd(const void* dy, int dy_is_f32, const float* x, const 
     return ERGM_ERR_ARG;
   LnBwdParams p{dy, x, mean, rstd, gamma, dres_in, dx_out, reinterpret_cast<__nv_bfloat16*>(dx_bf16),
                 dgamma, dbeta, dbias_next, rows, dy_is_f32,
-                DropoutSite{seed, offset, dropout_p, (uint32_t)(H / 4)}, dropout_p > 0.f};
+                make_site(seed, offset, dropout_p, (uint32_t)H), dropout_p > 0.f};
   return dispatch_nv(H, [&](auto nv) {
     const int need = (rows + ROW_WARPS - 1) / ROW_WARPS;
     const int grid = need < 2 * num_sms() ? need : 2 * num_sms();

@@ -50,7 +50,7 @@ struct GemmParams {
   int split_k;
   int m_tiles, n_tiles, kb_total, kb_per_split;
   float dropout_p;
-  uint64_t seed, offset;
+  DropoutSite site;
 };
 
 template <int BN>
@@ -186,7 +186,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const bool exact = (p.epi & ERGM_EPI_EXACT) != 0;
     const bool do_gelu_grad = (p.epi & ERGM_EPI_GELU_GRAD) != 0;
     const float keep_scale = do_drop ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
-    const DropoutSite site{p.seed, p.offset, p.dropout_p, (uint32_t)((p.N + 3) >> 2)};
+    const DropoutSite site = p.site.resolved();
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -378,7 +378,8 @@ static int launch_gemm(const ergm_gemm_args* a, cudaStream_t stream) {
   if (p.split_k > p.kb_total) p.split_k = p.kb_total;
   p.kb_per_split = (p.kb_total + p.split_k - 1) / p.split_k;
   p.split_k = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
-  p.dropout_p = a->dropout_p; p.seed = a->seed; p.offset = a->offset;
+  p.dropout_p = a->dropout_p;
+  p.site = make_site(a->seed, a->offset, a->dropout_p, (uint32_t)a->N);
 
   static bool attr_set = false;
   if (!attr_set) {

@@ -1,0 +1,428 @@
+"""Forward / backward composition of the ERGM hot path out of the C-ABI kernels.
+
+This is the host-side runtime behind ergm_b200.model.GPT2LMHeadModel.forward: it mirrors the
+data flow of /root/reference/src/model.py (GPT2Model.forward :420-596, GPT2Block.forward
+:286-341, GPT2LMHeadModel.forward :654-737) but every arithmetic step is a call into
+libergm_b200.so — PyTorch only owns the memory and the stream.  The backward pass is written
+by hand (one monolithic pass in reverse layer order) so that residual-gradient adds, bias
+gradients, dropout masks and bf16 operand casts are fused into the LayerNorm-backward and
+GEMM epilogues instead of being separate autograd nodes.
+"""
+import torch
+
+from . import _lib as L
+from . import ops
+from .param_store import ParamStore
+
+K_MAJOR, MN_MAJOR = L.ERGM_MAJOR_K, L.ERGM_MAJOR_MN
+
+
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+class Workspace:
+    """Named, shape-keyed device buffers, allocated once and reused every step (static
+    addresses keep the whole step CUDA-graph capturable)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs = {}
+
+    def get(self, name, shape, dtype, zero=False):
+        key = (name, tuple(shape), dtype)
+        t = self.bufs.get(key)
+        if t is None:
+            t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.device)
+            self.bufs[key] = t
+        return t
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in self.bufs.values())
+
+
+class LayerParams:
+    __slots__ = ("f", "b", "g")  # fp32 views, bf16 shadow views, grad views (dicts by short name)
+
+
+class Engine:
+    def __init__(self, model):
+        self.model = model
+        self.cfg = model.config
+        self.store = ParamStore(model)
+        self.device = self.store.device
+        self.ws_train = Workspace(self.device)
+        self.ws_eval = Workspace(self.device)
+        self.saved = None
+        self.seed = 0x5EED
+        self.site_counter = 0
+        self.rng_step = None
+        self._index()
+
+    # ------------------------------------------------------------------
+    def _index(self):
+        st = self.store
+        cfg = self.cfg
+        self.H = cfg.n_embd
+        self.nh = cfg.n_head
+        self.L = cfg.n_layer
+        self.I = cfg.n_inner if cfg.n_inner is not None else 4 * cfg.n_embd
+        if self.H // self.nh != 64 or self.H % 128:
+            raise L.ErgmError("ergm_b200 kernels need head_dim == 64 and n_embd %% 128 == 0 (got n_embd=%d, n_head=%d)"
+                              % (self.H, self.nh))
+        if getattr(cfg, "activation_function", "gelu_new") != "gelu_new":
+            raise L.ErgmError("only activation_function='gelu_new' (model.py:259) is implemented")
+        if getattr(cfg, "scale_attn_by_inverse_layer_idx", False) or getattr(cfg, "reorder_and_upcast_attn", False) \
+                or not getattr(cfg, "scale_attn_weights", True):
+            raise L.ErgmError("non-default attention scaling flags (model.py:122-128,150-188) are not implemented")
+        names = set(st.entries)
+
+        def trio(name):
+            return st.view(name), st.shadow_view(name), st.grad_view(name)
+
+        self.P = {}
+        for name in names:
+            self.P[name] = trio(name)
+        self.V = st.entries["transformer.wte.weight"][2][0]
+        self.n_pos = st.entries["transformer.wpe.weight"][2][0]
+
+    def ensure_params(self):
+        if not self.store.valid():
+            self.store.build()
+            self._index()
+            self.ws_train = Workspace(self.store.device)
+            self.ws_eval = Workspace(self.store.device)
+            self.device = self.store.device
+
+    def p(self, name):
+        return self.P[name][0]
+
+    def pb(self, name):
+        return self.P[name][1]
+
+    def pg(self, name):
+        return self.P[name][2]
+
+    # ------------------------------------------------------------------
+    def _new_sites(self, training):
+        """Dropout site ids for one forward: (seed, base offset).  Offsets are unique per
+        nn.Dropout application; the optional device step counter de-correlates graph replays."""
+        self.site_counter += 1
+        return self.site_counter * 4096
+
+    def set_rng_step_tensor(self, t):
+        """Registers a device uint64 step counter (see ergm_set_rng_step_ptr)."""
+        self.rng_step = t
+        L.check(L.lib().ergm_set_rng_step_ptr(t.data_ptr() if t is not None else None), "ergm_set_rng_step_ptr")
+
+    # GEMM helpers ------------------------------------------------------
+    @staticmethod
+    def _fwd_gemm(x, w_b, out, M, N, K, **kw):
+        ops.gemm(x, w_b, out, M=M, N=N, K=K, a_major=K_MAJOR, b_major=MN_MAJOR, **kw)
+
+    @staticmethod
+    def _dgrad_gemm(dy, w_b, out, M, N_out, K_red, **kw):
+        # out[M, N_out] = dy[M, K_red] @ W[N_out, K_red]^T   (W is Conv1D [in=N_out, out=K_red])
+        ops.gemm(dy, w_b, out, M=M, N=N_out, K=K_red, a_major=K_MAJOR, b_major=K_MAJOR, **kw)
+
+    @staticmethod
+    def _wgrad_gemm(x, dy, dw, K_in, N_out, M_red):
+        # dw[K_in, N_out] += x[M_red, K_in]^T @ dy[M_red, N_out]
+        tiles = ((K_in + 127) // 128) * ((N_out + 127) // 128)
+        split = max(1, min(16, round(148.0 / tiles)))
+        ops.gemm(x, dy, dw, M=K_in, N=N_out, K=M_red, a_major=MN_MAJOR, b_major=MN_MAJOR,
+                 epilogue=L.EPI_ATOMIC, split_k=split, block_n=128)
+
+    # ------------------------------------------------------------------
+    def forward(self, input_ids, token_type_ids=None, labels=None, emotion_labels=None, imgs=None, auds=None,
+                caption_ids=None, position_ids=None, past_len=0, kv_lens=None, training=False, save=False,
+                want_logits=True, logits_fp32=False, dropout=None):
+        """Runs the full forward.  Returns a dict of device tensors (views into the workspace):
+        logits [B,T,V] (bf16 or fp32, leading dim padded), emotion_logits [B,7], losses [5]
+        (loss, lm_loss, emo_loss, 1/n_valid, 1/n_samples), hidden (bf16 ln_f output)."""
+        self.ensure_params()
+        self.store.refresh_shadow()
+        cfg, H, nh, Lyr, I, V = self.cfg, self.H, self.nh, self.L, self.I, self.V
+        B, T = input_ids.shape
+        M = B * T
+        if T + past_len > self.n_pos and position_ids is None:
+            raise ValueError("sequence length %d + past %d exceeds n_positions %d" % (T, past_len, self.n_pos))
+        ws = self.ws_train if save else self.ws_eval
+        dev = self.device
+        f32, bf16 = torch.float32, torch.bfloat16
+        eps = cfg.layer_norm_epsilon
+        pd_embd = cfg.embd_pdrop if (training and dropout is None) else (dropout or 0.0) if training else 0.0
+        pd_attn = cfg.attn_pdrop if (training and dropout is None) else (dropout or 0.0) if training else 0.0
+        pd_res = cfg.resid_pdrop if (training and dropout is None) else (dropout or 0.0) if training else 0.0
+        site0 = self._new_sites(training)
+        seed = self.seed
+
+        def lname(base, l):
+            return "%s_%d" % (base, l) if save else base
+
+        fuse = imgs is not None and past_len == 0  # boundary decision (3): fusion on the prefill only
+        if imgs is not None and auds is None:
+            raise ValueError("imgs given without auds (model.py:495-498 uses both)")
+        img2 = aud2 = None
+        if fuse:
+            img2 = self._feature_rows(imgs, B, H, "imgs")
+            aud2 = self._feature_rows(auds, B, H, "auds")
+        x = ws.get(lname("x", 0), (M, H), f32)
+        ops.embed_fuse_fwd(input_ids, token_type_ids, position_ids, self.p("transformer.wte.weight"),
+                           self.p("transformer.wpe.weight"), img2, aud2, x, past_len=past_len,
+                           dropout_p=pd_embd, seed=seed, offset=site0)
+        enc = None
+        Tc = Mc = 0
+        if caption_ids is not None:
+            caption_ids = caption_ids.reshape(B, -1)
+            Tc = caption_ids.shape[1]
+            Mc = B * Tc
+            enc = ws.get("enc", (Mc, H), bf16)
+            ops.gather_rows_bf16(caption_ids, self.p("transformer.wte.weight"), enc)
+
+        sv = dict(B=B, T=T, Tc=Tc, layers=[], site0=site0, seed=seed, pd=(pd_embd, pd_attn, pd_res),
+                  past_len=past_len, kv_lens=kv_lens, ids=input_ids, tts=token_type_ids, pos=position_ids,
+                  cap=caption_ids, enc=enc, labels=labels, emo=emotion_labels, fuse=fuse) if save else None
+        kv_present = []
+        for l in range(Lyr):
+            pfx = "transformer.h.%d." % l
+            s_attn, s_res1, s_xattn, s_res2, s_res3 = [site0 + 8 * l + 1 + i for i in range(5)]
+            rec = {}
+            # ---- self attention (model.py:297-309) ----
+            a1 = ws.get(lname("a1", l), (M, H), bf16)
+            mean1 = ws.get(lname("mean1", l), (M,), f32)
+            rstd1 = ws.get(lname("rstd1", l), (M,), f32)
+            ops.ln_fwd(x, self.p(pfx + "ln_1.weight"), self.p(pfx + "ln_1.bias"), a1, None, mean1, rstd1, eps)
+            qkv = ws.get("qkv_%d" % l if (save or past_len == 0) else "qkv", (M, 3 * H), bf16)
+            self._fwd_gemm(a1, self.pb(pfx + "attn.c_attn.weight"), qkv, M, 3 * H, H,
+                           bias=self.p(pfx + "attn.c_attn.bias"))
+            ctx = ws.get(lname("ctx", l), (M, H), bf16)
+            lse1 = ws.get(lname("lse1", l), (B, nh, T), f32)
+            ops.attn_fwd(qkv, qkv, qkv, ctx, lse1, B=B, nh=nh, Tq=T, Tk=T, q_col0=0, k_col0=H, v_col0=2 * H,
+                         causal=True, kv_lens=kv_lens, dropout_p=pd_attn, seed=seed, offset=s_attn)
+            kv_present.append(qkv)
+            x1 = ws.get(lname("x1", l), (M, H), f32) if save else x
+            self._fwd_gemm(ctx, self.pb(pfx + "attn.c_proj.weight"), x1, M, H, H,
+                           bias=self.p(pfx + "attn.c_proj.bias"), residual=x, dropout_p=pd_res, seed=seed,
+                           offset=s_res1)
+            rec.update(x=x, a1=a1, mean1=mean1, rstd1=rstd1, qkv=qkv, ctx=ctx, lse1=lse1, x1=x1)
+            # ---- cross attention over caption embeddings (model.py:311-329) ----
+            x2 = x1
+            if enc is not None:
+                a2 = ws.get(lname("a2", l), (M, H), bf16)
+                mean2 = ws.get(lname("mean2", l), (M,), f32)
+                rstd2 = ws.get(lname("rstd2", l), (M,), f32)
+                ops.ln_fwd(x1, self.p(pfx + "ln_cross_attn.weight"), self.p(pfx + "ln_cross_attn.bias"), a2, None,
+                           mean2, rstd2, eps)
+                q2 = ws.get(lname("q2", l), (M, H), bf16)
+                self._fwd_gemm(a2, self.pb(pfx + "crossattention.q_attn.weight"), q2, M, H, H,
+                               bias=self.p(pfx + "crossattention.q_attn.bias"))
+                kv2 = ws.get(lname("kv2", l), (Mc, 2 * H), bf16)
+                self._fwd_gemm(enc, self.pb(pfx + "crossattention.c_attn.weight"), kv2, Mc, 2 * H, H,
+                               bias=self.p(pfx + "crossattention.c_attn.bias"))
+                ctx2 = ws.get(lname("ctx2", l), (M, H), bf16)
+                lse2 = ws.get(lname("lse2", l), (B, nh, T), f32)
+                ops.attn_fwd(q2, kv2, kv2, ctx2, lse2, B=B, nh=nh, Tq=T, Tk=Tc, q_col0=0, k_col0=0, v_col0=H,
+                             causal=False, dropout_p=pd_attn, seed=seed, offset=s_xattn)
+                x2 = ws.get(lname("x2", l), (M, H), f32) if save else x1
+                self._fwd_gemm(ctx2, self.pb(pfx + "crossattention.c_proj.weight"), x2, M, H, H,
+                               bias=self.p(pfx + "crossattention.c_proj.bias"), residual=x1, dropout_p=pd_res,
+                               seed=seed, offset=s_res2)
+                rec.update(a2=a2, mean2=mean2, rstd2=rstd2, q2=q2, kv2=kv2, ctx2=ctx2, lse2=lse2, x2=x2)
+            # ---- MLP (model.py:331-334, 262-267) ----
+            a3 = ws.get(lname("a3", l), (M, H), bf16)
+            mean3 = ws.get(lname("mean3", l), (M,), f32)
+            rstd3 = ws.get(lname("rstd3", l), (M,), f32)
+            ops.ln_fwd(x2, self.p(pfx + "ln_2.weight"), self.p(pfx + "ln_2.bias"), a3, None, mean3, rstd3, eps)
+            g = ws.get(lname("g", l), (M, I), bf16)
+            u = ws.get(lname("u", l), (M, I), bf16) if save else None
+            self._fwd_gemm(a3, self.pb(pfx + "mlp.c_fc.weight"), g, M, I, H, bias=self.p(pfx + "mlp.c_fc.bias"),
+                           preact=u, epilogue=L.EPI_GELU)
+            x3 = ws.get(lname("x", l + 1), (M, H), f32) if save else x2
+            self._fwd_gemm(g, self.pb(pfx + "mlp.c_proj.weight"), x3, M, H, I, bias=self.p(pfx + "mlp.c_proj.bias"),
+                           residual=x2, dropout_p=pd_res, seed=seed, offset=s_res3)
+            rec.update(a3=a3, mean3=mean3, rstd3=rstd3, g=g, u=u)
+            if save:
+                sv["layers"].append(rec)
+            x = x3
+        # ---- final LN, heads, losses (model.py:578, 698-721) ----
+        hn = ws.get("hn", (M, H), bf16)
+        meanf = ws.get("meanf", (M,), f32)
+        rstdf = ws.get("rstdf", (M,), f32)
+        ops.ln_fwd(x, self.p("transformer.ln_f.weight"), self.p("transformer.ln_f.bias"), hn, None, meanf, rstdf, eps)
+        out = dict(hidden=hn, kv_present=kv_present, B=B, T=T)
+        ldl = (V + 63) // 64 * 64  # padded leading dimension: 16-byte rows for TMA / vector access
+        logits = None
+        need_lm = want_logits or labels is not None
+        if need_lm:
+            logits = ws.get("logits32" if logits_fp32 else "logits", (M, ldl), f32 if logits_fp32 else bf16)
+            ops.gemm(hn, self.pb("transformer.wte.weight"), logits, M=M, N=V, K=H, a_major=K_MAJOR, b_major=K_MAJOR)
+            out["logits"] = logits
+        sums = ws.get("loss_sums", (4,), f32)
+        sums.zero_()
+        losses = ws.get("losses", (5,), f32)
+        hlast = ws.get("hlast", (B, H), f32)
+        emo_logits = ws.get("emo_logits", (B, 7), f32)
+        emo_dlog = ws.get("emo_dlog", (B, 7), f32)
+        ops.emotion_head_fwd(x, meanf, rstdf, self.p("transformer.ln_f.weight"), self.p("transformer.ln_f.bias"),
+                             self.p("emotion_head.weight"), emotion_labels, hlast, emo_logits, emo_dlog, sums,
+                             B=B, T=T)
+        out["emotion_logits"] = emo_logits
+        lse = row_loss = None
+        if labels is not None:
+            lse = ws.get("ce_lse", (M,), f32)
+            row_loss = ws.get("ce_row_loss", (M,), f32)
+            ops.ce_fwd(logits, labels, lse, row_loss, sums, T=T, V=V)
+        out["loss_sums"] = sums
+        out["losses"] = losses
+        out["has_lm"] = labels is not None
+        out["has_emo"] = emotion_labels is not None
+        if save:
+            sv.update(xf=x, hn=hn, meanf=meanf, rstdf=rstdf, logits=logits, ce_lse=lse, hlast=hlast,
+                      emo_dlog=emo_dlog, losses=losses, ldl=ldl)
+            self.saved = sv
+        return out
+
+    def finalize_loss(self, out):
+        """loss = CE_lm + CE_emotion (model.py:704-721) from the (possibly all-reduced) sums."""
+        ops.loss_finalize(out["loss_sums"], out["has_lm"], out["has_emo"], out["losses"])
+        return out["losses"]
+
+    def _feature_rows(self, feat, B, H, what):
+        """imgs: [B, >=1, H] (first row used, model.py:497 `imgs[i][0]`) or [B, H]; auds: [B, H] or
+        [B, 1, H] (model.py:498 `auds[i].unsqueeze(0)` broadcasts)."""
+        if isinstance(feat, (list, tuple)):
+            feat = torch.stack([torch.as_tensor(f[0] if what == "imgs" and torch.as_tensor(f).dim() > 1 else f)
+                                for f in feat]).to(self.device)
+        if feat.dim() == 3:
+            feat = feat[:, 0]
+        if feat.dim() != 2 or feat.shape[0] != B or feat.shape[1] != H:
+            raise ValueError("%s must be broadcastable to [B=%d, n_embd=%d] (got %s); use the pooled / projected "
+                             "feature path for other widths" % (what, B, H, tuple(feat.shape)))
+        if feat.dtype != torch.float32 or feat.stride(1) != 1 or feat.stride(0) % 4 or feat.data_ptr() % 16:
+            feat = feat.float().contiguous()
+        return feat
+
+    # ------------------------------------------------------------------
+    def backward(self, grad_loss, accumulate=False):
+        """Hand-written backward of the whole path.  grad_loss: device fp32 scalar tensor (dLoss).
+        Gradients are accumulated into the flat gradient buffer (zeroed first unless
+        `accumulate`)."""
+        sv = self.saved
+        if sv is None:
+            raise RuntimeError("backward() without a saved training forward")
+        self.saved = None
+        cfg, H, nh, Lyr, I, V = self.cfg, self.H, self.nh, self.L, self.I, self.V
+        B, T, Tc = sv["B"], sv["T"], sv["Tc"]
+        M, Mc = B * T, B * Tc
+        ws = self.ws_train
+        f32, bf16 = torch.float32, torch.bfloat16
+        seed, site0 = sv["seed"], sv["site0"]
+        pd_embd, pd_attn, pd_res = sv["pd"]
+        if not accumulate:
+            self.store.grad.zero_()
+        losses = sv["losses"]
+        scales = ws.get("bwd_scales", (2,), f32)
+        ops.scalar_mul(grad_loss, losses[3:4], scales[0:1])  # dL/d(row loss) = g / n_valid
+        ops.scalar_mul(grad_loss, losses[4:5], scales[1:2])  # g / n_samples
+        dhn = ws.get("dhn", (M, H), f32)
+        hn = sv["hn"]
+        if sv["labels"] is not None:
+            ldl = sv["ldl"]
+            dlogits = ws.get("dlogits", (M, ldl), bf16)
+            ops.ce_bwd(sv["logits"], sv["labels"], sv["ce_lse"], scales[0:1], dlogits, T=T, V=V)
+            wte_b = self.pb("transformer.wte.weight")
+            # d hn = dlogits @ wte
+            ops.gemm(dlogits, wte_b, dhn, M=M, N=H, K=V, a_major=K_MAJOR, b_major=MN_MAJOR)
+            # d wte += dlogits^T @ hn
+            ops.gemm(dlogits, hn, self.pg("transformer.wte.weight"), M=V, N=H, K=M, a_major=MN_MAJOR,
+                     b_major=MN_MAJOR, epilogue=L.EPI_ATOMIC, block_n=128)
+        else:
+            dhn.zero_()
+        if sv["emo"] is not None:
+            ops.emotion_head_bwd(sv["emo_dlog"], sv["hlast"], self.p("emotion_head.weight"), scales[1:2],
+                                 self.pg("emotion_head.weight"), dhn, B=B, T=T)
+        # residual-stream gradient dx (fp32) and its bf16 (dropout-masked) operand copy dxb
+        dx = ws.get("dx", (M, H), f32)
+        dxb = ws.get("dxb", (M, H), bf16)
+        last = "transformer.h.%d." % (Lyr - 1)
+        ops.ln_bwd(dhn, sv["xf"], sv["meanf"], sv["rstdf"], self.p("transformer.ln_f.weight"), None, dx, dxb,
+                   self.pg("transformer.ln_f.weight"), self.pg("transformer.ln_f.bias"),
+                   self.pg(last + "mlp.c_proj.bias"), dropout_p=pd_res, seed=seed,
+                   offset=site0 + 8 * (Lyr - 1) + 5)
+        dI = ws.get("du", (M, I), bf16)
+        dH = ws.get("dact", (M, H), bf16)
+        dqkv = ws.get("dqkv", (M, 3 * H), bf16)
+        dq_acc = ws.get("dq_acc", (M, H), f32)
+        delta = ws.get("delta", (B, nh, T), f32)
+        denc = None
+        if sv["enc"] is not None:
+            denc = ws.get("denc", (Mc, H), f32)
+            denc.zero_()
+            dq2 = ws.get("dq2", (M, H), bf16)
+            dkv2 = ws.get("dkv2", (Mc, 2 * H), bf16)
+        for l in reversed(range(Lyr)):
+            pfx = "transformer.h.%d." % l
+            r = sv["layers"][l]
+            s_attn, s_res1, s_xattn, s_res2, s_res3 = [site0 + 8 * l + 1 + i for i in range(5)]
+            has_x = "a2" in r
+            # ---- MLP backward ----
+            self._wgrad_gemm(r["g"], dxb, self.pg(pfx + "mlp.c_proj.weight"), I, H, M)
+            self._dgrad_gemm(dxb, self.pb(pfx + "mlp.c_proj.weight"), dI, M, I, H, gelu_grad_of=r["u"])
+            ops.colsum_bf16(dI, self.pg(pfx + "mlp.c_fc.bias"))
+            self._wgrad_gemm(r["a3"], dI, self.pg(pfx + "mlp.c_fc.weight"), H, I, M)
+            self._dgrad_gemm(dI, self.pb(pfx + "mlp.c_fc.weight"), dH, M, H, I)
+            x_in = r["x2"] if has_x else r["x1"]
+            nb = pfx + ("crossattention.c_proj.bias" if has_x else "attn.c_proj.bias")
+            ops.ln_bwd(dH, x_in, r["mean3"], r["rstd3"], self.p(pfx + "ln_2.weight"), dx, dx, dxb,
+                       self.pg(pfx + "ln_2.weight"), self.pg(pfx + "ln_2.bias"), self.pg(nb), dropout_p=pd_res,
+                       seed=seed, offset=s_res2 if has_x else s_res1)
+            # ---- cross attention backward ----
+            if has_x:
+                self._wgrad_gemm(r["ctx2"], dxb, self.pg(pfx + "crossattention.c_proj.weight"), H, H, M)
+                self._dgrad_gemm(dxb, self.pb(pfx + "crossattention.c_proj.weight"), dH, M, H, H)
+                dq_acc.zero_()
+                ops.attn_bwd(r["q2"], r["kv2"], r["kv2"], r["ctx2"], dH, r["lse2"], delta, dq_acc, dkv2, dkv2,
+                             B=B, nh=nh, Tq=T, Tk=Tc, q_col0=0, k_col0=0, v_col0=H, dk_col0=0, dv_col0=H,
+                             causal=False, dropout_p=pd_attn, seed=seed, offset=s_xattn)
+                ops.cast_f32_bf16_2d(dq_acc, dq2, self.pg(pfx + "crossattention.q_attn.bias"))
+                ops.colsum_bf16(dkv2, self.pg(pfx + "crossattention.c_attn.bias"))
+                self._wgrad_gemm(r["a2"], dq2, self.pg(pfx + "crossattention.q_attn.weight"), H, H, M)
+                self._wgrad_gemm(sv["enc"], dkv2, self.pg(pfx + "crossattention.c_attn.weight"), H, 2 * H, Mc)
+                self._dgrad_gemm(dq2, self.pb(pfx + "crossattention.q_attn.weight"), dH, M, H, H)
+                # d enc accumulates over layers (the caption embeddings feed every block, model.py:521)
+                self._dgrad_gemm(dkv2, self.pb(pfx + "crossattention.c_attn.weight"), denc, Mc, H, 2 * H,
+                                 residual=denc)
+                ops.ln_bwd(dH, r["x1"], r["mean2"], r["rstd2"], self.p(pfx + "ln_cross_attn.weight"), dx, dx, dxb,
+                           self.pg(pfx + "ln_cross_attn.weight"), self.pg(pfx + "ln_cross_attn.bias"),
+                           self.pg(pfx + "attn.c_proj.bias"), dropout_p=pd_res, seed=seed, offset=s_res1)
+            # ---- self attention backward ----
+            self._wgrad_gemm(r["ctx"], dxb, self.pg(pfx + "attn.c_proj.weight"), H, H, M)
+            self._dgrad_gemm(dxb, self.pb(pfx + "attn.c_proj.weight"), dH, M, H, H)
+            dq_acc.zero_()
+            qkv = r["qkv"]
+            ops.attn_bwd(qkv, qkv, qkv, r["ctx"], dH, r["lse1"], delta, dq_acc, dqkv, dqkv, B=B, nh=nh, Tq=T, Tk=T,
+                         q_col0=0, k_col0=H, v_col0=2 * H, dk_col0=H, dv_col0=2 * H, causal=True,
+                         kv_lens=sv["kv_lens"], dropout_p=pd_attn, seed=seed, offset=s_attn)
+            gb = self.pg(pfx + "attn.c_attn.bias")
+            ops.cast_f32_bf16_2d(dq_acc, dqkv[:, :H], gb[:H])
+            ops.colsum_bf16(dqkv[:, H:], gb[H:], rows=M, N=2 * H, ld=3 * H)
+            self._wgrad_gemm(r["a1"], dqkv, self.pg(pfx + "attn.c_attn.weight"), H, 3 * H, M)
+            self._dgrad_gemm(dqkv, self.pb(pfx + "attn.c_attn.weight"), dH, M, H, 3 * H)
+            if l > 0:
+                prev = "transformer.h.%d." % (l - 1)
+                ops.ln_bwd(dH, r["x"], r["mean1"], r["rstd1"], self.p(pfx + "ln_1.weight"), dx, dx, dxb,
+                           self.pg(pfx + "ln_1.weight"), self.pg(pfx + "ln_1.bias"),
+                           self.pg(prev + "mlp.c_proj.bias"), dropout_p=pd_res, seed=seed,
+                           offset=site0 + 8 * (l - 1) + 5)
+            else:
+                ops.ln_bwd(dH, r["x"], r["mean1"], r["rstd1"], self.p(pfx + "ln_1.weight"), dx, dx, None,
+                           self.pg(pfx + "ln_1.weight"), self.pg(pfx + "ln_1.bias"), None)
+        # ---- embedding backward (model.py:459, 500-506) ----
+        ops.embed_bwd(dx, sv["ids"], sv["tts"], sv["pos"], self.pg("transformer.wte.weight"),
+                      self.pg("transformer.wpe.weight"), T=T, past_len=sv["past_len"], dropout_p=pd_embd,
+                      seed=seed, offset=site0)
+        if denc is not None:
+            ops.embed_bwd(denc, sv["cap"], None, None, self.pg("transformer.wte.weight"), None, T=Tc)
+        skip = () if sv["enc"] is not None else ("crossattention.", "ln_cross_attn.")
+        self.store.bind_grads(skip)

@@ -19,8 +19,8 @@ def _ptr(t):
 
 
 def gemm(a, b, d, *, M, N, K, a_major=L.ERGM_MAJOR_K, b_major=L.ERGM_MAJOR_MN, lda=None, ldb=None,
-         ldd=None, bias=None, residual=None, ldr=None, preact=None, epilogue=0, split_k=1, block_n=0,
-         dropout_p=0.0, seed=0, offset=0):
+         ldd=None, bias=None, residual=None, ldr=None, preact=None, gelu_grad_of=None, epilogue=0, split_k=1,
+         block_n=0, dropout_p=0.0, seed=0, offset=0):
     """D[M,N] = epilogue(A * B).  a/b bf16, d bf16 or fp32.  See include/ergm_b200.h."""
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     args = L.GemmArgs()
@@ -41,6 +41,9 @@ def gemm(a, b, d, *, M, N, K, a_major=L.ERGM_MAJOR_K, b_major=L.ERGM_MAJOR_MN, l
         epilogue |= L.EPI_RESIDUAL
     if preact is not None:
         epilogue |= L.EPI_PREACT
+    if gelu_grad_of is not None:  # multiply by gelu_new'(saved pre-activation)
+        args.preact = gelu_grad_of.data_ptr()
+        epilogue |= L.EPI_GELU_GRAD
     if dropout_p > 0.0:
         epilogue |= L.EPI_DROPOUT
     args.epilogue = epilogue
@@ -135,6 +138,17 @@ def attn_fwd(q, k, v, out, lse, *, B, nh, Tq, Tk, q_col0=0, k_col0=0, v_col0=0, 
     _call("ergm_attn_fwd", q.data_ptr(), q.stride(0), q_col0, k.data_ptr(), k.stride(0), k_col0, v.data_ptr(),
           v.stride(0), v_col0, out.data_ptr(), out.stride(0), _p(lse), _p(kv_lens), B, nh, Tq, Tk, 64, int(causal),
           causal_off, dropout_p, seed, offset)
+
+
+def attn_bwd(q, k, v, out, dout, lse, delta, dq_accum, dk, dv, *, B, nh, Tq, Tk, q_col0=0, k_col0=0, v_col0=0,
+             dk_col0=0, dv_col0=0, causal=True, causal_off=None, kv_lens=None, dropout_p=0.0, seed=0, offset=0):
+    if causal_off is None:
+        causal_off = Tk - Tq
+    _call("ergm_attn_bwd", q.data_ptr(), q.stride(0), q_col0, k.data_ptr(), k.stride(0), k_col0, v.data_ptr(),
+          v.stride(0), v_col0, out.data_ptr(), out.stride(0), dout.data_ptr(), dout.stride(0), lse.data_ptr(),
+          delta.data_ptr(), dq_accum.data_ptr(), dq_accum.stride(0), dk.data_ptr(), dk.stride(0), dk_col0,
+          dv.data_ptr(), dv.stride(0), dv_col0, _p(kv_lens), B, nh, Tq, Tk, 64, int(causal), causal_off,
+          dropout_p, seed, offset)
 
 
 def ce_fwd(logits, labels, lse, row_loss, sums, *, T, V):

@@ -30,6 +30,11 @@ extern "C" {
 /* library / device probes (no compute) */
 int ergm_abi_version(void);
 int ergm_device_sm_count(void);
+/* Dropout masks are Philox functions of (seed + *step, offset, element); the
+ * step counter lives in device memory so that CUDA-graph replays draw fresh
+ * masks.  NULL (default) disables the indirection.                          */
+int ergm_set_rng_step_ptr(const uint64_t* dev_ptr);
+int ergm_rng_step_advance(uint64_t* dev_ptr, uint64_t inc, void* stream);
 
 /* ------------------------------------------------------------------------ */
 /* GEMM: D[M,N] = epilogue(A[M,K] * B[K,N])  — bf16 operands, fp32 accumulate
@@ -128,6 +133,18 @@ int ergm_attn_fwd(const void* q, int64_t ld_q, int q_col0, const void* k, int64_
                   float* lse, const int* kv_lens, int B, int nh, int Tq, int Tk, int head_dim,
                   int causal, int causal_off, float dropout_p, uint64_t seed, uint64_t offset,
                   void* stream);
+
+/* Backward of ergm_attn_fwd: recomputes P from lse; dq_accum (fp32, pre-zeroed,
+ * [B*Tq, ld_dq]) is accumulated with red.add across key blocks; dk / dv are
+ * written (bf16) at [B*Tk, ld] column offsets dk_col0 / dv_col0 (+64h);
+ * delta ([B,nh,Tq] scratch) receives rowsum(dO * O).                         */
+int ergm_attn_bwd(const void* q, int64_t ld_q, int q_col0, const void* k, int64_t ld_k,
+                  int k_col0, const void* v, int64_t ld_v, int v_col0, const void* out,
+                  int64_t ld_out, const void* dout, int64_t ld_do, const float* lse, float* delta,
+                  float* dq_accum, int64_t ld_dq, void* dk, int64_t ld_dk, int dk_col0, void* dv,
+                  int64_t ld_dv, int dv_col0, const int* kv_lens, int B, int nh, int Tq, int Tk,
+                  int head_dim, int causal, int causal_off, float dropout_p, uint64_t seed,
+                  uint64_t offset, void* stream);
 
 /* ------------------------------------------------------------------------ */
 /* Token cross-entropy over LM-head logits with the reference's shift and     */
