@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""Benchmark of the ERGM hot path on B200 — contract: see the task description / DESIGN.md §Measurement.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+step      = one teacher-forced training step (forward + backward + AdamW) of ERGM GPT-2 small on a
+            synthetic MELD-shaped batch, B=32 x T=256 per GPU (BASELINE.json configs[1]; weak scaling).
+value     = training tokens/s (B*T*N / step time) with inputs already resident in HBM (CUDA-graph replay).
+e2e       = same metric through the public API ergm_b200.trainer.GraphedTrainStep with HOST (pinned)
+            batches: H2D copy of the step's inputs + D2H read of the loss inside the timed region.
+roofline  = dominant kernel (gemm_bf16_kernel, tcgen05): algorithmic GEMM FLOPs / CUDA-event time of
+            those launches, against the measured bf16 peak in MEASURED_PEAKS.json.
+cpu_baseline / --impl reference = the oracle port (oracle/ergm_oracle.py, a restatement bit-identical
+            to the reference model) timed on the host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "train_tokens_per_s"
+UNIT = "tokens/s"
+B_PER_GPU, SEQ = 32, 256
+VOCAB = 50260
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+def train_flops_per_token(H, L, V, T, Tc, caption=True):
+    """Algorithmic FLOPs (multiply-add = 2) per token of one training step = 3 x forward
+    (SURVEY.md §8d): GEMMs L*(24 or 32)H^2 + 2HV, attention L*(2TH [+4TcH])."""
+    per_layer = (32 if caption else 24) * H * H
+    attn = L * (2 * T * H + (4 * Tc * H if caption else 0))
+    fwd = L * per_layer + 2 * H * V + attn
+    return 3 * fwd, 3 * (L * per_layer + 2 * H * V)
+
+
+def gemm_flops(info):
+    M, N, K = info[0], info[1], info[2]
+    return 2.0 * M * N * K
+
+
+def build(device, n_layer=12, n_embd=768, n_head=12, dropout=0.1, seed=0):
+    from transformers import GPT2Config
+    from ergm_b200.model import GPT2LMHeadModel
+    torch.manual_seed(seed)
+    cfg = GPT2Config(vocab_size=VOCAB, n_embd=n_embd, n_layer=n_layer, n_head=n_head,
+                     attn_pdrop=dropout, resid_pdrop=dropout, embd_pdrop=dropout)
+    m = GPT2LMHeadModel(cfg).to(device)
+    return m.train()
+
+
+def host_batch(B, T, seed, pin=True):
+    from oracle import synthetic
+    b = synthetic.make_batch(B, T, seed=seed)
+    out = {k: b[k] for k in ("input_ids", "token_type_ids", "labels", "emotion_labels", "caption_ids", "imgs", "auds")}
+    out["imgs"] = out["imgs"][:, 0].contiguous()
+    if pin:
+        out = {k: v.pin_memory() for k, v in out.items()}
+    return out
+
+
+def cpu_reference_run(steps, warmup, B=2, T=SEQ, threads=None):
+    """fwd + bwd + AdamW of the oracle port on the host cores (fp32, dropout omitted: the oracle is the
+    p=0 / eval restatement; dropout is <1% of CPU time).  Returns (tokens/s, ms/step, threads)."""
+    from oracle import ergm_oracle as O
+    from oracle import synthetic
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cfg = O.OracleConfig()
+    sd = {k: v.clone().requires_grad_(True) for k, v in O.init_state_dict(cfg, seed=0).items() if k != "lm_head.weight"}
+    sd["lm_head.weight"] = sd["transformer.wte.weight"]
+    opt = torch.optim.AdamW([v for k, v in sd.items() if k != "lm_head.weight"], lr=2e-5)
+    b = synthetic.make_batch(B, T, seed=1234)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        o = O.forward(sd, cfg, b["input_ids"], b["token_type_ids"], b["labels"], b["emotion_labels"],
+                      b["imgs"], b["auds"], b["caption_ids"])
+        o["loss"].backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    return B * T / (ms / 1e3), ms, threads
+
+
+# ------------------------------------------------------------------------------------------
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    B = 2
+    tps, ms, threads = cpu_reference_run(args.steps, args.warmup, B=B)
+    sample = "oracle port fwd+bwd+AdamW, GPT-2 small caption mode, B=%d x T=%d per step (bounded sample of the B=32 step)" % (B, SEQ)
+    line = {"impl": "reference", "metric": METRIC, "value": tps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "ERGM GPT-2 small teacher-forced training step (fwd+bwd+AdamW), caption mode, "
+                                   "synthetic MELD-shaped, CPU sample B=%d T=%d" % (B, SEQ)},
+            "cpu_baseline": {"value": tps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": tps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def bench_generation(model, device, B=64, prompt=128, new=64, reps=3):
+    """BASELINE config 4: greedy decode, ragged prompts 64..128, 64 new tokens, paged KV."""
+    from oracle import synthetic
+    from ergm_b200 import generation
+    g = torch.Generator().manual_seed(7)
+    b = synthetic.make_batch(B, prompt, seed=99, ragged=False)
+    lens = torch.randint(prompt // 2, prompt + 1, (B,), generator=g)
+    ids, tt, cap = b["input_ids"].to(device), b["token_type_ids"].to(device), b["caption_ids"].to(device)
+    model.eval()
+    res = {}
+    for mode, capt in (("nocaption", None), ("caption", cap)):
+        times = []
+        for r in range(reps + 1):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = generation.generate(model, ids, tt, max_new_tokens=new, eos_token_id=None, sp2_id=50259,
+                                      caption_ids=capt, prompt_lens=lens)
+            e1.record()
+            torch.cuda.synchronize()
+            if r > 0:
+                times.append(e0.elapsed_time(e1))
+        ms = statistics.median(times)
+        res[mode] = {"gen_tokens_per_s": B * new / (ms / 1e3), "ms_total": ms, "batch": B, "new_tokens": new}
+    # per-token latency: time graph replays of the decode step alone
+    out, st = generation.generate(model, ids, tt, max_new_tokens=new, sp2_id=50259, prompt_lens=lens, return_state=True)
+    if st.graph is not None:
+        st.step.zero_()
+        st.seq_lens.copy_(lens.to(device).int())
+        lat = []
+        for _ in range(new - 2):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); st.graph.replay(); e1.record()
+            torch.cuda.synchronize()
+            lat.append(e0.elapsed_time(e1))
+        p50 = statistics.median(lat)
+        eng = model.engine
+        H, L, V = eng.H, eng.L, eng.V
+        ctx = float(lens.float().mean()) + new / 2
+        bytes_step = 2 * (12 * L * H * H + V * H) + B * (2 * L * ctx * H * 2)
+        res["decode_step"] = {"p50_ms_per_token": p50, "tokens_per_s_steady": B / (p50 / 1e3),
+                              "algorithmic_bytes_per_step": bytes_step,
+                              "hbm_gbs_achieved": bytes_step / (p50 / 1e3) / 1e9,
+                              "hbm_frac_of_measured": bytes_step / (p50 / 1e3) / 1e9 / peaks()["hbm"]}
+    model.train()
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ergm_b200")
+    ap.add_argument("--no-gen", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--dropout", type=float, default=0.1)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    import torch.distributed as dist
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from ergm_b200 import ops
+    from ergm_b200.optim import FusedAdamW
+    from ergm_b200.trainer import GraphedTrainStep
+    pk = peaks()
+
+    model = build(device, dropout=args.dropout)
+    opt = FusedAdamW(model, lr=2e-5)
+    dp = None
+    if world > 1:
+        from ergm_b200.parallel import DataParallel
+        dp = DataParallel(model)
+    step = GraphedTrainStep(model, opt, dp=dp, use_graph=not args.no_graph)
+    batch = host_batch(B_PER_GPU, SEQ, seed=1234 + rank)
+    H, L = model.config.n_embd, model.config.n_layer
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (first call captures the graph) ----
+    for _ in range(args.warmup):
+        loss = step(batch)
+    key, st = step.copy_in(batch)
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    # ---- timed: device-resident inputs ----
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step.run_device(key, st)
+    e1.record()
+    barrier()
+    ms_dev = e0.elapsed_time(e1) / args.steps
+    # ---- timed: end to end through the public API with host batches ----
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(batch)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+    clk = clocks.stop()
+    t = torch.tensor([ms_dev, ms_e2e], device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = float(t[0]), float(t[1])
+    tokens = B_PER_GPU * SEQ * world
+    value = tokens / (ms_dev / 1e3)
+    e2e_value = tokens / (ms_e2e / 1e3)
+
+    # ---- roofline of the dominant kernel: CUDA events around every GEMM launch of two eager steps ----
+    roof = None
+    if rank == 0:
+        eager = GraphedTrainStep(model, opt, dp=None, use_graph=False) if world == 1 else None
+        if eager is not None:
+            k2, s2 = eager.copy_in(batch)
+            eager.run_device(k2, s2)
+            torch.cuda.synchronize()
+            ops.PROFILE = []
+            for _ in range(2):
+                eager.run_device(k2, s2)
+            torch.cuda.synchronize()
+            prof, ops.PROFILE = ops.PROFILE, None
+            g_ms = sum(a.elapsed_time(b) for n, i, a, b in prof if n == "ergm_gemm_bf16") / 2
+            g_fl = sum(gemm_flops(i) for n, i, a, b in prof if n == "ergm_gemm_bf16") / 2
+            n_gemm = sum(1 for n, i, a, b in prof if n == "ergm_gemm_bf16") // 2
+            by = {}
+            for n, i, a, b in prof:
+                by[n] = by.get(n, 0.0) + a.elapsed_time(b) / 2
+            achieved = g_fl / (g_ms / 1e3) / 1e12
+            roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": achieved,
+                    "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sust"],
+                    "peak_source": pk["src"] + " (sustained bf16)", "traffic": None,
+                    "gemm_launches_per_step": n_gemm, "gemm_ms_per_step": g_ms, "gemm_flops_per_step": g_fl,
+                    "avg_launch_us": 1e3 * g_ms / max(n_gemm, 1),
+                    "eager_ms_by_entry_point": {k: round(v, 3) for k, v in sorted(by.items(), key=lambda kv: -kv[1])}}
+            step.eng.set_rng_step_tensor(step.rng_step)
+    fl_tok, gemm_fl_tok = train_flops_per_token(H, L, VOCAB, SEQ, SEQ, caption=True)
+    model_tf = value / world * fl_tok / 1e12
+
+    gen = None
+    if rank == 0 and not args.no_gen:
+        try:
+            gen = bench_generation(model, device)
+        except Exception as e:  # generation is a secondary line; never lose the training number
+            gen = {"error": "%s: %s" % (type(e).__name__, e)}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        tps, ms_cpu, threads = cpu_reference_run(steps=2, warmup=1, B=2)
+        cpu = {"value": tps, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "oracle port fwd+bwd+AdamW, B=2 x T=256 caption mode, 2 timed steps (%.0f ms/step)" % ms_cpu}
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "ERGM GPT-2 small (152.8M params, V=50260) teacher-forced training step: "
+                                       "fwd + bwd + AdamW, caption mode (cross-attention) + img/aud fusion, "
+                                       "dropout %.2f, B=%d x T=%d per GPU, synthetic MELD-shaped, random init"
+                                       % (args.dropout, B_PER_GPU, SEQ),
+                           "per_gpu_batch": B_PER_GPU, "seq_len": SEQ, "parallelism": "dp%d" % world,
+                           "l2": "no flush needed: the step streams >5 GB of activations/weights/grads per "
+                                 "iteration, far above the 126 MB L2",
+                           "cuda_graph": not args.no_graph},
+                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
+                        "h2d_bytes_per_step": step.h2d_bytes * world, "d2h_bytes_per_step": 20 * world,
+                        "api": "ergm_b200.trainer.GraphedTrainStep(model, FusedAdamW)(pinned_host_batch) -> loss"},
+                "gpu_launches": step.launches_per_step * args.steps,
+                "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+                "model_tflops_per_gpu": model_tf, "model_flops_per_token": fl_tok,
+                "mfu_of_measured_sustained": model_tf / pk["tf_sust"], "last_loss": loss,
+                "generation": gen}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

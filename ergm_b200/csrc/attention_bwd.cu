@@ -289,7 +289,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 // delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]   (one warp per row of the [B*Tq, nh*64] matrices)
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ dout, int64_t ld_do,
-                  const __nv_bfloat16* __restrict__ out, int64_t ld_o, float* __restrict__ delta,
+                  const __nv_bfloat16* __restrict__ out, int64_t ld_o,
+                  const float* __restrict__ out_f32, float* __restrict__ delta,
                   int rows, int Tq, int nh) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
@@ -302,9 +303,15 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ dout, int64_t ld_do,
     if (h < nh) {
       const int col = h * 64 + (lane & 15) * 4;
       const uint2 a = *reinterpret_cast<const uint2*>(dout + (int64_t)row * ld_do + col);
-      const uint2 o = *reinterpret_cast<const uint2*>(out + (int64_t)row * ld_o + col);
-      const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), o0 = unpack_bf16x2(o.x), o1 = unpack_bf16x2(o.y);
-      s = a0.x * o0.x + a0.y * o0.y + a1.x * o1.x + a1.y * o1.y;
+      const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y);
+      if (out_f32) {  // un-rounded forward output: keeps sum_j dS_ij = 0 to fp32 accuracy
+        const float4 o = *reinterpret_cast<const float4*>(out_f32 + (int64_t)row * (nh * 64) + col);
+        s = a0.x * o.x + a0.y * o.y + a1.x * o.z + a1.y * o.w;
+      } else {
+        const uint2 o = *reinterpret_cast<const uint2*>(out + (int64_t)row * ld_o + col);
+        const float2 o0 = unpack_bf16x2(o.x), o1 = unpack_bf16x2(o.y);
+        s = a0.x * o0.x + a0.y * o0.y + a1.x * o1.x + a1.y * o1.y;
+      }
     }
 #pragma unroll
     for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
@@ -318,7 +325,7 @@ using namespace ergm;
 
 extern "C" int ergm_attn_bwd(const void* q, int64_t ld_q, int q_col0, const void* k, int64_t ld_k,
                              int k_col0, const void* v, int64_t ld_v, int v_col0, const void* out,
-                             int64_t ld_out, const void* dout, int64_t ld_do, const float* lse,
+                             int64_t ld_out, const float* out_f32, const void* dout, int64_t ld_do, const float* lse,
                              float* delta, float* dq_accum, int64_t ld_dq, void* dk, int64_t ld_dk,
                              int dk_col0, void* dv, int64_t ld_dv, int dv_col0, const int* kv_lens,
                              int B, int nh, int Tq, int Tk, int head_dim, int causal, int causal_off,
@@ -332,7 +339,7 @@ extern "C" int ergm_attn_bwd(const void* q, int64_t ld_q, int q_col0, const void
   cudaStream_t s = (cudaStream_t)stream;
   attn_delta_kernel<<<(B * Tq + 7) / 8, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dout), ld_do,
                                                     reinterpret_cast<const __nv_bfloat16*>(out), ld_out,
-                                                    delta, B * Tq, Tq, nh);
+                                                    out_f32, delta, B * Tq, Tq, nh);
   CUtensorMap tq, tk, tv, tdo;
   int rc;
   if ((rc = encode_tmap_3d(&tq, q, 2, (uint64_t)(q_col0 + nh * 64), (uint64_t)Tq, (uint64_t)B,

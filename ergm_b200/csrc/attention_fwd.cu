@@ -28,6 +28,7 @@ constexpr int AT_SMEM = AT_TILE /*Q*/ + 4 * AT_TILE /*K,V x2*/ + 2 * AT_TILE /*P
 struct AttnFwdParams {
   __nv_bfloat16* out;  // [B*Tq, ld_out], head h at columns [h*64, h*64+64)
   float* lse;          // [B, nh, Tq]
+  float* out_f32;      // nullable [B*Tq, nh*64]: un-rounded context, used by backward's delta
   const int* kv_lens;  // nullable [B]: keys >= kv_lens[b] are masked
   int64_t ld_out;
   int Tq, Tk, nh;
@@ -208,6 +209,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                                    pack_bf16x2(o[i + 4] * inv, o[i + 5] * inv), pack_bf16x2(o[i + 6] * inv, o[i + 7] * inv));
         *reinterpret_cast<uint4*>(op + i) = u;
       }
+      if (p.out_f32) {
+        float* of = p.out_f32 + ((int64_t)b * p.Tq + qi) * (p.nh * AT_D) + h * AT_D;
+#pragma unroll
+        for (int i = 0; i < AT_D; i += 4)
+          *reinterpret_cast<float4*>(of + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
+      }
       if (p.lse) p.lse[((int64_t)b * p.nh + h) * p.Tq + qi] = (m == -INFINITY ? 0.f : m) * p.scale + logf(l);
     }
   }
@@ -222,7 +229,7 @@ using namespace ergm;
 
 extern "C" int ergm_attn_fwd(const void* q, int64_t ld_q, int q_col0, const void* k, int64_t ld_k,
                              int k_col0, const void* v, int64_t ld_v, int v_col0, void* out,
-                             int64_t ld_out, float* lse, const int* kv_lens, int B, int nh, int Tq,
+                             int64_t ld_out, float* out_f32, float* lse, const int* kv_lens, int B, int nh, int Tq,
                              int Tk, int head_dim, int causal, int causal_off, float dropout_p,
                              uint64_t seed, uint64_t offset, void* stream) {
   if (!q || !k || !v || !out || B <= 0 || nh <= 0 || Tq <= 0 || Tk <= 0) return ERGM_ERR_ARG;
@@ -242,7 +249,7 @@ extern "C" int ergm_attn_fwd(const void* q, int64_t ld_q, int q_col0, const void
     return rc;
   AttnFwdParams p;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
-  p.lse = lse; p.kv_lens = kv_lens; p.ld_out = ld_out;
+  p.lse = lse; p.out_f32 = out_f32; p.kv_lens = kv_lens; p.ld_out = ld_out;
   p.Tq = Tq; p.Tk = Tk; p.nh = nh;
   p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
   p.causal_off = causal_off;

@@ -16,7 +16,9 @@ constexpr int ROW_WARPS = 8;  // warps (rows in flight) per CTA
 struct EmbedFwdParams {
   const int64_t* ids;
   const int64_t* tts;       // nullable
-  const int64_t* pos_ids;   // nullable, [T] (shared by the batch) when given
+  const int64_t* pos_ids;   // nullable; pos = pos_ids[b * pos_stride_b + t] (stride 0: shared [T])
+  int64_t pos_stride_b;
+  const int* past_lens;     // nullable: per-sequence past length (decode with ragged prompts)
   const float* wte;
   const float* wpe;
   const float* imgs;        // nullable, [B, ld_img]
@@ -39,7 +41,8 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) embed_fuse_fwd_kernel(const Em
     const int b = row / p.T, t = row - b * p.T;
     const int64_t id = p.ids[row];
     const int64_t tt = p.tts ? p.tts[row] : -1;
-    const int64_t pos = p.pos_ids ? p.pos_ids[t] : (int64_t)(p.past_len + t);
+    const int64_t pos = p.pos_ids ? p.pos_ids[b * p.pos_stride_b + t]
+                                  : (int64_t)((p.past_lens ? p.past_lens[b] : p.past_len) + t);
     if (id < 0 || id >= p.vocab || pos < 0 || pos >= p.n_pos || (p.tts && (tt < 0 || tt >= p.vocab))) {
       if (lane == 0) *p.err_flag = 1;
       continue;
@@ -94,7 +97,8 @@ struct EmbedBwdParams {
   const float* dh;          // [rows, H]
   const int64_t* ids;       // nullable
   const int64_t* tts;       // nullable
-  const int64_t* pos_ids;   // nullable ([T]); positions used only when dwpe != null
+  const int64_t* pos_ids;   // nullable; positions used only when dwpe != null
+  int64_t pos_stride_b;
   float* dwte;
   float* dwpe;              // nullable
   float* dimgs;             // nullable [B, H]  (+= dh[b,0])
@@ -134,7 +138,7 @@ __global__ void embed_bwd_kernel(const EmbedBwdParams p_in) {
     int64_t idx[3];
     idx[0] = p.ids ? p.ids[row] : -1;
     idx[1] = p.tts ? p.tts[row] : -1;
-    idx[2] = p.dwpe ? (p.pos_ids ? p.pos_ids[t] : (int64_t)(p.past_len + t)) : -1;
+    idx[2] = p.dwpe ? (p.pos_ids ? p.pos_ids[(row / p.T) * p.pos_stride_b + t] : (int64_t)(p.past_len + t)) : -1;
 #pragma unroll
     for (int s = 0; s < 3; ++s) {
       if (!tables[s]) continue;
@@ -162,7 +166,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ beta, __nv_bfloat16* __restrict__ y_bf16,
               float* __restrict__ y_f32, float* __restrict__ mean_out, float* __restrict__ rstd_out,
-              int rows, float eps) {
+              int rows, float eps, const int* __restrict__ row_idx) {
   constexpr int H = NV * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4 g[NV], bt[NV];
@@ -172,7 +176,8 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
     bt[i] = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * i);
   }
   for (int row = blockIdx.x * ROW_WARPS + warp; row < rows; row += gridDim.x * ROW_WARPS) {
-    const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)row * H);
+    const int src_row = row_idx ? row_idx[row] : row;  // optional gather (last prompt token per sequence)
+    const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)src_row * H);
     float4 v[NV];
     float s = 0.f;
 #pragma unroll
@@ -412,14 +417,15 @@ static int row_grid(int rows) {
 using namespace ergm;
 
 extern "C" int ergm_embed_fuse_fwd(const int64_t* ids, const int64_t* token_type_ids,
-                                   const int64_t* position_ids, const float* wte, const float* wpe,
+                                   const int64_t* position_ids, int64_t pos_stride_b,
+                                   const int* past_lens, const float* wte, const float* wpe,
                                    const float* imgs, int64_t ld_img, const float* auds,
                                    int64_t ld_aud, float* out, int B, int T, int H, int past_len,
                                    int vocab, int n_pos, float dropout_p, uint64_t seed,
                                    uint64_t offset, int* err_flag, void* stream) {
   if (!ids || !wte || !wpe || !out || !err_flag || B <= 0 || T <= 0 || H % 128) return ERGM_ERR_ARG;
   if ((imgs && ld_img % 4) || (auds && ld_aud % 4)) return ERGM_ERR_ARG;
-  EmbedFwdParams p{ids, token_type_ids, position_ids, wte, wpe, imgs, auds, out, ld_img, ld_aud,
+  EmbedFwdParams p{ids, token_type_ids, position_ids, pos_stride_b, past_lens, wte, wpe, imgs, auds, out, ld_img, ld_aud,
                    B, T, H, past_len, vocab, n_pos,
                    make_site(seed, offset, dropout_p, (uint32_t)H), dropout_p > 0.f, err_flag};
   embed_fuse_fwd_kernel<<<row_grid(B * T), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
@@ -435,12 +441,12 @@ extern "C" int ergm_gather_rows_bf16(const int64_t* ids, const float* table, voi
 }
 
 extern "C" int ergm_embed_bwd(const float* dh, const int64_t* ids, const int64_t* token_type_ids,
-                              const int64_t* position_ids, float* dwte, float* dwpe, float* dimgs,
+                              const int64_t* position_ids, int64_t pos_stride_b, float* dwte, float* dwpe, float* dimgs,
                               float* dauds, int rows, int T, int H, int past_len, float dropout_p,
                               uint64_t seed, uint64_t offset, void* stream) {
   if (!dh || rows <= 0 || T <= 0 || H % 128 || H / 4 > 1024) return ERGM_ERR_ARG;
   if ((ids || token_type_ids) && !dwte) return ERGM_ERR_ARG;
-  EmbedBwdParams p{dh, ids, token_type_ids, position_ids, dwte, dwpe, dimgs, dauds, rows, T, H,
+  EmbedBwdParams p{dh, ids, token_type_ids, position_ids, pos_stride_b, dwte, dwpe, dimgs, dauds, rows, T, H,
                    past_len, 32, make_site(seed, offset, dropout_p, (uint32_t)H),
                    dropout_p > 0.f};
   const int threads = ((H / 4 + 31) / 32) * 32;
@@ -450,11 +456,11 @@ extern "C" int ergm_embed_bwd(const float* dh, const int64_t* ids, const int64_t
 
 extern "C" int ergm_ln_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16,
                            float* y_f32, float* mean, float* rstd, int rows, int H, float eps,
-                           void* stream) {
+                           const int* row_idx, void* stream) {
   if (!x || !gamma || !beta || rows <= 0 || H % 128) return ERGM_ERR_ARG;
   return dispatch_nv(H, [&](auto nv) {
     ln_fwd_kernel<decltype(nv)::value><<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd, rows, eps);
+        x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd, rows, eps, row_idx);
     return (int)cudaGetLastError();
   });
 }

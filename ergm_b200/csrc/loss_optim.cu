@@ -15,6 +15,7 @@ constexpr int CE_THREADS = 256;
 
 ERGM_DEVINL void online_merge(float& m, float& s, float m2, float s2) {
   const float mn = fmaxf(m, m2);
+  if (mn == -INFINITY) { s = 0.f; return; }  // both partials empty: exp(-inf - -inf) would be NaN
   s = s * __expf(m - mn) + s2 * __expf(m2 - mn);
   m = mn;
 }
@@ -48,8 +49,9 @@ template <bool F32>
 __global__ void __launch_bounds__(CE_THREADS)
 ce_fwd_kernel(const void* __restrict__ logits, int64_t ldl, const int64_t* __restrict__ labels,
               int T, int V, float* __restrict__ lse_out, float* __restrict__ row_loss,
-              float* __restrict__ sums /* [0]=loss sum, [1]=valid count */, int* err_flag) {
-  __shared__ float sm[CE_THREADS / 32], ss[CE_THREADS / 32];
+              float* __restrict__ sums /* [0]=loss sum, [1]=valid count */, int* err_flag,
+              const __nv_bfloat16* __restrict__ hn, const __nv_bfloat16* __restrict__ w, int H) {
+  __shared__ float sm[CE_THREADS / 32], ss[CE_THREADS / 32], st[CE_THREADS / 32];
   const int row = blockIdx.x;
   const int64_t tgt = shifted_target(labels, row, T);
   if (tgt == -100) {
@@ -77,18 +79,32 @@ ce_fwd_kernel(const void* __restrict__ logits, int64_t ldl, const int64_t* __res
     m = mn;
   }
   for (int c = nfull * 8 + threadIdx.x; c < V; c += CE_THREADS) online_merge(m, s, load1<F32>(rp, c), 1.f);
+  // Target logit from the fp32 dot product of the GEMM operands (the stored logits may be bf16-
+  // rounded; the loss must come from fp32 accumulation).
+  float tl = 0.f;
+  if (hn) {
+    const uint4* hr = reinterpret_cast<const uint4*>(hn + (int64_t)row * H);
+    const uint4* wr = reinterpret_cast<const uint4*>(w + tgt * H);
+    for (int c = threadIdx.x; c < H / 8; c += CE_THREADS) {
+      const uint4 a = hr[c], b = wr[c];
+      const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+      const float2 b0 = unpack_bf16x2(b.x), b1 = unpack_bf16x2(b.y), b2 = unpack_bf16x2(b.z), b3 = unpack_bf16x2(b.w);
+      tl += a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y + a3.x * b3.x + a3.y * b3.y;
+    }
+    tl = warp_sum(tl);
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
     online_merge(m, s, m2, s2);
   }
-  if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5] = m; ss[threadIdx.x >> 5] = s; }
+  if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5] = m; ss[threadIdx.x >> 5] = s; st[threadIdx.x >> 5] = tl; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    float M = sm[0], S = ss[0];
-    for (int w = 1; w < CE_THREADS / 32; ++w) online_merge(M, S, sm[w], ss[w]);
+    float M = sm[0], S = ss[0], TL = st[0];
+    for (int w = 1; w < CE_THREADS / 32; ++w) { online_merge(M, S, sm[w], ss[w]); TL += st[w]; }
     const float lse = M + logf(S);
-    const float loss = lse - load1<F32>(rp, (int)tgt);
+    const float loss = lse - (hn ? TL : load1<F32>(rp, (int)tgt));
     lse_out[row] = lse;
     row_loss[row] = loss;
     atomicAdd(sums, loss);
@@ -274,14 +290,18 @@ using namespace ergm;
 
 extern "C" int ergm_ce_fwd(const void* logits, int logits_is_f32, int64_t ldl, const int64_t* labels,
                            int rows, int T, int V, float* lse, float* row_loss, float* sums,
-                           int* err_flag, void* stream) {
+                           int* err_flag, const void* hn_bf16, const void* w_bf16, int H,
+                           void* stream) {
   if (!logits || !labels || !lse || !row_loss || !sums || !err_flag || rows <= 0 || T <= 0 || V <= 0)
     return ERGM_ERR_ARG;
   if (ldl % 8 || (reinterpret_cast<uintptr_t>(logits) & 15)) return ERGM_ERR_ARG;
+  if ((hn_bf16 != nullptr) != (w_bf16 != nullptr) || (hn_bf16 && H % 8)) return ERGM_ERR_ARG;
+  const __nv_bfloat16* hn = reinterpret_cast<const __nv_bfloat16*>(hn_bf16);
+  const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(w_bf16);
   if (logits_is_f32)
-    ce_fwd_kernel<true><<<rows, CE_THREADS, 0, (cudaStream_t)stream>>>(logits, ldl, labels, T, V, lse, row_loss, sums, err_flag);
+    ce_fwd_kernel<true><<<rows, CE_THREADS, 0, (cudaStream_t)stream>>>(logits, ldl, labels, T, V, lse, row_loss, sums, err_flag, hn, w, H);
   else
-    ce_fwd_kernel<false><<<rows, CE_THREADS, 0, (cudaStream_t)stream>>>(logits, ldl, labels, T, V, lse, row_loss, sums, err_flag);
+    ce_fwd_kernel<false><<<rows, CE_THREADS, 0, (cudaStream_t)stream>>>(logits, ldl, labels, T, V, lse, row_loss, sums, err_flag, hn, w, H);
   return (int)cudaGetLastError();
 }
 

@@ -136,7 +136,7 @@ class Engine:
     # ------------------------------------------------------------------
     def forward(self, input_ids, token_type_ids=None, labels=None, emotion_labels=None, imgs=None, auds=None,
                 caption_ids=None, position_ids=None, past_len=0, kv_lens=None, training=False, save=False,
-                want_logits=True, logits_fp32=False, dropout=None):
+                want_logits=True, logits_fp32=False, dropout=None, heads=True, gen_state=None, legacy_past=None):
         """Runs the full forward.  Returns a dict of device tensors (views into the workspace):
         logits [B,T,V] (bf16 or fp32, leading dim padded), emotion_logits [B,7], losses [5]
         (loss, lm_loss, emo_loss, 1/n_valid, 1/n_samples), hidden (bf16 ln_f output)."""
@@ -145,6 +145,8 @@ class Engine:
         cfg, H, nh, Lyr, I, V = self.cfg, self.H, self.nh, self.L, self.I, self.V
         B, T = input_ids.shape
         M = B * T
+        if legacy_past is not None:
+            past_len = legacy_past[0].shape[1]
         if T + past_len > self.n_pos and position_ids is None:
             raise ValueError("sequence length %d + past %d exceeds n_positions %d" % (T, past_len, self.n_pos))
         ws = self.ws_train if save else self.ws_eval
@@ -197,15 +199,30 @@ class Engine:
             self._fwd_gemm(a1, self.pb(pfx + "attn.c_attn.weight"), qkv, M, 3 * H, H,
                            bias=self.p(pfx + "attn.c_attn.bias"))
             ctx = ws.get(lname("ctx", l), (M, H), bf16)
+            ctx32 = ws.get(lname("ctx32", l), (M, H), f32) if save else None
             lse1 = ws.get(lname("lse1", l), (B, nh, T), f32)
-            ops.attn_fwd(qkv, qkv, qkv, ctx, lse1, B=B, nh=nh, Tq=T, Tk=T, q_col0=0, k_col0=H, v_col0=2 * H,
-                         causal=True, kv_lens=kv_lens, dropout_p=pd_attn, seed=seed, offset=s_attn)
-            kv_present.append(qkv)
+            if legacy_past is not None:
+                # legacy tuple cache (model.py:228-231): keys/values = cat(past, new); O(ctx) copy like the
+                # reference's torch.cat — the fast decode path is the paged cache in generation.py
+                kvf = torch.cat([legacy_past[l], qkv.view(B, T, 3 * H)[:, :, H:]], dim=1).contiguous()
+                Tk_all = past_len + T
+                kv2d = kvf.view(B * Tk_all, 2 * H)
+                ops.attn_fwd(qkv, kv2d, kv2d, ctx, lse1, B=B, nh=nh, Tq=T, Tk=Tk_all, q_col0=0, k_col0=0, v_col0=H,
+                             causal=True, causal_off=past_len, kv_lens=kv_lens)
+                kv_present.append(kvf)
+            else:
+                ops.attn_fwd(qkv, qkv, qkv, ctx, lse1, B=B, nh=nh, Tq=T, Tk=T, q_col0=0, k_col0=H, v_col0=2 * H,
+                             causal=True, kv_lens=kv_lens, dropout_p=pd_attn, seed=seed, offset=s_attn,
+                             out_f32=ctx32)
+                kv_present.append(qkv)
+            if gen_state is not None:
+                ops.kv_to_pages(qkv, gen_state.pool[l], gen_state.block_table, kv_lens, B=B, T=T, nh=nh,
+                                k_col0=H, v_col0=2 * H)
             x1 = ws.get(lname("x1", l), (M, H), f32) if save else x
             self._fwd_gemm(ctx, self.pb(pfx + "attn.c_proj.weight"), x1, M, H, H,
                            bias=self.p(pfx + "attn.c_proj.bias"), residual=x, dropout_p=pd_res, seed=seed,
                            offset=s_res1)
-            rec.update(x=x, a1=a1, mean1=mean1, rstd1=rstd1, qkv=qkv, ctx=ctx, lse1=lse1, x1=x1)
+            rec.update(x=x, a1=a1, mean1=mean1, rstd1=rstd1, qkv=qkv, ctx=ctx, ctx32=ctx32, lse1=lse1, x1=x1)
             # ---- cross attention over caption embeddings (model.py:311-329) ----
             x2 = x1
             if enc is not None:
@@ -217,18 +234,19 @@ class Engine:
                 q2 = ws.get(lname("q2", l), (M, H), bf16)
                 self._fwd_gemm(a2, self.pb(pfx + "crossattention.q_attn.weight"), q2, M, H, H,
                                bias=self.p(pfx + "crossattention.q_attn.bias"))
-                kv2 = ws.get(lname("kv2", l), (Mc, 2 * H), bf16)
+                kv2 = gen_state.kv2[l] if gen_state is not None else ws.get(lname("kv2", l), (Mc, 2 * H), bf16)
                 self._fwd_gemm(enc, self.pb(pfx + "crossattention.c_attn.weight"), kv2, Mc, 2 * H, H,
                                bias=self.p(pfx + "crossattention.c_attn.bias"))
                 ctx2 = ws.get(lname("ctx2", l), (M, H), bf16)
+                ctx2_32 = ws.get(lname("ctx2_32", l), (M, H), f32) if save else None
                 lse2 = ws.get(lname("lse2", l), (B, nh, T), f32)
                 ops.attn_fwd(q2, kv2, kv2, ctx2, lse2, B=B, nh=nh, Tq=T, Tk=Tc, q_col0=0, k_col0=0, v_col0=H,
-                             causal=False, dropout_p=pd_attn, seed=seed, offset=s_xattn)
+                             causal=False, dropout_p=pd_attn, seed=seed, offset=s_xattn, out_f32=ctx2_32)
                 x2 = ws.get(lname("x2", l), (M, H), f32) if save else x1
                 self._fwd_gemm(ctx2, self.pb(pfx + "crossattention.c_proj.weight"), x2, M, H, H,
                                bias=self.p(pfx + "crossattention.c_proj.bias"), residual=x1, dropout_p=pd_res,
                                seed=seed, offset=s_res2)
-                rec.update(a2=a2, mean2=mean2, rstd2=rstd2, q2=q2, kv2=kv2, ctx2=ctx2, lse2=lse2, x2=x2)
+                rec.update(a2=a2, mean2=mean2, rstd2=rstd2, q2=q2, kv2=kv2, ctx2=ctx2, ctx2_32=ctx2_32, lse2=lse2, x2=x2)
             # ---- MLP (model.py:331-334, 262-267) ----
             a3 = ws.get(lname("a3", l), (M, H), bf16)
             mean3 = ws.get(lname("mean3", l), (M,), f32)
@@ -245,6 +263,8 @@ class Engine:
             if save:
                 sv["layers"].append(rec)
             x = x3
+        if not heads:
+            return dict(x_final=x, kv_present=kv_present, B=B, T=T)
         # ---- final LN, heads, losses (model.py:578, 698-721) ----
         hn = ws.get("hn", (M, H), bf16)
         meanf = ws.get("meanf", (M,), f32)
@@ -272,7 +292,7 @@ class Engine:
         if labels is not None:
             lse = ws.get("ce_lse", (M,), f32)
             row_loss = ws.get("ce_row_loss", (M,), f32)
-            ops.ce_fwd(logits, labels, lse, row_loss, sums, T=T, V=V)
+            ops.ce_fwd(logits, labels, lse, row_loss, sums, T=T, V=V, hn=hn, w=self.pb("transformer.wte.weight"))
         out["loss_sums"] = sums
         out["losses"] = losses
         out["has_lm"] = labels is not None
@@ -304,7 +324,7 @@ class Engine:
         return feat
 
     # ------------------------------------------------------------------
-    def backward(self, grad_loss, accumulate=False):
+    def backward(self, grad_loss, accumulate=False, on_layer_done=None):
         """Hand-written backward of the whole path.  grad_loss: device fp32 scalar tensor (dLoss).
         Gradients are accumulated into the flat gradient buffer (zeroed first unless
         `accumulate`)."""
@@ -384,7 +404,7 @@ class Engine:
                 dq_acc.zero_()
                 ops.attn_bwd(r["q2"], r["kv2"], r["kv2"], r["ctx2"], dH, r["lse2"], delta, dq_acc, dkv2, dkv2,
                              B=B, nh=nh, Tq=T, Tk=Tc, q_col0=0, k_col0=0, v_col0=H, dk_col0=0, dv_col0=H,
-                             causal=False, dropout_p=pd_attn, seed=seed, offset=s_xattn)
+                             causal=False, dropout_p=pd_attn, seed=seed, offset=s_xattn, out_f32=r["ctx2_32"])
                 ops.cast_f32_bf16_2d(dq_acc, dq2, self.pg(pfx + "crossattention.q_attn.bias"))
                 ops.colsum_bf16(dkv2, self.pg(pfx + "crossattention.c_attn.bias"))
                 self._wgrad_gemm(r["a2"], dq2, self.pg(pfx + "crossattention.q_attn.weight"), H, H, M)
@@ -403,7 +423,7 @@ class Engine:
             qkv = r["qkv"]
             ops.attn_bwd(qkv, qkv, qkv, r["ctx"], dH, r["lse1"], delta, dq_acc, dqkv, dqkv, B=B, nh=nh, Tq=T, Tk=T,
                          q_col0=0, k_col0=H, v_col0=2 * H, dk_col0=H, dv_col0=2 * H, causal=True,
-                         kv_lens=sv["kv_lens"], dropout_p=pd_attn, seed=seed, offset=s_attn)
+                         kv_lens=sv["kv_lens"], dropout_p=pd_attn, seed=seed, offset=s_attn, out_f32=r["ctx32"])
             gb = self.pg(pfx + "attn.c_attn.bias")
             ops.cast_f32_bf16_2d(dq_acc, dqkv[:, :H], gb[:H])
             ops.colsum_bf16(dqkv[:, H:], gb[H:], rows=M, N=2 * H, ld=3 * H)
@@ -418,11 +438,17 @@ class Engine:
             else:
                 ops.ln_bwd(dH, r["x"], r["mean1"], r["rstd1"], self.p(pfx + "ln_1.weight"), dx, dx, None,
                            self.pg(pfx + "ln_1.weight"), self.pg(pfx + "ln_1.bias"), None)
+            if on_layer_done is not None:
+                # every gradient of layer l is final now: its mlp.c_proj.bias was completed earlier by
+                # layer l+1's ln_1 backward, and this layer's ln_1 backward only touched layer l-1's slot
+                on_layer_done(l)
         # ---- embedding backward (model.py:459, 500-506) ----
         ops.embed_bwd(dx, sv["ids"], sv["tts"], sv["pos"], self.pg("transformer.wte.weight"),
                       self.pg("transformer.wpe.weight"), T=T, past_len=sv["past_len"], dropout_p=pd_embd,
                       seed=seed, offset=site0)
         if denc is not None:
             ops.embed_bwd(denc, sv["cap"], None, None, self.pg("transformer.wte.weight"), None, T=Tc)
+        if on_layer_done is not None:
+            on_layer_done(-1)
         skip = () if sv["enc"] is not None else ("crossattention.", "ln_cross_attn.")
         self.store.bind_grads(skip)

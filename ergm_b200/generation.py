@@ -1,0 +1,207 @@
+"""KV-cached response generation for the drop-in model (BASELINE config 4).
+
+The reference decodes with one FULL forward per new token (main.py:253-282) and its model-side
+cache grows by torch.cat (model.py:228-236).  Here a request batch is prefetched once (fused
+attention over the right-padded prompts, K/V scattered into a paged pool, cross-attention K/V
+of the captions projected once), then every new token is ONE CUDA-graph replay of the decode
+step: embed -> L x [LN, QKV GEMM, paged one-query attention (+append), proj GEMM, (cross), MLP]
+-> ln_f -> LM head on B rows -> on-device arg-max / top-k sampling.  No host synchronisation
+happens until the generated ids are read back.
+"""
+import torch
+
+from . import _lib as L
+from . import ops
+from .engine import K_MAJOR
+
+PAGE = 16
+
+
+class GenState:
+    """Device state of one generation batch: paged K/V pool + block table per layer, cached
+    cross-attention K/V, per-sequence lengths / finished flags, output ids."""
+
+    def __init__(self, eng, B, max_ctx, Tc, max_new):
+        dev = eng.device
+        H, nh, Lyr = eng.H, eng.nh, eng.L
+        self.B, self.max_ctx, self.Tc, self.max_new = B, max_ctx, Tc, max_new
+        self.pages_per_seq = (max_ctx + PAGE - 1) // PAGE
+        n_pages = B * self.pages_per_seq
+        self.pool = [torch.zeros(n_pages, 2, nh, PAGE, 64, dtype=torch.bfloat16, device=dev) for _ in range(Lyr)]
+        self.block_table = torch.arange(n_pages, dtype=torch.int32, device=dev).view(B, self.pages_per_seq).contiguous()
+        self.kv2 = [torch.empty(B * Tc, 2 * H, dtype=torch.bfloat16, device=dev) for _ in range(Lyr)] if Tc else None
+        self.seq_lens = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.finished = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.next_ids = torch.zeros(B, 1, dtype=torch.int64, device=dev)
+        self.out_ids = torch.zeros(B, max_new, dtype=torch.int64, device=dev)
+        self.step = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.tt = None
+        self.logits = torch.empty(B, (eng.V + 63) // 64 * 64, dtype=torch.float32, device=dev)
+        self.graph = None
+
+    def kv_bytes(self):
+        return sum(p.numel() * 2 for p in self.pool) + (sum(k.numel() * 2 for k in self.kv2) if self.kv2 else 0)
+
+
+def _head_on_rows(eng, x, row_idx, logits):
+    """ln_f + tied LM head on selected rows (fp32 logits so the arg-max is not bf16-rounded)."""
+    ws = eng.ws_eval
+    n = row_idx.numel() if row_idx is not None else x.shape[0]
+    hn = ws.get("gen_hn", (n, eng.H), torch.bfloat16)
+    ops.ln_fwd(x, eng.p("transformer.ln_f.weight"), eng.p("transformer.ln_f.bias"), hn, None, None, None,
+               eng.cfg.layer_norm_epsilon, row_idx=row_idx)
+    ops.gemm(hn, eng.pb("transformer.wte.weight"), logits, M=n, N=eng.V, K=eng.H, a_major=K_MAJOR, b_major=K_MAJOR)
+
+
+def decode_step(eng, st, sample_kw):
+    """One token for every sequence of the batch; pure device work (CUDA-graph capturable)."""
+    H, nh, I, B = eng.H, eng.nh, eng.I, st.B
+    ws = eng.ws_eval
+    f32, bf16 = torch.float32, torch.bfloat16
+    eps = eng.cfg.layer_norm_epsilon
+    x = ws.get("dec_x", (B, H), f32)
+    ops.embed_fuse_fwd(st.next_ids, st.tt, None, eng.p("transformer.wte.weight"), eng.p("transformer.wpe.weight"),
+                       None, None, x, past_lens=st.seq_lens)
+    a = ws.get("dec_a", (B, H), bf16)
+    qkv = ws.get("dec_qkv", (B, 3 * H), bf16)
+    ctx = ws.get("dec_ctx", (B, H), bf16)
+    q2 = ws.get("dec_q2", (B, H), bf16)
+    g = ws.get("dec_g", (B, I), bf16)
+    for l in range(eng.L):
+        pfx = "transformer.h.%d." % l
+        ops.ln_fwd(x, eng.p(pfx + "ln_1.weight"), eng.p(pfx + "ln_1.bias"), a, None, None, None, eps)
+        eng._fwd_gemm(a, eng.pb(pfx + "attn.c_attn.weight"), qkv, B, 3 * H, H, bias=eng.p(pfx + "attn.c_attn.bias"))
+        ops.attn_decode_paged(qkv, st.pool[l], st.block_table, st.seq_lens, ctx, B=B, nh=nh, H=H)
+        eng._fwd_gemm(ctx, eng.pb(pfx + "attn.c_proj.weight"), x, B, H, H, bias=eng.p(pfx + "attn.c_proj.bias"),
+                      residual=x)
+        if st.kv2 is not None:
+            ops.ln_fwd(x, eng.p(pfx + "ln_cross_attn.weight"), eng.p(pfx + "ln_cross_attn.bias"), a, None, None,
+                       None, eps)
+            eng._fwd_gemm(a, eng.pb(pfx + "crossattention.q_attn.weight"), q2, B, H, H,
+                          bias=eng.p(pfx + "crossattention.q_attn.bias"))
+            ops.attn_decode_contig(q2, st.kv2[l], ctx, B=B, nh=nh, Tk=st.Tc, k_col0=0, v_col0=H)
+            eng._fwd_gemm(ctx, eng.pb(pfx + "crossattention.c_proj.weight"), x, B, H, H,
+                          bias=eng.p(pfx + "crossattention.c_proj.bias"), residual=x)
+        ops.ln_fwd(x, eng.p(pfx + "ln_2.weight"), eng.p(pfx + "ln_2.bias"), a, None, None, None, eps)
+        eng._fwd_gemm(a, eng.pb(pfx + "mlp.c_fc.weight"), g, B, I, H, bias=eng.p(pfx + "mlp.c_fc.bias"),
+                      epilogue=L.EPI_GELU)
+        eng._fwd_gemm(g, eng.pb(pfx + "mlp.c_proj.weight"), x, B, H, I, bias=eng.p(pfx + "mlp.c_proj.bias"),
+                      residual=x)
+    _head_on_rows(eng, x, None, st.logits)
+    ops.sample(st.logits, V=eng.V, step=st.step, out_ids=st.out_ids, next_ids=st.next_ids, finished=st.finished,
+               seq_lens=st.seq_lens, **sample_kw)
+    ops.int_add(st.step, 1)
+
+
+@torch.no_grad()
+def generate(model, input_ids, token_type_ids=None, max_new_tokens=64, do_sample=False, top_k=0, top_p=1.0,
+             temperature=1.0, eos_token_id=None, sp2_id=None, imgs=None, auds=None, caption_ids=None,
+             prompt_lens=None, seed=0, use_cuda_graph=True, return_state=False):
+    """input_ids [B, T] right-padded prompts, prompt_lens [B] their true lengths (default T).
+    Every generated token gets speaker type sp2_id (main.py:277-279).  Returns int64 [B,
+    max_new_tokens]; after a sequence emits eos it keeps emitting eos."""
+    if top_p < 1.0:
+        raise L.ErgmError("top-p sampling is a 'next' row (SURVEY.md §8f N2) and is not implemented yet; "
+                          "use greedy or top_k")
+    eng = model.engine
+    eng.ensure_params()
+    eng.store.refresh_shadow()
+    dev = eng.device
+    B, T = input_ids.shape
+    input_ids = input_ids.to(dev, torch.int64).contiguous()
+    if token_type_ids is not None:
+        token_type_ids = token_type_ids.to(dev, torch.int64).contiguous()
+    if prompt_lens is None:
+        lens = torch.full((B,), T, dtype=torch.int32, device=dev)
+    else:
+        lens = prompt_lens.to(dev, torch.int32).contiguous()
+    cap = caption_ids.to(dev, torch.int64).reshape(B, -1).contiguous() if caption_ids is not None else None
+    Tc = cap.shape[1] if cap is not None else 0
+    max_ctx = T + max_new_tokens
+    if max_ctx > eng.n_pos:
+        raise ValueError("prompt + max_new_tokens = %d exceeds n_positions = %d" % (max_ctx, eng.n_pos))
+    with torch.cuda.device(dev):
+        st = GenState(eng, B, max_ctx, Tc, max_new_tokens)
+        if sp2_id is not None:
+            st.tt = torch.full((B, 1), int(sp2_id), dtype=torch.int64, device=dev)
+        k = int(top_k) if do_sample else 0
+        sample_kw = dict(top_k=k, temperature=float(temperature), seed=int(seed),
+                         eos_id=int(eos_token_id) if eos_token_id is not None else -1)
+        # ---- prefill: fused attention over the padded prompts, K/V -> pages, cross K/V cached ----
+        out = eng.forward(input_ids, token_type_ids, None, None, imgs, auds, cap, None, kv_lens=lens,
+                          training=False, save=False, heads=False, gen_state=st)
+        st.seq_lens.copy_(lens)
+        last = (torch.arange(B, device=dev, dtype=torch.int32) * T + lens - 1).to(torch.int32)
+        _head_on_rows(eng, out["x_final"], last, st.logits)
+        ops.sample(st.logits, V=eng.V, step=st.step, out_ids=st.out_ids, next_ids=st.next_ids,
+                   finished=st.finished, seq_lens=None, **sample_kw)
+        ops.int_add(st.step, 1)
+        # ---- decode: one graph replay per token ----
+        n_steps = max_new_tokens - 1
+        if n_steps > 0:
+            if use_cuda_graph:
+                s = torch.cuda.Stream(device=dev)
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    # warm-up run outside capture is not possible without consuming a step, so the
+                    # first token is decoded eagerly and the graph replays the remaining ones
+                    decode_step(eng, st, sample_kw)
+                torch.cuda.current_stream().wait_stream(s)
+                if n_steps > 1:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        decode_step(eng, st, sample_kw)
+                    st.graph = g
+                    for _ in range(n_steps - 2):
+                        g.replay()
+            else:
+                for _ in range(n_steps):
+                    decode_step(eng, st, sample_kw)
+    if return_state:
+        return st.out_ids, st
+    return st.out_ids
+
+
+def legacy_cached_forward(model, input_ids, token_type_ids, pos, past_key_values, attention_mask, caption_ids,
+                          use_cache, return_dict):
+    """forward(..., past_key_values=tuple) — the reference's own cache surface (model.py:228-236,
+    469-476), kept so that code driving the model token by token keeps working."""
+    from .model import CausalLMOutputWithEmotionClassification
+    eng = model.engine
+    dev = eng.device
+    B, T = input_ids.shape
+    H, nh = eng.H, eng.nh
+    past = []
+    for k, v in past_key_values:
+        ctx = k.shape[-2]
+        k2 = k.to(dev).permute(0, 2, 1, 3).reshape(B, ctx, H)
+        v2 = v.to(dev).permute(0, 2, 1, 3).reshape(B, ctx, H)
+        past.append(torch.cat([k2, v2], dim=-1).to(torch.bfloat16).contiguous())
+    ctx = past[0].shape[1]
+    kv_lens = None
+    if attention_mask is not None:
+        kv_lens = model._kv_lens_from_mask(attention_mask.to(dev), B, ctx + T)
+    out = eng.forward(input_ids, token_type_ids, None, None, None, None, caption_ids, pos, kv_lens=kv_lens,
+                      training=False, save=False, want_logits=True, logits_fp32=model.fp32_logits, legacy_past=past)
+    V = eng.V
+    logits_buf = out["logits"]
+    kv_bufs = out["kv_present"]
+
+    def logits_fn():
+        return logits_buf[:, :V].to(torch.float32).view(B, T, V)
+
+    def past_fn():
+        res = []
+        for kvf in kv_bufs:
+            tk = kvf.shape[1]
+            k = kvf[:, :, :H].view(B, tk, nh, 64).permute(0, 2, 1, 3).float()
+            v = kvf[:, :, H:].view(B, tk, nh, 64).permute(0, 2, 1, 3).float()
+            res.append((k, v))
+        return tuple(res)
+
+    ret = CausalLMOutputWithEmotionClassification(loss=None, logits_fn=logits_fn,
+                                                  emotion_logits=out["emotion_logits"].clone(),
+                                                  past_fn=past_fn if use_cache else None)
+    if not return_dict:
+        return (ret.logits, ret.emotion_logits) + ((ret.past_key_values,) if use_cache else ())
+    return ret

@@ -51,11 +51,46 @@ def gemm(a, b, d, *, M, N, K, a_major=L.ERGM_MAJOR_K, b_major=L.ERGM_MAJOR_MN, l
     args.block_n = block_n
     args.dropout_p = dropout_p
     args.seed, args.offset = seed, offset
+    global _launch_count
+    _launch_count += 1
+    if PROFILE is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(L.lib().ergm_gemm_bf16(ctypes.byref(args), _stream()), "ergm_gemm_bf16")
+        e1.record()
+        PROFILE.append(("ergm_gemm_bf16", (M, N, K, a_major, b_major, split_k), e0, e1))
+        return
     L.check(L.lib().ergm_gemm_bf16(ctypes.byref(args), _stream()), "ergm_gemm_bf16")
 
 
+# kernels launched per C-ABI call (for bench.py's gpu_launches claim)
+_LAUNCHES = {"ergm_attn_bwd": 2}
+_launch_count = 0
+PROFILE = None  # set to a list to collect (name, info, start_event, end_event) per call
+
+
+def reset_launch_count():
+    global _launch_count
+    _launch_count = 0
+
+
+def launch_count():
+    return _launch_count
+
+
 def _call(name, *args):
+    global _launch_count
     fn = getattr(L.lib(), name)
+    _launch_count += _LAUNCHES.get(name, 1)
+    if PROFILE is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(fn(*args, torch.cuda.current_stream().cuda_stream), name)
+        e1.record()
+        PROFILE.append((name, None, e0, e1))
+        return
     L.check(fn(*args, torch.cuda.current_stream().cuda_stream), name)
 
 
@@ -81,10 +116,17 @@ def check_err_flag(device):
         raise IndexError("ergm_b200: index out of range in input_ids / token_type_ids / labels")
 
 
-def embed_fuse_fwd(ids, tts, pos_ids, wte, wpe, imgs, auds, out, *, past_len=0, dropout_p=0.0, seed=0, offset=0):
+def _pos_stride(pos_ids, T):
+    return 0 if (pos_ids is None or pos_ids.numel() == T) else T
+
+
+def embed_fuse_fwd(ids, tts, pos_ids, wte, wpe, imgs, auds, out, *, past_len=0, past_lens=None, dropout_p=0.0, seed=0,
+                   offset=0):
+    """pos_ids: None, [T] (shared by the batch) or [B, T] (per sample)."""
     B, T = ids.shape
     H = wte.shape[1]
-    _call("ergm_embed_fuse_fwd", ids.data_ptr(), _p(tts), _p(pos_ids), wte.data_ptr(), wpe.data_ptr(),
+    _call("ergm_embed_fuse_fwd", ids.data_ptr(), _p(tts), _p(pos_ids), _pos_stride(pos_ids, T), _p(past_lens),
+          wte.data_ptr(), wpe.data_ptr(),
           _p(imgs), imgs.stride(0) if imgs is not None else 0, _p(auds), auds.stride(0) if auds is not None else 0,
           out.data_ptr(), B, T, H, past_len, wte.shape[0], wpe.shape[0], dropout_p, seed, offset,
           err_flag(ids.device).data_ptr())
@@ -97,14 +139,16 @@ def gather_rows_bf16(ids, table, out):
 
 def embed_bwd(dh, ids, tts, pos_ids, dwte, dwpe, *, T, past_len=0, dimgs=None, dauds=None, dropout_p=0.0, seed=0, offset=0):
     rows, H = dh.shape
-    _call("ergm_embed_bwd", dh.data_ptr(), _p(ids), _p(tts), _p(pos_ids), _p(dwte), _p(dwpe), _p(dimgs), _p(dauds),
+    _call("ergm_embed_bwd", dh.data_ptr(), _p(ids), _p(tts), _p(pos_ids), _pos_stride(pos_ids, T), _p(dwte), _p(dwpe), _p(dimgs), _p(dauds),
           rows, T, H, past_len, dropout_p, seed, offset)
 
 
-def ln_fwd(x, gamma, beta, y_bf16, y_f32, mean, rstd, eps):
+def ln_fwd(x, gamma, beta, y_bf16, y_f32, mean, rstd, eps, row_idx=None):
     rows, H = x.shape
+    if row_idx is not None:
+        rows = row_idx.numel()
     _call("ergm_ln_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _p(y_bf16), _p(y_f32), _p(mean), _p(rstd),
-          rows, H, eps)
+          rows, H, eps, _p(row_idx))
 
 
 def ln_bwd(dy, x, mean, rstd, gamma, dres_in, dx_out, dx_bf16, dgamma, dbeta, dbias_next=None, *, dropout_p=0.0,
@@ -131,30 +175,33 @@ def cast_f32_bf16(src, dst):
 
 
 def attn_fwd(q, k, v, out, lse, *, B, nh, Tq, Tk, q_col0=0, k_col0=0, v_col0=0, causal=True, causal_off=None,
-             kv_lens=None, dropout_p=0.0, seed=0, offset=0):
+             kv_lens=None, dropout_p=0.0, seed=0, offset=0, out_f32=None):
     """q/k/v: bf16 2-D matrices [B*T, ld] (may be the same tensor with different col0)."""
     if causal_off is None:
         causal_off = Tk - Tq
     _call("ergm_attn_fwd", q.data_ptr(), q.stride(0), q_col0, k.data_ptr(), k.stride(0), k_col0, v.data_ptr(),
-          v.stride(0), v_col0, out.data_ptr(), out.stride(0), _p(lse), _p(kv_lens), B, nh, Tq, Tk, 64, int(causal),
+          v.stride(0), v_col0, out.data_ptr(), out.stride(0), _p(out_f32), _p(lse), _p(kv_lens), B, nh, Tq, Tk, 64,
+          int(causal),
           causal_off, dropout_p, seed, offset)
 
 
 def attn_bwd(q, k, v, out, dout, lse, delta, dq_accum, dk, dv, *, B, nh, Tq, Tk, q_col0=0, k_col0=0, v_col0=0,
-             dk_col0=0, dv_col0=0, causal=True, causal_off=None, kv_lens=None, dropout_p=0.0, seed=0, offset=0):
+             dk_col0=0, dv_col0=0, causal=True, causal_off=None, kv_lens=None, dropout_p=0.0, seed=0, offset=0,
+             out_f32=None):
     if causal_off is None:
         causal_off = Tk - Tq
     _call("ergm_attn_bwd", q.data_ptr(), q.stride(0), q_col0, k.data_ptr(), k.stride(0), k_col0, v.data_ptr(),
-          v.stride(0), v_col0, out.data_ptr(), out.stride(0), dout.data_ptr(), dout.stride(0), lse.data_ptr(),
+          v.stride(0), v_col0, out.data_ptr(), out.stride(0), _p(out_f32), dout.data_ptr(), dout.stride(0), lse.data_ptr(),
           delta.data_ptr(), dq_accum.data_ptr(), dq_accum.stride(0), dk.data_ptr(), dk.stride(0), dk_col0,
           dv.data_ptr(), dv.stride(0), dv_col0, _p(kv_lens), B, nh, Tq, Tk, 64, int(causal), causal_off,
           dropout_p, seed, offset)
 
 
-def ce_fwd(logits, labels, lse, row_loss, sums, *, T, V):
+def ce_fwd(logits, labels, lse, row_loss, sums, *, T, V, hn=None, w=None):
     rows = logits.shape[0]
     _call("ergm_ce_fwd", logits.data_ptr(), int(logits.dtype == torch.float32), logits.stride(0), labels.data_ptr(),
-          rows, T, V, lse.data_ptr(), row_loss.data_ptr(), sums.data_ptr(), err_flag(logits.device).data_ptr())
+          rows, T, V, lse.data_ptr(), row_loss.data_ptr(), sums.data_ptr(), err_flag(logits.device).data_ptr(),
+          _p(hn), _p(w), hn.shape[1] if hn is not None else 0)
 
 
 def ce_bwd(logits, labels, lse, scale, dlogits, *, T, V):
@@ -187,3 +234,34 @@ def scalar_mul(a, b, dst):
 def adamw_flat(p, g, m, v, shadow, hyper, grad_scale=None):
     _call("ergm_adamw_flat", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _p(shadow), p.numel(),
           hyper.data_ptr(), _p(grad_scale))
+
+
+def attn_decode_paged(qkv, pool, block_table, seq_lens, out, *, B, nh, H):
+    _call("ergm_attn_decode_paged", qkv.data_ptr(), qkv.stride(0), 0, H, 2 * H, pool.data_ptr(),
+          block_table.data_ptr(), seq_lens.data_ptr(), block_table.shape[1], out.data_ptr(), out.stride(0), B, nh, 64)
+
+
+def attn_decode_contig(q, kv, out, *, B, nh, Tk, k_col0, v_col0, kv_lens=None, q_col0=0):
+    _call("ergm_attn_decode_contig", q.data_ptr(), q.stride(0), q_col0, kv.data_ptr(), kv.stride(0), k_col0, v_col0,
+          _p(kv_lens), out.data_ptr(), out.stride(0), B, nh, Tk, 64)
+
+
+def kv_to_pages(kv, pool, block_table, lens, *, B, T, nh, k_col0, v_col0):
+    _call("ergm_kv_to_pages", kv.data_ptr(), kv.stride(0), k_col0, v_col0, pool.data_ptr(), block_table.data_ptr(),
+          _p(lens), block_table.shape[1], B, T, nh)
+
+
+def sample(logits, *, V, top_k=0, temperature=1.0, seed=0, step=None, out_ids=None, next_ids=None, finished=None,
+           seq_lens=None, eos_id=-1):
+    B = logits.shape[0]
+    _call("ergm_sample", logits.data_ptr(), logits.stride(0), B, V, top_k, float(temperature), seed, _p(step),
+          _p(out_ids), out_ids.stride(0) if out_ids is not None else 0, _p(next_ids), _p(finished), _p(seq_lens),
+          eos_id)
+
+
+def int_add(t, inc):
+    _call("ergm_int_add", t.data_ptr(), inc)
+
+
+def rng_step_advance(t, inc=1):
+    _call("ergm_rng_step_advance", t.data_ptr(), inc)

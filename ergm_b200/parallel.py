@@ -1,0 +1,117 @@
+"""Data-parallel training and per-GPU-sharded generation.
+
+The reference is single-process / single-GPU (main.py:40-41); the path shards naturally over
+samples, so the build adds exactly one exchange step per iteration: a bucketed all-reduce (sum)
+of the flat fp32 gradient buffer over NCCL / NVLink, issued layer-group by layer-group while the
+hand-written backward is still running, plus one 4-float all-reduce of
+[lm_loss_sum, n_valid_tokens, emotion_loss_sum, n_samples] right after the forward so that every
+rank scales its backward by 1 / (GLOBAL count): the N-GPU step then equals the single-GPU
+reference on the concatenated batch (per-rank means would not, because the number of non -100
+labels differs per rank).
+
+One process per GPU (torchrun), backend nccl on GPUs and gloo for the CPU tests of the host
+logic in this file.
+"""
+import torch
+import torch.distributed as dist
+
+
+def plan_buckets(entries, n_layer, bucket_bytes):
+    """Splits the flat gradient buffer into all-reduce ranges in the order the backward pass
+    completes them.  `entries`: {param name: (offset, numel, shape)} in flat-buffer order
+    (wte, wpe, h.0 ... h.L-1, ln_f, emotion_head).  Returns a list of
+    (trigger_layer, lo, hi): after the backward of `trigger_layer` (L-1 ... 0, or -1 for the
+    embedding stage) the fp32 range [lo, hi) is final."""
+    total_hi = max(o + ((n + 63) // 64) * 64 for o, n, _ in entries.values())
+    layer_lo = [entries["transformer.h.%d.ln_1.weight" % l][0] for l in range(n_layer)]
+    buckets = []
+    hi = total_hi  # the head parameters (ln_f, emotion_head) sit after the last layer
+    for l in reversed(range(n_layer)):
+        lo = layer_lo[l]
+        if (hi - lo) * 4 >= bucket_bytes or l == 0:
+            buckets.append((l, lo, hi))
+            hi = lo
+    buckets.append((-1, 0, layer_lo[0] if n_layer else total_hi))  # wte / wpe: complete last
+    return buckets
+
+
+def global_loss_from_sums(sums, has_lm=True, has_emo=True):
+    """loss = CE_lm + CE_emotion as means over the GLOBAL counts (model.py:704-721)."""
+    lm = sums[0] / sums[1] if has_lm else 0.0
+    em = sums[2] / sums[3] if has_emo else 0.0
+    return lm + em
+
+
+def shard_range(n, rank, world):
+    """Contiguous split of n requests over `world` ranks (first ranks get the remainder)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class DataParallel:
+    """Wraps an ergm_b200 GPT2LMHeadModel for one-process-per-GPU data parallelism."""
+
+    def __init__(self, model, bucket_mb=32, process_group=None, broadcast_params=True):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self.model = model
+        self.group = process_group
+        self.world = dist.get_world_size(process_group)
+        self.rank = dist.get_rank(process_group)
+        self.bucket_bytes = int(bucket_mb * (1 << 20))
+        eng = model.engine
+        eng.ensure_params()
+        if broadcast_params and self.world > 1:
+            dist.broadcast(eng.store.flat, 0, group=process_group)
+            eng.store.shadow_fresh = False
+        self.buckets = plan_buckets(eng.store.entries, eng.L, self.bucket_bytes)
+        self._pending = []
+        model._dp = self
+
+    def reduce_loss_sums(self, sums):
+        if self.world > 1:
+            dist.all_reduce(sums, group=self.group)
+
+    def _launch(self, layer):
+        g = self.model.engine.store.grad
+        for trig, lo, hi in self.buckets:
+            if trig == layer and hi > lo:
+                self._pending.append(dist.all_reduce(g[lo:hi], group=self.group, async_op=True))
+
+    def backward(self, grad_loss, accumulate):
+        eng = self.model.engine
+        self._pending = []
+        if self.world > 1 and accumulate:
+            raise RuntimeError("gradient accumulation across backward calls is not supported under DataParallel")
+        eng.backward(grad_loss, accumulate=accumulate, on_layer_done=self._launch if self.world > 1 else None)
+        for w in self._pending:
+            w.wait()
+        self._pending = []
+
+    @torch.no_grad()
+    def generate(self, input_ids, *args, **kw):
+        """Per-GPU sharded batched generation: every rank decodes its contiguous slice of the
+        request batch with its own paged-KV pool; the ids are all-gathered."""
+        n = input_ids.shape[0]
+        lo, hi = shard_range(n, self.rank, self.world)
+        sl = slice(lo, hi)
+
+        def cut(t):
+            return t[sl] if (torch.is_tensor(t) and t.shape[0] == n) else t
+
+        local = self.model.generate(cut(input_ids), *[cut(a) for a in args], **{k: cut(v) for k, v in kw.items()})
+        return gather_rows(local, n, self.rank, self.world, self.group)
+
+
+def gather_rows(local, n, rank, world, group=None):
+    """all-gather of ragged row shards produced by shard_range back into [n, ...]."""
+    if world == 1:
+        return local
+    sizes = [shard_range(n, r, world) for r in range(world)]
+    maxr = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros((maxr,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    outs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(outs, pad, group=group)
+    return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(outs, sizes)], 0)

@@ -1,0 +1,110 @@
+"""Graph-captured training step: the public entry point for the throughput path.
+
+    step = GraphedTrainStep(model, optimizer)          # optimizer: ergm_b200.optim.FusedAdamW
+    loss = step(batch_on_pinned_host)                  # python float (D2H of the loss)
+
+One step = H2D copy of the batch from pinned host memory into static device buffers, then ONE
+CUDA-graph replay of  forward -> hand-written backward (-> bucketed NCCL all-reduce under
+DataParallel) -> fused AdamW (+ bf16 shadow refresh), then the D2H read of the loss.  The graph
+is captured on the first call for a given batch shape; the arithmetic is exactly what
+model(**batch).loss.backward(); optimizer.step() runs eagerly (same C-ABI calls, same order).
+Learning-rate / bias-correction values and the dropout step counter live in device memory, so
+the replayed kernels see fresh values every step.
+"""
+import torch
+
+from . import ops
+
+_KEYS = ("input_ids", "token_type_ids", "labels", "emotion_labels", "caption_ids", "imgs", "auds")
+
+
+class GraphedTrainStep:
+    def __init__(self, model, optimizer, dp=None, use_graph=True):
+        self.model = model
+        self.opt = optimizer
+        self.dp = dp if dp is not None else getattr(model, "_dp", None)
+        self.use_graph = use_graph
+        self.graphs = {}
+        self.static = {}
+        eng = model.engine
+        self.eng = eng
+        self.rng_step = torch.zeros(1, dtype=torch.int64, device=eng.device)
+        eng.set_rng_step_tensor(self.rng_step)
+        self.one = torch.ones(1, dtype=torch.float32, device=eng.device)
+        self.loss_host = torch.zeros(5, dtype=torch.float32).pin_memory()
+        self.h2d_bytes = 0
+        self.launches_per_step = 0
+
+    # the device work of one step (identical in eager and captured mode)
+    def _device_step(self, b):
+        eng, model = self.eng, self.model
+        ops.reset_launch_count()
+        out = eng.forward(b["input_ids"], b.get("token_type_ids"), b.get("labels"), b.get("emotion_labels"),
+                          b.get("imgs"), b.get("auds"), b.get("caption_ids"), None, training=model.training,
+                          save=True, want_logits=True, logits_fp32=model.fp32_logits)
+        if self.dp is not None:
+            self.dp.reduce_loss_sums(out["loss_sums"])
+        losses = eng.finalize_loss(out)
+        if self.dp is not None:
+            self.dp.backward(self.one, False)
+        else:
+            eng.backward(self.one, accumulate=False)
+        self.opt.apply()
+        L = ops.launch_count()
+        ops.rng_step_advance(self.rng_step, 1)
+        self.launches_per_step = L + 1
+        return losses
+
+    def _stage(self, key, batch):
+        st = {}
+        nbytes = 0
+        for k in _KEYS:
+            v = batch.get(k)
+            if v is None:
+                continue
+            if k == "imgs" and v.dim() == 3:
+                v = v[:, 0]
+            dt = torch.float32 if k in ("imgs", "auds") else torch.int64
+            st[k] = torch.empty(tuple(v.shape), dtype=dt, device=self.eng.device)
+            nbytes += st[k].numel() * st[k].element_size()
+        self.static[key] = st
+        self.h2d_bytes = nbytes
+        return st
+
+    def _key(self, batch):
+        return tuple((k, tuple(batch[k].shape)) for k in _KEYS if batch.get(k) is not None)
+
+    def copy_in(self, batch):
+        key = self._key(batch)
+        st = self.static.get(key) or self._stage(key, batch)
+        for k, dst in st.items():
+            src = batch[k]
+            if k == "imgs" and src.dim() == 3:
+                src = src[:, 0]
+            dst.copy_(src, non_blocking=True)
+        return key, st
+
+    def run_device(self, key, st):
+        """Forward + backward + optimizer on the static buffers (graph replay after capture)."""
+        self.opt.load_hyper()
+        if not self.use_graph:
+            self.losses = self._device_step(st)
+            return
+        g = self.graphs.get(key)
+        if g is None:
+            # warm-up eagerly once (allocates workspaces, NCCL channels), then capture
+            self.losses = self._device_step(st)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()  # capture executes nothing: the hyper buffer is re-staged before each replay
+            with torch.cuda.graph(g):
+                self.losses = self._device_step(st)
+            self.graphs[key] = g
+            return
+        g.replay()
+
+    def __call__(self, batch):
+        key, st = self.copy_in(batch)
+        self.run_device(key, st)
+        self.loss_host.copy_(self.losses, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self.loss_host[0])

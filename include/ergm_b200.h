@@ -83,11 +83,14 @@ int ergm_gemm_bf16(const ergm_gemm_args* args, void* stream);
 /* ------------------------------------------------------------------------ */
 /* Embedding + multimodal fusion (model.py:458-507):                          */
 /*   h[b,t] = ((wte[id] (+imgs[b] if t==0) (+auds[b] if t==1)) + wpe[pos]) + wte[type]
- * then embd dropout.  pos = past_len + t unless position_ids[T] is given.   */
+ * then embd dropout.  pos = past_len + t unless position_ids is given, in
+ * which case pos = position_ids[b * pos_stride_b + t] (stride 0 = shared).  */
 /* imgs / auds: fp32 [B, ld] (the pooled vectors model.py:497-498 adds) or    */
 /* NULL.  err_flag (device int) is set to 1 on an out-of-range index.         */
 int ergm_embed_fuse_fwd(const int64_t* ids, const int64_t* token_type_ids,
-                        const int64_t* position_ids, const float* wte, const float* wpe,
+                        const int64_t* position_ids, int64_t pos_stride_b,
+                        const int* past_lens /* nullable int32 [B]: per-sequence past length */,
+                        const float* wte, const float* wpe,
                         const float* imgs, int64_t ld_img, const float* auds, int64_t ld_aud,
                         float* out, int B, int T, int H, int past_len, int vocab, int n_pos,
                         float dropout_p, uint64_t seed, uint64_t offset, int* err_flag,
@@ -98,7 +101,7 @@ int ergm_gather_rows_bf16(const int64_t* ids, const float* table, void* out_bf16
 /* backward of the embedding stage: scatter-add dh rows into dwte (by id and  */
 /* by token type), dwpe, and optionally the fused-feature gradients.          */
 int ergm_embed_bwd(const float* dh, const int64_t* ids, const int64_t* token_type_ids,
-                   const int64_t* position_ids, float* dwte, float* dwpe, float* dimgs,
+                   const int64_t* position_ids, int64_t pos_stride_b, float* dwte, float* dwpe, float* dimgs,
                    float* dauds, int rows, int T, int H, int past_len, float dropout_p,
                    uint64_t seed, uint64_t offset, void* stream);
 
@@ -107,6 +110,7 @@ int ergm_embed_bwd(const float* dh, const int64_t* ids, const int64_t* token_typ
 /* fwd writes bf16 and/or fp32 outputs and the row statistics.                */
 int ergm_ln_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16,
                 float* y_f32, float* mean, float* rstd, int rows, int H, float eps,
+                const int* row_idx /* nullable: output row r normalises x[row_idx[r]] */,
                 void* stream);
 /* bwd fused with the residual-gradient add: dx_out = dres_in + LN'(dy);      */
 /* dx_bf16 = bf16(dropout_mask(dx_out)) feeds the next dgrad/wgrad GEMMs;     */
@@ -130,6 +134,7 @@ int ergm_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
 /* kv_lens (nullable, int32 [B]) masks right-padded keys.                     */
 int ergm_attn_fwd(const void* q, int64_t ld_q, int q_col0, const void* k, int64_t ld_k,
                   int k_col0, const void* v, int64_t ld_v, int v_col0, void* out, int64_t ld_out,
+                  float* out_f32 /* nullable [B*Tq, nh*64]: un-rounded copy for backward */,
                   float* lse, const int* kv_lens, int B, int nh, int Tq, int Tk, int head_dim,
                   int causal, int causal_off, float dropout_p, uint64_t seed, uint64_t offset,
                   void* stream);
@@ -140,7 +145,7 @@ int ergm_attn_fwd(const void* q, int64_t ld_q, int q_col0, const void* k, int64_
  * delta ([B,nh,Tq] scratch) receives rowsum(dO * O).                         */
 int ergm_attn_bwd(const void* q, int64_t ld_q, int q_col0, const void* k, int64_t ld_k,
                   int k_col0, const void* v, int64_t ld_v, int v_col0, const void* out,
-                  int64_t ld_out, const void* dout, int64_t ld_do, const float* lse, float* delta,
+                  int64_t ld_out, const float* out_f32 /* nullable */, const void* dout, int64_t ld_do, const float* lse, float* delta,
                   float* dq_accum, int64_t ld_dq, void* dk, int64_t ld_dk, int dk_col0, void* dv,
                   int64_t ld_dv, int dv_col0, const int* kv_lens, int B, int nh, int Tq, int Tk,
                   int head_dim, int causal, int causal_off, float dropout_p, uint64_t seed,
@@ -150,9 +155,11 @@ int ergm_attn_bwd(const void* q, int64_t ld_q, int q_col0, const void* k, int64_
 /* Token cross-entropy over LM-head logits with the reference's shift and     */
 /* ignore_index=-100 (model.py:705-708): row (b,t) is scored against          */
 /* labels[b,t+1].  sums[0] += sum of row losses, sums[1] += valid rows.       */
+/* hn / w (nullable, bf16 [rows,H] / [V,H]): when given, the target logit is
+ * recomputed as their fp32 dot product instead of read from rounded logits.  */
 int ergm_ce_fwd(const void* logits, int logits_is_f32, int64_t ldl, const int64_t* labels,
                 int rows, int T, int V, float* lse, float* row_loss, float* sums, int* err_flag,
-                void* stream);
+                const void* hn_bf16, const void* w_bf16, int H, void* stream);
 /* dlogits = (softmax - onehot) * (*scale_ptr), zero for ignored rows (bf16)   */
 int ergm_ce_bwd(const void* logits, int logits_is_f32, int64_t ldl, const int64_t* labels,
                 int rows, int T, int V, const float* lse, const float* scale_ptr,
@@ -169,6 +176,34 @@ int ergm_emotion_head_bwd(const float* dlogits, const float* hlast, const float*
 /* out = [loss, lm_loss, emo_loss, 1/lm_valid, 1/emo_count] (model.py:713)    */
 int ergm_loss_finalize(const float* sums, int has_lm, int has_emotion, float* out, void* stream);
 int ergm_scalar_mul(const float* a, const float* b, float* dst, void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* Decode: paged KV cache + one-query attention + on-device sampling.  Replaces
+ * the torch.cat cache growth of model.py:228-236 and the per-token sampling /
+ * host sync of main.py:253-282.  Pool layout (bf16):
+ * [page][k|v][head][16 tokens][64]; block_table is int32 [B, max_pages].     */
+/* appends the new token's K/V (columns k_col0 / v_col0 of qkv [B, ld_q]) at
+ * slot seq_lens[b] and attends over seq_lens[b] + 1 tokens.                  */
+int ergm_attn_decode_paged(const void* qkv, int64_t ld_q, int q_col0, int k_col0, int v_col0,
+                           void* pool, const int* block_table, const int* seq_lens, int max_pages,
+                           void* out, int64_t ld_out, int B, int nh, int head_dim, void* stream);
+/* one-query attention over a contiguous [B*Tk, ld_k] K/V matrix (cached
+ * cross-attention K/V of the caption embeddings, model.py:219)               */
+int ergm_attn_decode_contig(const void* q, int64_t ld_q, int q_col0, const void* kv, int64_t ld_k,
+                            int k_col0, int v_col0, const int* kv_lens, void* out, int64_t ld_out,
+                            int B, int nh, int Tk, int head_dim, void* stream);
+/* prompt K/V rows -> pages (rows t >= lens[b] are skipped when lens != NULL)  */
+int ergm_kv_to_pages(const void* kv, int64_t ld, int k_col0, int v_col0, void* pool,
+                     const int* block_table, const int* lens, int max_pages, int B, int T, int nh,
+                     void* stream);
+/* next token per row of fp32 logits: top_k <= 1 greedy arg-max (lowest index
+ * on ties), else top-k / temperature sampling (Philox(seed, *step_ptr)).
+ * Writes out_ids[b, *step_ptr], next_ids[b]; finished rows emit eos_id;
+ * seq_lens[b] += 1.                                                          */
+int ergm_sample(const float* logits, int64_t ld, int B, int V, int top_k, float temperature,
+                uint64_t seed, const int* step_ptr, int64_t* out_ids, int64_t out_ld,
+                int64_t* next_ids, int* finished, int* seq_lens, int64_t eos_id, void* stream);
+int ergm_int_add(int* dev_ptr, int inc, void* stream);
 
 /* ------------------------------------------------------------------------ */
 /* Flat AdamW, torch.optim.AdamW arithmetic (main.py:68,155).  hyper (device) */

@@ -136,11 +136,11 @@ def test_colsum_and_casts(cuda_device):
     assert torch.equal(fb, flat.bfloat16())
 
 
+@pytest.mark.parametrize("V,ld", [(50260, 50304), (1024, 1024), (77, 128)])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
-def test_ce_fwd_bwd(cuda_device, dtype):
+def test_ce_fwd_bwd(cuda_device, dtype, V, ld):
     from ergm_b200 import ops
-    B, T, V = 3, 17, 50260
-    ld = 50304
+    B, T = 3, 17
     g = _g(5)
     logits = torch.zeros(B * T, ld, device="cuda", dtype=dtype)
     logits[:, :V] = (torch.randn(B * T, V, device="cuda", generator=g) * 2).to(dtype)
@@ -163,7 +163,8 @@ def test_ce_fwd_bwd(cuda_device, dtype):
     lr = lf.clone().requires_grad_(True)
     F.cross_entropy(lr[:, :-1].reshape(-1, V), labels[:, 1:].reshape(-1)).backward()
     assert (dl[:, :V].float().view(B, T, V) - lr.grad).abs().max().item() < 2e-3 / nvalid * 10
-    assert dl[:, V:].abs().max().item() == 0
+    if ld > V:
+        assert dl[:, V:].abs().max().item() == 0
     ops.check_err_flag(logits.device)
 
 
