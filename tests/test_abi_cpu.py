@@ -1,0 +1,98 @@
+"""CPU checks of the drop-in boundary: the C-ABI library builds / loads without a GPU and
+exports every symbol include/ergm_b200.h declares; the Python model mirrors the reference's
+module tree; the product path refuses to run without CUDA (no CPU fallback)."""
+import ctypes
+import os
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from ergm_b200 import build
+    build.build()
+    from ergm_b200 import _lib
+    return _lib.lib()
+
+
+def test_header_symbols_exported(lib):
+    from ergm_b200 import _lib
+    protos = _lib.header_prototypes()
+    assert len(protos) >= 27
+    for name in protos:
+        assert hasattr(lib, name), name
+    assert lib.ergm_abi_version() == 1
+
+
+def test_header_is_plain_c():
+    """The boundary must be consumable by a C compiler: no C++ / torch types in the signatures."""
+    import subprocess
+    import tempfile
+    src = '#include "ergm_b200.h"\nint main(void){ergm_gemm_args a; (void)a; return ERGM_OK;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "t.c")
+        open(p, "w").write(src)
+        r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", p,
+                            "-o", os.path.join(d, "t.o")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+
+
+def test_gemm_args_struct_matches_header():
+    from ergm_b200 import _lib
+    # 6 pointers + 4 int64 + 9 int32 + float + 2 uint64, natural alignment
+    assert ctypes.sizeof(_lib.GemmArgs) == 6 * 8 + 4 * 8 + 9 * 4 + 4 + 2 * 8
+
+
+def test_argument_errors_without_gpu(lib):
+    from ergm_b200 import _lib
+    a = _lib.GemmArgs()
+    assert lib.ergm_gemm_bf16(ctypes.byref(a), None) == -1  # null operands -> ERGM_ERR_ARG, nothing launched
+    assert lib.ergm_ln_fwd(None, None, None, None, None, None, None, 4, 128, 1e-5, None, None) == -1
+    assert lib.ergm_attn_fwd(1, 8, 0, 1, 8, 0, 1, 8, 0, 1, 8, None, None, None, 1, 1, 8, 8, 32, 1, 0, 0.0, 0, 0, None) == -2
+
+
+def test_model_tree_matches_reference_keys():
+    from transformers import GPT2Config
+    from ergm_b200.model import GPT2LMHeadModel
+    from oracle import ergm_oracle as O
+    m = GPT2LMHeadModel(GPT2Config(vocab_size=1024, n_positions=64, n_embd=128, n_layer=2, n_head=2))
+    want = dict(O.param_shapes(O.OracleConfig(1024, 64, 128, 2, 2)))
+    want["lm_head.weight"] = want["transformer.wte.weight"]
+    sd = m.state_dict()
+    assert set(sd) == set(want)
+    assert all(tuple(sd[k].shape) == want[k] for k in want)
+    assert m.lm_head.weight is m.transformer.wte.weight
+    assert m.config.n_ctx == 64 and m.config.add_cross_attention is True
+    # init distributions of model.py:359-375
+    assert abs(m.transformer.h[0].attn.c_proj.weight.std().item() - 0.02 / 2.0) < 2e-3
+    assert abs(m.transformer.h[0].attn.c_attn.weight.std().item() - 0.02) < 2e-3
+
+
+def test_no_cpu_fallback():
+    from transformers import GPT2Config
+    from ergm_b200.model import GPT2LMHeadModel
+    from ergm_b200._lib import ErgmError
+    m = GPT2LMHeadModel(GPT2Config(vocab_size=1024, n_positions=64, n_embd=128, n_layer=1, n_head=2))
+    with pytest.raises(ErgmError):
+        m(input_ids=torch.zeros(1, 4, dtype=torch.long))
+
+
+def test_product_never_imports_oracle():
+    for dp, _, files in os.walk(os.path.join(ROOT, "ergm_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_reference_compat_shim_exports():
+    """`from model import *` (main.py:22) must find the reference's public names."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("model", os.path.join(ROOT, "compat", "model.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    for name in ("GPT2LMHeadModel", "GPT2Model", "CausalLMOutputWithEmotionClassification", "torch", "nn", "F"):
+        assert hasattr(mod, name)
