@@ -156,11 +156,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const bool key_ok = kj < kv_len;
     const uint32_t lane_addr = (uint32_t)(qr * 32) << 16;
     const float c = p.scale * 1.4426950408889634f;
-    const float keep_scale = p.do_drop ? 1.f / (1.f - p.drop.p) : 1.f;
+    const uint32_t thr16 = p.drop.thr16();
+    const float keep_scale = p.do_drop ? 65536.f / (65536.f - (float)thr16) : 1.f;
+    const uint32_t drop_shift = (kj & 1) ? 16u : 0u;  // which 16-bit lane of hash2(row, kj >> 1) is ours
     const int ct = threadIdx.x - 128;    // 0..255 inside the compute group
     for (int it = 0; it < n_iter; ++it) {
       const int q0 = (i_min + it) * 128;
-      // stage this query block's lse / delta in smem
+      // stage this query block's lse (pre-multiplied by log2 e) / delta in smem
       {
         const uint32_t dst = sStat + (it & 1) * 1024 + ct * 4;
         const int qi = q0 + (ct & 127);
@@ -172,6 +174,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst), "f"(val) : "memory");
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      // warp-uniform: does this (key rows, query block) tile need any masking?
+      const bool need_mask = (k0 + qr * 32 + 31 > kv_len - 1) || (q0 + 127 > p.Tq - 1) ||
+                             (CAUSAL && (k0 + qr * 32 + 31 > q0 + p.causal_off));
       mbar_wait(bar_sdp, it & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -179,26 +184,36 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         uint32_t sv[32], dv_[32];
         tmem_ld_32x32b_x32(tS + lane_addr + cc, sv);
         tmem_ld_32x32b_x32(tDP + lane_addr + cc, dv_);
+        float ls[32], dl[32];
+        const uint32_t stat = sStat + (it & 1) * 1024 + cc * 4;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(ls[i]), "=f"(ls[i + 1]), "=f"(ls[i + 2]), "=f"(ls[i + 3]) : "r"(stat + i * 4));
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(dl[i]), "=f"(dl[i + 1]), "=f"(dl[i + 2]), "=f"(dl[i + 3]) : "r"(stat + 512 + i * 4));
+        }
         tmem_ld_wait();
         float pt[32], ds[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const int qi = q0 + cc + i;
-          float lse2, dl;
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(lse2) : "r"(sStat + (it & 1) * 1024 + (cc + i) * 4));
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(dl) : "r"(sStat + (it & 1) * 1024 + 512 + (cc + i) * 4));
-          bool vis = key_ok && qi < p.Tq;
-          if (CAUSAL) vis = vis && (kj <= qi + p.causal_off);
-          const float pr = vis ? exp2f(__uint_as_float(sv[i]) * c - lse2) : 0.f;
+          float pr = ex2_fast(fminf(fmaf(__uint_as_float(sv[i]), c, -ls[i]), 0.f));
+          if (need_mask) {
+            const int qi = q0 + cc + i;
+            bool vis = key_ok && qi < p.Tq;
+            if (CAUSAL) vis = vis && (kj <= qi + p.causal_off);
+            pr = vis ? pr : 0.f;
+          }
           float dp = __uint_as_float(dv_[i]);
           float pd = pr;
           if (p.do_drop) {
-            const bool keep = p.drop.keep((uint32_t)((b * p.nh + h) * p.Tq + qi), (uint32_t)kj);
+            const uint32_t hsh = p.drop.hash2((uint32_t)((b * p.nh + h) * p.Tq + q0 + cc + i), (uint32_t)kj >> 1);
+            const bool keep = ((hsh >> drop_shift) & 0xffffu) >= thr16;
             dp = keep ? dp * keep_scale : 0.f;
             pd = keep ? pr * keep_scale : 0.f;
           }
           pt[i] = pd;
-          ds[i] = pr * (dp - dl) * p.scale;
+          ds[i] = pr * (dp - dl[i]) * p.scale;
         }
         const uint32_t rowoff = (cc >> 6) * AB_TILE + r * 128;
 #pragma unroll

@@ -227,6 +227,12 @@ ERGM_DEVINL float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f
 // ----------------------------------------------------------------------------
 // numerics
 // ----------------------------------------------------------------------------
+// 2^x for x <= 0 (softmax exponents): one MUFU.EX2, denormal results flush to zero
+ERGM_DEVINL float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 ERGM_DEVINL float tanh_fast(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));

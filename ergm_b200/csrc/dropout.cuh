@@ -38,6 +38,29 @@ struct DropoutSite {
   ERGM_DEVINL bool keep(uint32_t row, uint32_t col) const {
     return (keep4(row, col >> 2) >> (col & 3)) & 1u;
   }
+
+  // ---- cheap per-element generator for the attention-probability dropout (model.py:142) ----
+  // The [B*nh*Tq, Tk] probability tile is two orders of magnitude larger than any other dropout
+  // site and is visited once per element in BOTH forward and backward, so Philox-10 would cost
+  // more than the softmax itself.  One 32-bit avalanche hash (two multiply-xorshift rounds on a
+  // counter keyed by seed/offset, "lowbias32" constants) yields two independent 16-bit uniforms:
+  // element (row, col) is kept iff its 16-bit lane >= thr16 = round(p * 65536).
+  ERGM_DEVINL uint32_t thr16() const { return (uint32_t)(p * 65536.f + 0.5f); }
+  ERGM_DEVINL uint32_t hash2(uint32_t row, uint32_t col2) const {
+    uint32_t h = (row * ncol4 * 2u + col2) ^ (uint32_t)seed;
+    h ^= h >> 16; h *= 0x7feb352du;
+    h ^= h >> 15; h *= 0x846ca68bu;
+    h ^= h >> 16;
+    h += (uint32_t)offset * 0x9E3779B9u + (uint32_t)(seed >> 32);
+    h ^= h >> 16; h *= 0x7feb352du;
+    h ^= h >> 15; h *= 0x846ca68bu;
+    h ^= h >> 16;
+    return h;
+  }
+  ERGM_DEVINL bool keep_hash(uint32_t row, uint32_t col) const {
+    const uint32_t h = hash2(row, col >> 1);
+    return ((col & 1u) ? (h >> 16) : (h & 0xffffu)) >= thr16();
+  }
 };
 
 // host side: library-global step pointer (set by ergm_set_rng_step_ptr, see api.cu)
