@@ -86,14 +86,19 @@ __global__ void __launch_bounds__(DEC_THREADS) attn_decode_kernel(const DecodeAt
   };
   // phase 1: scores
   float mx = -INFINITY;
-  for (int t = grp; t < ctx; t += DEC_THREADS / 8) {
-    float s = dot8(qv, *k_row(t));
+  // uniform trip count for the whole warp: the shuffles below are full-mask collectives
+  for (int tb = 0; tb < ctx; tb += DEC_THREADS / 8) {
+    const int t = tb + grp;
+    const bool ok = t < ctx;
+    float s = ok ? dot8(qv, *k_row(t)) : 0.f;
     s += __shfl_xor_sync(0xffffffffu, s, 4);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s *= p.scale;
-    if (gl == 0) s_score[t] = s;
-    mx = fmaxf(mx, s);
+    if (ok) {
+      if (gl == 0) s_score[t] = s;
+      mx = fmaxf(mx, s);
+    }
   }
   mx = warp_max(mx);
   if (lane == 0) s_red[warp] = mx;

@@ -25,7 +25,8 @@ constexpr int BK = 64;
 constexpr int GEMM_THREADS = 384;
 constexpr int EPI_WARP0 = 4;
 constexpr int NUM_EPI_WARPS = 8;
-constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int SMEM_BUDGET = 192 * 1024;
+constexpr int EPI_STAGING = NUM_EPI_WARPS * 4096;  // per-warp 32x32 fp32 transpose tiles
 
 template <int BN>
 struct GemmCfg {
@@ -34,7 +35,7 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGING + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 struct GemmParams {
@@ -53,6 +54,173 @@ struct GemmParams {
   DropoutSite site;
 };
 
+
+struct EpiFlags {
+  bool has_bias, do_gelu, do_res, do_atomic, do_drop, do_pre, exact, do_gelu_grad;
+  float keep_scale;
+  DropoutSite site;
+};
+
+ERGM_DEVINL EpiFlags make_epi_flags(const GemmParams& p) {
+  EpiFlags e;
+  e.has_bias = (p.epi & ERGM_EPI_BIAS) != 0;
+  e.do_gelu = (p.epi & ERGM_EPI_GELU) != 0;
+  e.do_res = (p.epi & ERGM_EPI_RESIDUAL) != 0;
+  e.do_atomic = (p.epi & ERGM_EPI_ATOMIC) != 0;
+  e.do_drop = (p.epi & ERGM_EPI_DROPOUT) != 0;
+  e.do_pre = (p.epi & ERGM_EPI_PREACT) != 0;
+  e.exact = (p.epi & ERGM_EPI_EXACT) != 0;
+  e.do_gelu_grad = (p.epi & ERGM_EPI_GELU_GRAD) != 0;
+  e.keep_scale = e.do_drop ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
+  e.site = p.site.resolved();
+  return e;
+}
+
+// Fused epilogue of one 32-row x 32-column chunk of an accumulator tile, per warp.
+//
+// tcgen05.ld hands every thread one accumulator ROW (32 consecutive columns).  Storing from that
+// layout makes each warp-wide 16-byte store touch 32 different 128-byte lines (measured: 12 us of a
+// 36 us QKV GEMM, profiles/r1_gemm_epilogue.md).  The chunk is therefore transposed through a
+// per-warp, XOR-swizzled 4 KB shared-memory tile: afterwards lane l owns 4 consecutive columns
+// (float4) of rows {4*it + l/8}, so that one warp instruction reads / writes four fully coalesced
+// 128-byte row segments (fp32) or 64-byte segments (bf16).  All fused work is done in that layout:
+// bias -> (store pre-activation) -> GELU' / GELU -> dropout -> + residual -> store / red.add.
+ERGM_DEVINL void epilogue_chunk(const GemmParams& p, const EpiFlags& ep, int row0, int col0, bool first_split,
+                                const float (&v)[32], uint32_t stage_smem, int lane) {
+  if (p.epi & (1 << 30)) {  // timing experiment: no global traffic at all
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc += v[i];
+    if (acc == 123.456f) reinterpret_cast<float*>(p.d)[0] = acc;
+    return;
+  }
+  // ---- transpose: row-per-thread -> (row group, float4 column) per lane ----
+  if (!(p.epi & (1 << 28))) __syncwarp();  // previous chunk's reads of the staging tile are done
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint32_t addr = stage_smem + lane * 128 + ((uint32_t)(c ^ (lane & 7)) << 4);
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[4 * c]), "f"(v[4 * c + 1]),
+                 "f"(v[4 * c + 2]), "f"(v[4 * c + 3])
+                 : "memory");
+  }
+  if (!(p.epi & (1 << 28))) __syncwarp();
+  const int c4 = lane & 7;             // float4 column index inside the chunk
+  const int col = col0 + 4 * c4;       // first of this lane's 4 columns
+  const bool col_full = col + 4 <= p.N;
+  const bool col_any = col < p.N;
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ep.has_bias && first_split && col_any) {
+    if (col_full) {
+      b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+    } else {
+      b4.x = __ldg(p.bias + col);
+      if (col + 1 < p.N) b4.y = __ldg(p.bias + col + 1);
+      if (col + 2 < p.N) b4.z = __ldg(p.bias + col + 2);
+    }
+  }
+  // not unrolled on purpose: the body carries every fused variant, 8 copies overflow the I-cache
+#pragma unroll 1
+  for (int it = 0; it < 8; ++it) {
+    const int r = 4 * it + (lane >> 3);
+    const int row = row0 + r;
+    float4 x;
+    {
+      const uint32_t addr = stage_smem + r * 128 + ((uint32_t)(c4 ^ (r & 7)) << 4);
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(addr));
+    }
+    if (row >= p.M || !col_any) continue;
+    if (p.epi & (1 << 29)) {  // timing experiment: transposition only, no global traffic
+      if (x.x == 123.456f) reinterpret_cast<float*>(p.d)[0] = x.y;
+      continue;
+    }
+    x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+    const int64_t off = (int64_t)row * p.ldd + col;
+    if (ep.do_pre) {
+      __nv_bfloat16* pp = reinterpret_cast<__nv_bfloat16*>(p.preact) + off;
+      if (col_full) {
+        *reinterpret_cast<uint2*>(pp) = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+      } else {
+        pp[0] = __float2bfloat16_rn(x.x);
+        if (col + 1 < p.N) pp[1] = __float2bfloat16_rn(x.y);
+        if (col + 2 < p.N) pp[2] = __float2bfloat16_rn(x.z);
+      }
+    }
+    if (ep.do_gelu_grad) {  // x *= gelu_new'(u), u = saved pre-activation (model.py:264 backward)
+      const __nv_bfloat16* up = reinterpret_cast<const __nv_bfloat16*>(p.preact) + off;
+      float u0, u1, u2 = 0.f, u3 = 0.f;
+      if (col_full) {
+        const uint2 uu = *reinterpret_cast<const uint2*>(up);
+        const float2 f0 = unpack_bf16x2(uu.x), f1 = unpack_bf16x2(uu.y);
+        u0 = f0.x; u1 = f0.y; u2 = f1.x; u3 = f1.y;
+      } else {
+        u0 = __bfloat162float(up[0]);
+        u1 = col + 1 < p.N ? __bfloat162float(up[1]) : 0.f;
+        u2 = col + 2 < p.N ? __bfloat162float(up[2]) : 0.f;
+      }
+      if (ep.exact) {
+        x.x *= gelu_new_grad<true>(u0); x.y *= gelu_new_grad<true>(u1);
+        x.z *= gelu_new_grad<true>(u2); x.w *= gelu_new_grad<true>(u3);
+      } else {
+        x.x *= gelu_new_grad<false>(u0); x.y *= gelu_new_grad<false>(u1);
+        x.z *= gelu_new_grad<false>(u2); x.w *= gelu_new_grad<false>(u3);
+      }
+    }
+    if (ep.do_gelu) {
+      if (ep.exact) {
+        x.x = gelu_new<true>(x.x); x.y = gelu_new<true>(x.y); x.z = gelu_new<true>(x.z); x.w = gelu_new<true>(x.w);
+      } else {
+        x.x = gelu_new<false>(x.x); x.y = gelu_new<false>(x.y); x.z = gelu_new<false>(x.z); x.w = gelu_new<false>(x.w);
+      }
+    }
+    if (ep.do_drop) {
+      const uint32_t keep = ep.site.keep4((uint32_t)row, (uint32_t)col >> 2);
+      x.x = (keep & 1u) ? x.x * ep.keep_scale : 0.f;
+      x.y = (keep & 2u) ? x.y * ep.keep_scale : 0.f;
+      x.z = (keep & 4u) ? x.z * ep.keep_scale : 0.f;
+      x.w = (keep & 8u) ? x.w * ep.keep_scale : 0.f;
+    }
+    if (ep.do_res) {
+      const float* rp = p.residual + (int64_t)row * p.ldr + col;
+      if (col_full) {
+        const float4 r4 = *reinterpret_cast<const float4*>(rp);
+        x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w;
+      } else {
+        x.x += rp[0];
+        if (col + 1 < p.N) x.y += rp[1];
+        if (col + 2 < p.N) x.z += rp[2];
+      }
+    }
+    if (p.d_f32) {
+      float* dp = reinterpret_cast<float*>(p.d) + off;
+      if (ep.do_atomic) {
+        if (col_full) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dp), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w)
+                       : "memory");
+        } else {
+          atomicAdd(dp, x.x);
+          if (col + 1 < p.N) atomicAdd(dp + 1, x.y);
+          if (col + 2 < p.N) atomicAdd(dp + 2, x.z);
+        }
+      } else if (col_full) {
+        *reinterpret_cast<float4*>(dp) = x;
+      } else {
+        dp[0] = x.x;
+        if (col + 1 < p.N) dp[1] = x.y;
+        if (col + 2 < p.N) dp[2] = x.z;
+      }
+    } else {
+      __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.d) + off;
+      if (col_full) {
+        *reinterpret_cast<uint2*>(dp) = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+      } else {
+        dp[0] = __float2bfloat16_rn(x.x);
+        if (col + 1 < p.N) dp[1] = __float2bfloat16_rn(x.y);
+        if (col + 2 < p.N) dp[2] = __float2bfloat16_rn(x.z);
+      }
+    }
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
@@ -61,7 +229,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle needs 1024-byte aligned tiles
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  const uint32_t stage_all = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bar_base = stage_all + EPI_STAGING;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };
@@ -177,16 +346,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // ===================== epilogue =====================
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
     const int half = (warp - EPI_WARP0) >> 2;  // which half of the columns
-    const bool has_bias = (p.epi & ERGM_EPI_BIAS) != 0;
-    const bool do_gelu = (p.epi & ERGM_EPI_GELU) != 0;
-    const bool do_res = (p.epi & ERGM_EPI_RESIDUAL) != 0;
-    const bool do_atomic = (p.epi & ERGM_EPI_ATOMIC) != 0;
-    const bool do_drop = (p.epi & ERGM_EPI_DROPOUT) != 0;
-    const bool do_pre = (p.epi & ERGM_EPI_PREACT) != 0;
-    const bool exact = (p.epi & ERGM_EPI_EXACT) != 0;
-    const bool do_gelu_grad = (p.epi & ERGM_EPI_GELU_GRAD) != 0;
-    const float keep_scale = do_drop ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
-    const DropoutSite site = p.site.resolved();
+    const EpiFlags ep = make_epi_flags(p);
+    const uint32_t stage_smem = stage_all + (warp - EPI_WARP0) * 4096;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -209,130 +370,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        const bool full = (col0 + 32 <= p.N);
-        if (has_bias && first_split) {
-          if (full) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
-              v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < p.N) v[i] += __ldg(p.bias + col0 + i);
-          }
-        }
-        if (row_ok) {
-          if (do_pre) {
-            __nv_bfloat16* pp = reinterpret_cast<__nv_bfloat16*>(p.preact) + (int64_t)row * p.ldd + col0;
-            if (full) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                uint4 u = make_uint4(pack_bf16x2(v[i], v[i + 1]), pack_bf16x2(v[i + 2], v[i + 3]),
-                                     pack_bf16x2(v[i + 4], v[i + 5]), pack_bf16x2(v[i + 6], v[i + 7]));
-                *reinterpret_cast<uint4*>(pp + i) = u;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (col0 + i < p.N) pp[i] = __float2bfloat16_rn(v[i]);
-            }
-          }
-          if (do_gelu_grad) {
-            // v *= gelu_new'(u), u = saved pre-activation (bf16 [M, ldd]) -> dU of model.py:264
-            const __nv_bfloat16* up =
-                reinterpret_cast<const __nv_bfloat16*>(p.preact) + (int64_t)row * p.ldd + col0;
-            if (full) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                const uint4 u4 = *reinterpret_cast<const uint4*>(up + i);
-                const uint32_t uu[4] = {u4.x, u4.y, u4.z, u4.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 f = unpack_bf16x2(uu[j]);
-                  v[i + 2 * j] *= exact ? gelu_new_grad<true>(f.x) : gelu_new_grad<false>(f.x);
-                  v[i + 2 * j + 1] *= exact ? gelu_new_grad<true>(f.y) : gelu_new_grad<false>(f.y);
-                }
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (col0 + i < p.N) v[i] *= gelu_new_grad<true>(__bfloat162float(up[i]));
-            }
-          }
-          if (do_gelu) {
-            if (exact) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = gelu_new<true>(v[i]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = gelu_new<false>(v[i]);
-            }
-          }
-          if (do_drop) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const uint32_t keep = site.keep4((uint32_t)row, (uint32_t)(col0 + i) >> 2);
-              v[i] = (keep & 1u) ? v[i] * keep_scale : 0.f;
-              v[i + 1] = (keep & 2u) ? v[i + 1] * keep_scale : 0.f;
-              v[i + 2] = (keep & 4u) ? v[i + 2] * keep_scale : 0.f;
-              v[i + 3] = (keep & 8u) ? v[i + 3] * keep_scale : 0.f;
-            }
-          }
-          if (do_res) {
-            const float* rp = p.residual + (int64_t)row * p.ldr + col0;
-            if (full) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                const float4 r4 = *reinterpret_cast<const float4*>(rp + i);
-                v[i] += r4.x; v[i + 1] += r4.y; v[i + 2] += r4.z; v[i + 3] += r4.w;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (col0 + i < p.N) v[i] += rp[i];
-            }
-          }
-          if (p.d_f32) {
-            float* dp = reinterpret_cast<float*>(p.d) + (int64_t)row * p.ldd + col0;
-            if (do_atomic) {
-              if (full) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 4)
-                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dp + i),
-                               "f"(v[i]), "f"(v[i + 1]), "f"(v[i + 2]), "f"(v[i + 3])
-                               : "memory");
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (col0 + i < p.N) atomicAdd(dp + i, v[i]);
-              }
-            } else if (full) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4)
-                *reinterpret_cast<float4*>(dp + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (col0 + i < p.N) dp[i] = v[i];
-            }
-          } else {
-            __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.d) + (int64_t)row * p.ldd + col0;
-            if (full) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                uint4 u = make_uint4(pack_bf16x2(v[i], v[i + 1]), pack_bf16x2(v[i + 2], v[i + 3]),
-                                     pack_bf16x2(v[i + 4], v[i + 5]), pack_bf16x2(v[i + 6], v[i + 7]));
-                *reinterpret_cast<uint4*>(dp + i) = u;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (col0 + i < p.N) dp[i] = __float2bfloat16_rn(v[i]);
-            }
-          }
-        }
+        epilogue_chunk(p, ep, m0 + q * 32, col0, first_split, v, stage_smem, lane);
       }
       // hand the accumulator buffer back to the MMA warp
       tc_fence_before();
@@ -345,6 +383,245 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+
+// ------------------------------------------------------------------------------------------
+// CTA-pair variant: tcgen05.mma.cta_group::2, one 256 x BN output tile per 2-CTA cluster.
+// Each CTA stages its own 128 x 64 slice of A and HALF of the B tile (BN/2 x 64), the pair's
+// leader issues the MMAs for both tensor cores, accumulators land in each CTA's own TMEM
+// (128 lanes x BN columns).  Per SM and k-block this moves 16 KB (A) + BN/2*128 B (B) instead of
+// 16 KB + BN*128 B, which is what lifts the kernel off the L2->smem bandwidth / latency bound the
+// single-CTA kernel sits on (ncu: tensor pipe ~40 % active at 128x256, profiles/r1_gemm_attn.md).
+// Barriers: full[s] lives in the leader and counts the TMA bytes of BOTH CTAs; empty[s] and
+// tmem_full[a] are signalled in both CTAs by a multicast tcgen05.commit; tmem_empty[a] lives in
+// the leader and is arrived on remotely by the epilogue warps of both CTAs.
+// ------------------------------------------------------------------------------------------
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int A_BYTES = 128 * BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGING + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                  const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+  using Cfg = Gemm2Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_all = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bar_base = stage_all + EPI_STAGING;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 2 * NUM_EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int tiles_mn = p.m_tiles * p.n_tiles;  // m_tiles counts 256-row tiles here
+  const int total_tiles = tiles_mn * p.split_k;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        const int split = tile / tiles_mn;
+        const int mn = tile - split * tiles_mn;
+        const int m0 = (mn % p.m_tiles) * 256 + (int)rank * 128;
+        const int n0 = (mn / p.m_tiles) * BN + (int)rank * (BN / 2);
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint32_t fb = mapa_cluster(full_bar(stage), 0);  // the leader's barrier
+          if (leader) mbar_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+          const int k0 = kb * BK;
+          if (!p.a_mn) {
+            tma_load_2d_2sm(sa, &tmap_a, fb, k0, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) tma_load_2d_2sm(sa + j * 8192, &tmap_a, fb, m0 + 64 * j, k0);
+          }
+          if (!p.b_mn) {
+            tma_load_2d_2sm(sb, &tmap_b, fb, k0, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 128; ++j) tma_load_2d_2sm(sb + j * 8192, &tmap_b, fb, n0 + 64 * j, k0);
+          }
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && leader) {
+      const uint32_t idesc = make_idesc_bf16(256, BN, p.a_mn, p.b_mn);
+      const uint32_t a_lbo = p.a_mn ? 8192u : 16u, a_kstep = p.a_mn ? 2048u : 32u;
+      const uint32_t b_lbo = p.b_mn ? 8192u : 16u, b_kstep = p.b_mn ? 2048u : 32u;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        const int split = tile / tiles_mn;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < BK / 16; ++ks) {
+            const uint64_t adesc = make_smem_desc_sw128(sa + ks * a_kstep, a_lbo, 1024);
+            const uint64_t bdesc = make_smem_desc_sw128(sb + ks * b_kstep, b_lbo, 1024);
+            umma_ss_2sm(d_tmem, adesc, bdesc, idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
+          }
+          umma_commit_2sm(empty_bar(stage), 3);  // frees the slot in BOTH CTAs
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(tfull_bar(acc), 3);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ===================== epilogue (both CTAs, own 128 rows) =====================
+    const int q = warp & 3;
+    const int half = (warp - EPI_WARP0) >> 2;
+    const EpiFlags ep = make_epi_flags(p);
+    const uint32_t stage_smem = stage_all + (warp - EPI_WARP0) * 4096;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      const int split = tile / tiles_mn;
+      const int mn = tile - split * tiles_mn;
+      const int m0 = (mn % p.m_tiles) * 256 + (int)rank * 128;
+      const int n0 = (mn / p.m_tiles) * BN;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const bool first_split = (split == 0);
+#pragma unroll 1
+      for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
+        const int col0 = n0 + c;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        epilogue_chunk(p, ep, m0 + q * 32, col0, first_split, v, stage_smem, lane);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_cluster(tempty_bar(acc), 0));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync();
+  if (warp == 2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int BN>
+static int launch_gemm2(const ergm_gemm_args* a, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BN>;
+  CUtensorMap ta, tb;
+  int rc;
+  if (a->a_major == ERGM_MAJOR_K)
+    rc = encode_tmap_2d(&ta, a->a, 2, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda * 2, BK, 128);
+  else
+    rc = encode_tmap_2d(&ta, a->a, 2, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda * 2, 64, BK);
+  if (rc) return rc;
+  if (a->b_major == ERGM_MAJOR_K)
+    rc = encode_tmap_2d(&tb, a->b, 2, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb * 2, BK, BN / 2);
+  else
+    rc = encode_tmap_2d(&tb, a->b, 2, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb * 2, 64, BK);
+  if (rc) return rc;
+  GemmParams p;
+  p.d = a->d; p.bias = a->bias; p.residual = a->residual; p.preact = a->preact;
+  p.ldd = a->ldd; p.ldr = a->ldr;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.a_mn = a->a_major == ERGM_MAJOR_MN; p.b_mn = a->b_major == ERGM_MAJOR_MN;
+  p.d_f32 = a->d_dtype == ERGM_DT_F32;
+  p.epi = a->epilogue;
+  p.split_k = a->split_k < 1 ? 1 : a->split_k;
+  p.m_tiles = (a->M + 255) / 256;
+  p.n_tiles = (a->N + BN - 1) / BN;
+  p.kb_total = (a->K + BK - 1) / BK;
+  if (p.split_k > p.kb_total) p.split_k = p.kb_total;
+  p.kb_per_split = (p.kb_total + p.split_k - 1) / p.split_k;
+  p.split_k = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  p.dropout_p = a->dropout_p;
+  p.site = make_site(a->seed, a->offset, a->dropout_p, (uint32_t)a->N);
+  static bool attr_set = false;
+  if (!attr_set) {
+    ERGM_CUDA_TRY(cudaFuncSetAttribute(gemm2_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int total = p.m_tiles * p.n_tiles * p.split_k;
+  const int max_clusters = num_sms() / 2;
+  const int clusters = total < max_clusters ? total : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return (int)cudaLaunchKernelEx(&cfg, gemm2_bf16_kernel<BN>, ta, tb, p);
 }
 
 template <int BN>
@@ -419,6 +696,18 @@ extern "C" int ergm_gemm_bf16(const ergm_gemm_args* a, void* stream) {
   if (a->lda % 8 || a->ldb % 8) return ERGM_ERR_ARG;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   int bn = a->block_n;
+  if (bn == 2256) return launch_gemm2<256>(a, s);
+  if (bn == 2128) return launch_gemm2<128>(a, s);
+  if (bn == 0 && a->M >= 512 && a->N >= 128) {
+    // CTA-pair kernel (cta_group::2): 256-row tiles; pick the N tile that fills the 74 clusters best
+    const long mt2 = (a->M + 255) / 256;
+    const int sk = a->split_k < 1 ? 1 : a->split_k;
+    const long t256 = mt2 * ((a->N + 255) / 256) * sk, t128 = mt2 * ((a->N + 127) / 128) * sk;
+    const int nc = num_sms() / 2;
+    auto eff = [&](long tiles) { return (double)tiles / (double)(((tiles + nc - 1) / nc) * nc); };
+    if (a->N >= 256 && eff(t256) >= eff(t128) - 0.08) return launch_gemm2<256>(a, s);
+    return launch_gemm2<128>(a, s);
+  }
   if (bn == 0) {
     // auto: widest tile that still yields at least ~1 wave of CTAs
     const long mt = (a->M + BM - 1) / BM;

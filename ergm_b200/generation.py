@@ -152,7 +152,7 @@ def generate(model, input_ids, token_type_ids=None, max_new_tokens=64, do_sample
                     with torch.cuda.graph(g):
                         decode_step(eng, st, sample_kw)
                     st.graph = g
-                    for _ in range(n_steps - 2):
+                    for _ in range(n_steps - 1):  # capture itself executes nothing
                         g.replay()
             else:
                 for _ in range(n_steps):

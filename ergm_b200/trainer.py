@@ -11,6 +11,8 @@ model(**batch).loss.backward(); optimizer.step() runs eagerly (same C-ABI calls,
 Learning-rate / bias-correction values and the dropout step counter live in device memory, so
 the replayed kernels see fresh values every step.
 """
+import os
+
 import torch
 
 from . import ops
@@ -23,6 +25,11 @@ class GraphedTrainStep:
         self.model = model
         self.opt = optimizer
         self.dp = dp if dp is not None else getattr(model, "_dp", None)
+        # NCCL collectives are kept out of CUDA-graph capture: under DataParallel the step runs eagerly
+        # (the host stays ahead of the GPU: ~900 C-ABI calls/step at a few us each vs >10 ms of GPU work)
+        # so that the bucketed all-reduces are ordinary async NCCL launches overlapping the backward.
+        if self.dp is not None and getattr(self.dp, "world", 1) > 1 and os.environ.get("ERGM_DP_GRAPH", "0") != "1":
+            use_graph = False
         self.use_graph = use_graph
         self.graphs = {}
         self.static = {}

@@ -72,7 +72,8 @@ typedef struct ergm_gemm_args {
   int32_t d_dtype;
   int32_t epilogue;    /* ERGM_EPI_* bitmask */
   int32_t split_k;     /* >=1; >1 requires ERGM_EPI_ATOMIC and fp32 D */
-  int32_t block_n;     /* 0 = auto, else 64 / 128 / 256 */
+  int32_t block_n;     /* 0 = auto; 64 / 128 / 256 = single-CTA tile width;
+                          2128 / 2256 = CTA-pair (cta_group::2) kernel, 256 x {128,256} tiles */
   float dropout_p;
   uint64_t seed, offset; /* Philox key / subsequence of this dropout site */
 } ergm_gemm_args;

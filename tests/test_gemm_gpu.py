@@ -15,7 +15,10 @@ def _ref(a, b, a_mn, b_mn):
 def _run(M, N, K, a_mn, b_mn, block_n=0, out_dtype=torch.float32, split_k=1, atomic=False, seed=0):
     from ergm_b200 import ops, _lib as L
     g = torch.Generator(device="cuda").manual_seed(seed)
-    a = torch.randn((K, M) if a_mn else (M, K), device="cuda", generator=g).bfloat16()
+    if a_mn:
+        a = torch.randn(K, (M + 7) // 8 * 8, device="cuda", generator=g).bfloat16()[:, :M]
+    else:
+        a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
     if b_mn:  # rows of a TMA operand must be 16-byte aligned: pad the leading dimension
         b = torch.randn(K, (N + 7) // 8 * 8, device="cuda", generator=g).bfloat16()[:, :N]
     else:
@@ -37,6 +40,38 @@ def _run(M, N, K, a_mn, b_mn, block_n=0, out_dtype=torch.float32, split_k=1, ato
 def test_gemm_majors(cuda_device, a_mn, b_mn, block_n):
     err, scale, _ = _run(256, 512, 320, a_mn, b_mn, block_n)
     assert err <= 2e-3 * scale, (err, scale)
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize("block_n", [2128, 2256])
+@pytest.mark.parametrize("M,N,K", [(512, 512, 320), (300, 200, 136), (8192, 768, 768)])
+def test_gemm_cta_pair(cuda_device, a_mn, b_mn, block_n, M, N, K):
+    """tcgen05.mma.cta_group::2 kernel: 256-row tiles split over a 2-CTA cluster."""
+    err, scale, d = _run(M, N, K, a_mn, b_mn, block_n)
+    assert err <= 2e-3 * scale, (err, scale)
+    if d.shape[1] > N:
+        assert d[:, N:].abs().max().item() == 0
+
+
+def test_gemm_cta_pair_splitk_and_epilogues(cuda_device):
+    from ergm_b200 import ops, _lib as L
+    err, scale, _ = _run(768, 768, 4096, 1, 1, block_n=2128, split_k=4, atomic=True)
+    assert err <= 2e-3 * scale
+    M, N, K = 1000, 3072, 768
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(K, N, device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g)
+    ref = a.float() @ w.float() + bias
+    out = res.clone()
+    ops.gemm(a, w, out, M=M, N=N, K=K, bias=bias, residual=out, block_n=2256)
+    assert (out - (ref + res)).abs().max().item() < 1e-4
+    d = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    pre = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, d, M=M, N=N, K=K, bias=bias, preact=pre, epilogue=L.EPI_GELU, block_n=2256)
+    assert (d.float() - torch.nn.functional.gelu(ref, approximate="tanh")).abs().max().item() < 2e-2
+    assert (pre.float() - ref).abs().max().item() < 2e-2
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (8192, 2304, 768), (100, 72, 200), (1, 8, 8),
