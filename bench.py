@@ -312,12 +312,20 @@ def main():
             by = {}
             for n, i, a, b in prof:
                 by[n] = by.get(n, 0.0) + a.elapsed_time(b) / 2
+            shapes = {}
+            for n, i, a, b in prof:
+                if n == "ergm_gemm_bf16":
+                    k = "M%d N%d K%d a%d b%d sk%d" % i
+                    t, c = shapes.get(k, (0.0, 0))
+                    shapes[k] = (t + a.elapsed_time(b) / 2, c + 0.5)
+            by_shape = {k: {"ms": round(t, 3), "launches": c, "tflops": round(gemm_flops([int(x[1:]) for x in k.split()[:3]]) * c / (t / 1e3) / 1e12, 1)}
+                        for k, (t, c) in sorted(shapes.items(), key=lambda kv: -kv[1][0])}
             achieved = g_fl / (g_ms / 1e3) / 1e12
             roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": achieved,
                     "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sust"],
                     "peak_source": pk["src"] + " (sustained bf16)", "traffic": None,
                     "gemm_launches_per_step": n_gemm, "gemm_ms_per_step": g_ms, "gemm_flops_per_step": g_fl,
-                    "avg_launch_us": 1e3 * g_ms / max(n_gemm, 1),
+                    "avg_launch_us": 1e3 * g_ms / max(n_gemm, 1), "gemm_by_shape": by_shape,
                     "eager_ms_by_entry_point": {k: round(v, 3) for k, v in sorted(by.items(), key=lambda kv: -kv[1])}}
             step.eng.set_rng_step_tensor(step.rng_step)
     fl_tok, gemm_fl_tok = train_flops_per_token(H, L, VOCAB, SEQ, SEQ, caption=True)

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) embed_fuse_fwd_kernel(const Em
   p.drop = p_in.drop.resolved();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rows = p.B * p.T;
-  const float keep_scale = p.do_drop ? 1.f / (1.f - p.drop.p) : 1.f;
+  const float keep_scale = p.do_drop ? p.drop.keep_scale() : 1.f;
   for (int row = blockIdx.x * ROW_WARPS + warp; row < rows; row += gridDim.x * ROW_WARPS) {
     const int b = row / p.T, t = row - b * p.T;
     const int64_t id = p.ids[row];
@@ -121,7 +121,7 @@ __global__ void embed_bwd_kernel(const EmbedBwdParams p_in) {
   if (c >= p.H / 4) return;
   const int r0 = blockIdx.x * p.rows_per_cta;
   const int r1 = min(r0 + p.rows_per_cta, p.rows);
-  const float keep_scale = p.do_drop ? 1.f / (1.f - p.drop.p) : 1.f;
+  const float keep_scale = p.do_drop ? p.drop.keep_scale() : 1.f;
   int64_t cur[3] = {-1, -1, -1};
   float4 acc[3];
 #pragma unroll
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) ln_bwd_kernel(const LnBwdParam
   p.drop = p_in.drop.resolved();
   __shared__ float red[ROW_WARPS][H];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float keep_scale = p.do_drop ? 1.f / (1.f - p.drop.p) : 1.f;
+  const float keep_scale = p.do_drop ? p.drop.keep_scale() : 1.f;
   float4 gm[NV], ag[NV], ab[NV], an[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -349,6 +349,50 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ src, int64_t ld, int rows, 
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += red[w][c];
     atomicAdd(out + blockIdx.x * 256 + c, s);
+  }
+}
+
+// GELU backward fused with the c_fc bias gradient (model.py:263-264 backward):
+//   dU = dG * gelu_new'(U)  (in place over dG, bf16), colsum[n] += sum_rows dU[., n]
+// Kept out of the dgrad GEMM epilogue on purpose: there the U tile would have to be fetched by
+// demand loads that queue behind the mainloop's saturated TMA stream (measured +80 us per GEMM).
+__global__ void __launch_bounds__(256)
+gelu_bwd_colsum_kernel(__nv_bfloat16* __restrict__ dg, const __nv_bfloat16* __restrict__ u, int64_t ld,
+                       int rows, int N, float* __restrict__ colsum, int rows_per_cta, int exact) {
+  __shared__ float red[8][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col0 = blockIdx.x * 256 + lane * 8;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(r0 + rows_per_cta, rows);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col0 < N) {
+    for (int r = r0 + warp; r < r1; r += 8) {
+      uint4 g4 = *reinterpret_cast<const uint4*>(dg + (int64_t)r * ld + col0);
+      const uint4 u4 = *reinterpret_cast<const uint4*>(u + (int64_t)r * ld + col0);
+      uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w};
+      const uint32_t uw[4] = {u4.x, u4.y, u4.z, u4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 g = unpack_bf16x2(gw[j]), uu = unpack_bf16x2(uw[j]);
+        const float d0 = g.x * (exact ? gelu_new_grad<true>(uu.x) : gelu_new_grad<false>(uu.x));
+        const float d1 = g.y * (exact ? gelu_new_grad<true>(uu.y) : gelu_new_grad<false>(uu.y));
+        gw[j] = pack_bf16x2(d0, d1);
+        const float2 rr = unpack_bf16x2(gw[j]);  // sum what the GEMMs will actually read
+        acc[2 * j] += rr.x;
+        acc[2 * j + 1] += rr.y;
+      }
+      *reinterpret_cast<uint4*>(dg + (int64_t)r * ld + col0) = make_uint4(gw[0], gw[1], gw[2], gw[3]);
+    }
+  }
+  if (!colsum) return;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = acc[i];
+  __syncthreads();
+  const int c = threadIdx.x;
+  if (blockIdx.x * 256 + c < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][c];
+    atomicAdd(colsum + blockIdx.x * 256 + c, s);
   }
 }
 
@@ -492,6 +536,19 @@ extern "C" int ergm_colsum_bf16(const void* src, int64_t ld, int rows, int N, fl
   const int rpc = (rows + row_splits - 1) / row_splits;
   colsum_bf16_kernel<<<dim3(col_ctas, (rows + rpc - 1) / rpc), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(src), ld, rows, N, out, rpc);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int ergm_gelu_bwd_colsum(void* dg_bf16, const void* u_bf16, int64_t ld, int rows, int N,
+                                    float* colsum, int exact, void* stream) {
+  if (!dg_bf16 || !u_bf16 || rows <= 0 || N <= 0 || N % 8 || ld % 8) return ERGM_ERR_ARG;
+  const int col_ctas = (N + 255) / 256;
+  int row_splits = (4 * num_sms() + col_ctas - 1) / col_ctas;
+  if (row_splits > (rows + 63) / 64) row_splits = (rows + 63) / 64;
+  const int rpc = (rows + row_splits - 1) / row_splits;
+  gelu_bwd_colsum_kernel<<<dim3(col_ctas, (rows + rpc - 1) / rpc), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<__nv_bfloat16*>(dg_bf16), reinterpret_cast<const __nv_bfloat16*>(u_bf16), ld, rows, N,
+      colsum, rpc, exact);
   return (int)cudaGetLastError();
 }
 

@@ -71,20 +71,51 @@ ERGM_DEVINL EpiFlags make_epi_flags(const GemmParams& p) {
   e.do_pre = (p.epi & ERGM_EPI_PREACT) != 0;
   e.exact = (p.epi & ERGM_EPI_EXACT) != 0;
   e.do_gelu_grad = (p.epi & ERGM_EPI_GELU_GRAD) != 0;
-  e.keep_scale = e.do_drop ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
   e.site = p.site.resolved();
+  e.keep_scale = e.do_drop ? e.site.keep_scale() : 1.0f;
   return e;
 }
+
+// Scalar tail path of the epilogue: the lane's 4 columns straddle N (only the last column chunk of a
+// matrix whose N is not a multiple of 4, e.g. V = 50260 ... never on the hot path).  Kept out of line
+// so the unrolled fast path stays small enough for the instruction cache.
+__device__ __noinline__ void epilogue_tail(void* d, void* preact, const float* residual, int64_t ldd, int64_t ldr,
+                                           int N, int d_f32, int epi, uint32_t keep, float keep_scale, int row,
+                                           int col, float4 x) {
+  const float xv[4] = {x.x, x.y, x.z, x.w};
+  for (int j = 0; j < 4; ++j) {
+    if (col + j >= N) break;
+    const int64_t off = (int64_t)row * ldd + col + j;
+    float y = xv[j];
+    if (epi & ERGM_EPI_PREACT) reinterpret_cast<__nv_bfloat16*>(preact)[off] = __float2bfloat16_rn(y);
+    if (epi & ERGM_EPI_GELU_GRAD) y *= gelu_new_grad<true>(__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(preact)[off]));
+    if (epi & ERGM_EPI_GELU) y = gelu_new<true>(y);
+    if (epi & ERGM_EPI_DROPOUT) y = ((keep >> j) & 1u) ? y * keep_scale : 0.f;
+    if (epi & ERGM_EPI_RESIDUAL) y += residual[(int64_t)row * ldr + col + j];
+    if (d_f32) {
+      float* dp = reinterpret_cast<float*>(d) + off;
+      if (epi & ERGM_EPI_ATOMIC) atomicAdd(dp, y); else *dp = y;
+    } else {
+      reinterpret_cast<__nv_bfloat16*>(d)[off] = __float2bfloat16_rn(y);
+    }
+  }
+}
+
+// Epilogue classes: which fused variants a kernel instantiation carries (keeps each instantiation's
+// unrolled epilogue small enough for the instruction cache).
+enum { EC_LINEAR = 0, EC_GELU = 1, EC_GELU_GRAD = 2, EC_EXACT = 3 };
 
 // Fused epilogue of one 32-row x 32-column chunk of an accumulator tile, per warp.
 //
 // tcgen05.ld hands every thread one accumulator ROW (32 consecutive columns).  Storing from that
-// layout makes each warp-wide 16-byte store touch 32 different 128-byte lines (measured: 12 us of a
-// 36 us QKV GEMM, profiles/r1_gemm_epilogue.md).  The chunk is therefore transposed through a
-// per-warp, XOR-swizzled 4 KB shared-memory tile: afterwards lane l owns 4 consecutive columns
-// (float4) of rows {4*it + l/8}, so that one warp instruction reads / writes four fully coalesced
-// 128-byte row segments (fp32) or 64-byte segments (bf16).  All fused work is done in that layout:
+// layout makes each warp-wide 16-byte access touch 32 different 128-byte lines.  The chunk is
+// therefore transposed through a per-warp, XOR-swizzled 4 KB shared-memory tile: afterwards lane l
+// owns 4 consecutive columns (float4) of rows {4*it + l/8}, so one warp instruction reads / writes
+// four fully coalesced 128-byte (fp32) or 64-byte (bf16) row segments.  The residual / saved
+// pre-activation operands of all 8 row groups are fetched up front (before the transposition) so
+// their latency overlaps instead of serialising.  Fused order:
 // bias -> (store pre-activation) -> GELU' / GELU -> dropout -> + residual -> store / red.add.
+template <int EC>
 ERGM_DEVINL void epilogue_chunk(const GemmParams& p, const EpiFlags& ep, int row0, int col0, bool first_split,
                                 const float (&v)[32], uint32_t stage_smem, int lane) {
   if (p.epi & (1 << 30)) {  // timing experiment: no global traffic at all
@@ -94,20 +125,31 @@ ERGM_DEVINL void epilogue_chunk(const GemmParams& p, const EpiFlags& ep, int row
     if (acc == 123.456f) reinterpret_cast<float*>(p.d)[0] = acc;
     return;
   }
-  // ---- transpose: row-per-thread -> (row group, float4 column) per lane ----
-  if (!(p.epi & (1 << 28))) __syncwarp();  // previous chunk's reads of the staging tile are done
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const uint32_t addr = stage_smem + lane * 128 + ((uint32_t)(c ^ (lane & 7)) << 4);
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[4 * c]), "f"(v[4 * c + 1]),
-                 "f"(v[4 * c + 2]), "f"(v[4 * c + 3])
-                 : "memory");
-  }
-  if (!(p.epi & (1 << 28))) __syncwarp();
   const int c4 = lane & 7;             // float4 column index inside the chunk
+  const int rsub = lane >> 3;          // row inside each group of 4
   const int col = col0 + 4 * c4;       // first of this lane's 4 columns
   const bool col_full = col + 4 <= p.N;
   const bool col_any = col < p.N;
+  // ---- operand prefetch ----
+  float4 res[8];
+  uint2 pre[8];
+  if (ep.do_res && col_full) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = row0 + 4 * it + rsub;
+      res[it] = row < p.M ? *reinterpret_cast<const float4*>(p.residual + (int64_t)row * p.ldr + col)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  if ((EC == EC_GELU_GRAD || EC == EC_EXACT) && ep.do_gelu_grad && col_full) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = row0 + 4 * it + rsub;
+      pre[it] = row < p.M ? *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.preact) +
+                                                            (int64_t)row * p.ldd + col)
+                          : make_uint2(0u, 0u);
+    }
+  }
   float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (ep.has_bias && first_split && col_any) {
     if (col_full) {
@@ -118,10 +160,19 @@ ERGM_DEVINL void epilogue_chunk(const GemmParams& p, const EpiFlags& ep, int row
       if (col + 2 < p.N) b4.z = __ldg(p.bias + col + 2);
     }
   }
-  // not unrolled on purpose: the body carries every fused variant, 8 copies overflow the I-cache
-#pragma unroll 1
+  // ---- transpose: row-per-thread -> (row group, float4 column) per lane ----
+  __syncwarp();  // previous chunk's reads of the staging tile are done
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint32_t addr = stage_smem + lane * 128 + ((uint32_t)(c ^ (lane & 7)) << 4);
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[4 * c]), "f"(v[4 * c + 1]),
+                 "f"(v[4 * c + 2]), "f"(v[4 * c + 3])
+                 : "memory");
+  }
+  __syncwarp();
+#pragma unroll
   for (int it = 0; it < 8; ++it) {
-    const int r = 4 * it + (lane >> 3);
+    const int r = 4 * it + rsub;
     const int row = row0 + r;
     float4 x;
     {
@@ -129,48 +180,30 @@ ERGM_DEVINL void epilogue_chunk(const GemmParams& p, const EpiFlags& ep, int row
       asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(addr));
     }
     if (row >= p.M || !col_any) continue;
+    if (!col_full) {
+      const uint32_t keep = ep.do_drop ? ep.site.keep4((uint32_t)row, (uint32_t)col >> 2) : 0xfu;
+      epilogue_tail(p.d, p.preact, p.residual, p.ldd, p.ldr, p.N, p.d_f32, p.epi, keep, ep.keep_scale, row, col,
+                    make_float4(x.x + b4.x, x.y + b4.y, x.z + b4.z, x.w + b4.w));
+      continue;
+    }
     if (p.epi & (1 << 29)) {  // timing experiment: transposition only, no global traffic
       if (x.x == 123.456f) reinterpret_cast<float*>(p.d)[0] = x.y;
       continue;
     }
     x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
     const int64_t off = (int64_t)row * p.ldd + col;
-    if (ep.do_pre) {
-      __nv_bfloat16* pp = reinterpret_cast<__nv_bfloat16*>(p.preact) + off;
-      if (col_full) {
-        *reinterpret_cast<uint2*>(pp) = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
-      } else {
-        pp[0] = __float2bfloat16_rn(x.x);
-        if (col + 1 < p.N) pp[1] = __float2bfloat16_rn(x.y);
-        if (col + 2 < p.N) pp[2] = __float2bfloat16_rn(x.z);
-      }
+    if ((EC == EC_GELU || EC == EC_EXACT) && ep.do_pre)
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.preact) + off) =
+          make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+    if ((EC == EC_GELU_GRAD || EC == EC_EXACT) && ep.do_gelu_grad) {  // x *= gelu_new'(u) (model.py:264 backward)
+      const float2 f0 = unpack_bf16x2(pre[it].x), f1 = unpack_bf16x2(pre[it].y);
+      constexpr bool kExact = (EC == EC_EXACT);
+      x.x *= gelu_new_grad<kExact>(f0.x); x.y *= gelu_new_grad<kExact>(f0.y);
+      x.z *= gelu_new_grad<kExact>(f1.x); x.w *= gelu_new_grad<kExact>(f1.y);
     }
-    if (ep.do_gelu_grad) {  // x *= gelu_new'(u), u = saved pre-activation (model.py:264 backward)
-      const __nv_bfloat16* up = reinterpret_cast<const __nv_bfloat16*>(p.preact) + off;
-      float u0, u1, u2 = 0.f, u3 = 0.f;
-      if (col_full) {
-        const uint2 uu = *reinterpret_cast<const uint2*>(up);
-        const float2 f0 = unpack_bf16x2(uu.x), f1 = unpack_bf16x2(uu.y);
-        u0 = f0.x; u1 = f0.y; u2 = f1.x; u3 = f1.y;
-      } else {
-        u0 = __bfloat162float(up[0]);
-        u1 = col + 1 < p.N ? __bfloat162float(up[1]) : 0.f;
-        u2 = col + 2 < p.N ? __bfloat162float(up[2]) : 0.f;
-      }
-      if (ep.exact) {
-        x.x *= gelu_new_grad<true>(u0); x.y *= gelu_new_grad<true>(u1);
-        x.z *= gelu_new_grad<true>(u2); x.w *= gelu_new_grad<true>(u3);
-      } else {
-        x.x *= gelu_new_grad<false>(u0); x.y *= gelu_new_grad<false>(u1);
-        x.z *= gelu_new_grad<false>(u2); x.w *= gelu_new_grad<false>(u3);
-      }
-    }
-    if (ep.do_gelu) {
-      if (ep.exact) {
-        x.x = gelu_new<true>(x.x); x.y = gelu_new<true>(x.y); x.z = gelu_new<true>(x.z); x.w = gelu_new<true>(x.w);
-      } else {
-        x.x = gelu_new<false>(x.x); x.y = gelu_new<false>(x.y); x.z = gelu_new<false>(x.z); x.w = gelu_new<false>(x.w);
-      }
+    if ((EC == EC_GELU || EC == EC_EXACT) && ep.do_gelu) {
+      constexpr bool kExact = (EC == EC_EXACT);
+      x.x = gelu_new<kExact>(x.x); x.y = gelu_new<kExact>(x.y); x.z = gelu_new<kExact>(x.z); x.w = gelu_new<kExact>(x.w);
     }
     if (ep.do_drop) {
       const uint32_t keep = ep.site.keep4((uint32_t)row, (uint32_t)col >> 2);
@@ -179,49 +212,22 @@ ERGM_DEVINL void epilogue_chunk(const GemmParams& p, const EpiFlags& ep, int row
       x.z = (keep & 4u) ? x.z * ep.keep_scale : 0.f;
       x.w = (keep & 8u) ? x.w * ep.keep_scale : 0.f;
     }
-    if (ep.do_res) {
-      const float* rp = p.residual + (int64_t)row * p.ldr + col;
-      if (col_full) {
-        const float4 r4 = *reinterpret_cast<const float4*>(rp);
-        x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w;
-      } else {
-        x.x += rp[0];
-        if (col + 1 < p.N) x.y += rp[1];
-        if (col + 2 < p.N) x.z += rp[2];
-      }
-    }
+    if (ep.do_res) { x.x += res[it].x; x.y += res[it].y; x.z += res[it].z; x.w += res[it].w; }
     if (p.d_f32) {
       float* dp = reinterpret_cast<float*>(p.d) + off;
-      if (ep.do_atomic) {
-        if (col_full) {
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dp), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w)
-                       : "memory");
-        } else {
-          atomicAdd(dp, x.x);
-          if (col + 1 < p.N) atomicAdd(dp + 1, x.y);
-          if (col + 2 < p.N) atomicAdd(dp + 2, x.z);
-        }
-      } else if (col_full) {
+      if (ep.do_atomic)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dp), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w)
+                     : "memory");
+      else
         *reinterpret_cast<float4*>(dp) = x;
-      } else {
-        dp[0] = x.x;
-        if (col + 1 < p.N) dp[1] = x.y;
-        if (col + 2 < p.N) dp[2] = x.z;
-      }
     } else {
-      __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.d) + off;
-      if (col_full) {
-        *reinterpret_cast<uint2*>(dp) = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
-      } else {
-        dp[0] = __float2bfloat16_rn(x.x);
-        if (col + 1 < p.N) dp[1] = __float2bfloat16_rn(x.y);
-        if (col + 2 < p.N) dp[2] = __float2bfloat16_rn(x.z);
-      }
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.d) + off) =
+          make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
     }
   }
 }
 
-template <int BN>
+template <int BN, int EC>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
                  const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
@@ -370,7 +376,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        epilogue_chunk(p, ep, m0 + q * 32, col0, first_split, v, stage_smem, lane);
+        epilogue_chunk<EC>(p, ep, m0 + q * 32, col0, first_split, v, stage_smem, lane);
       }
       // hand the accumulator buffer back to the MMA warp
       tc_fence_before();
@@ -407,7 +413,7 @@ struct Gemm2Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGING + 1024 + 256;
 };
 
-template <int BN>
+template <int BN, int EC>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
                   const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
@@ -555,7 +561,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        epilogue_chunk(p, ep, m0 + q * 32, col0, first_split, v, stage_smem, lane);
+        epilogue_chunk<EC>(p, ep, m0 + q * 32, col0, first_split, v, stage_smem, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -569,7 +575,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp == 2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int BN>
+template <int BN, int EC>
 static int launch_gemm2(const ergm_gemm_args* a, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<BN>;
   CUtensorMap ta, tb;
@@ -602,7 +608,7 @@ static int launch_gemm2(const ergm_gemm_args* a, cudaStream_t stream) {
   p.site = make_site(a->seed, a->offset, a->dropout_p, (uint32_t)a->N);
   static bool attr_set = false;
   if (!attr_set) {
-    ERGM_CUDA_TRY(cudaFuncSetAttribute(gemm2_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ERGM_CUDA_TRY(cudaFuncSetAttribute(gemm2_bf16_kernel<BN, EC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::SMEM_BYTES));
     attr_set = true;
   }
@@ -621,10 +627,10 @@ static int launch_gemm2(const ergm_gemm_args* a, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return (int)cudaLaunchKernelEx(&cfg, gemm2_bf16_kernel<BN>, ta, tb, p);
+  return (int)cudaLaunchKernelEx(&cfg, gemm2_bf16_kernel<BN, EC>, ta, tb, p);
 }
 
-template <int BN>
+template <int BN, int EC>
 static int launch_gemm(const ergm_gemm_args* a, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   CUtensorMap ta, tb;
@@ -660,13 +666,13 @@ static int launch_gemm(const ergm_gemm_args* a, cudaStream_t stream) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    ERGM_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_kernel<BN>,
+    ERGM_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_kernel<BN, EC>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int total = p.m_tiles * p.n_tiles * p.split_k;
   const int grid = total < num_sms() ? total : num_sms();
-  gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  gemm_bf16_kernel<BN, EC><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
   return (int)cudaGetLastError();
 }
 
@@ -696,8 +702,6 @@ extern "C" int ergm_gemm_bf16(const ergm_gemm_args* a, void* stream) {
   if (a->lda % 8 || a->ldb % 8) return ERGM_ERR_ARG;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   int bn = a->block_n;
-  if (bn == 2256) return launch_gemm2<256>(a, s);
-  if (bn == 2128) return launch_gemm2<128>(a, s);
   if (bn == 0 && a->M >= 512 && a->N >= 128) {
     // CTA-pair kernel (cta_group::2): 256-row tiles; pick the N tile that fills the 74 clusters best
     const long mt2 = (a->M + 255) / 256;
@@ -705,8 +709,7 @@ extern "C" int ergm_gemm_bf16(const ergm_gemm_args* a, void* stream) {
     const long t256 = mt2 * ((a->N + 255) / 256) * sk, t128 = mt2 * ((a->N + 127) / 128) * sk;
     const int nc = num_sms() / 2;
     auto eff = [&](long tiles) { return (double)tiles / (double)(((tiles + nc - 1) / nc) * nc); };
-    if (a->N >= 256 && eff(t256) >= eff(t128) - 0.08) return launch_gemm2<256>(a, s);
-    return launch_gemm2<128>(a, s);
+    bn = (a->N >= 256 && eff(t256) >= eff(t128) - 0.08) ? 2256 : 2128;
   }
   if (bn == 0) {
     // auto: widest tile that still yields at least ~1 wave of CTAs
@@ -715,10 +718,25 @@ extern "C" int ergm_gemm_bf16(const ergm_gemm_args* a, void* stream) {
     bn = 256;
     while (bn > 64 && mt * ((a->N + bn - 1) / bn) * sk < num_sms()) bn >>= 1;
   }
+  int ec = EC_LINEAR;
+  if (a->epilogue & ERGM_EPI_EXACT) ec = EC_EXACT;
+  else if (a->epilogue & ERGM_EPI_GELU) ec = EC_GELU;
+  else if (a->epilogue & ERGM_EPI_GELU_GRAD) ec = EC_GELU_GRAD;
+  else if (a->epilogue & ERGM_EPI_PREACT) ec = EC_GELU;
+#define ERGM_DISPATCH_EC(FN, BNV)                                   \
+  switch (ec) {                                                     \
+    case EC_LINEAR: return FN<BNV, EC_LINEAR>(a, s);                \
+    case EC_GELU: return FN<BNV, EC_GELU>(a, s);                    \
+    case EC_GELU_GRAD: return FN<BNV, EC_GELU_GRAD>(a, s);          \
+    default: return FN<BNV, EC_EXACT>(a, s);                        \
+  }
   switch (bn) {
-    case 256: return launch_gemm<256>(a, s);
-    case 128: return launch_gemm<128>(a, s);
-    case 64: return launch_gemm<64>(a, s);
+    case 2256: ERGM_DISPATCH_EC(launch_gemm2, 256)
+    case 2128: ERGM_DISPATCH_EC(launch_gemm2, 128)
+    case 256: ERGM_DISPATCH_EC(launch_gemm, 256)
+    case 128: ERGM_DISPATCH_EC(launch_gemm, 128)
+    case 64: ERGM_DISPATCH_EC(launch_gemm, 64)
     default: return ERGM_ERR_ARG;
   }
+#undef ERGM_DISPATCH_EC
 }

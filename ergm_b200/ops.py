@@ -165,6 +165,11 @@ def colsum_bf16(src, out, *, rows=None, N=None, ld=None):
     _call("ergm_colsum_bf16", src.data_ptr(), src.stride(0) if ld is None else ld, rows, N, out.data_ptr())
 
 
+def gelu_bwd_colsum(dg, u, colsum, exact=False):
+    rows, N = dg.shape
+    _call("ergm_gelu_bwd_colsum", dg.data_ptr(), u.data_ptr(), dg.stride(0), rows, N, _p(colsum), int(exact))
+
+
 def cast_f32_bf16_2d(src, dst, colsum=None):
     rows, N = src.shape
     _call("ergm_cast_f32_bf16_2d", src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), rows, N, _p(colsum))

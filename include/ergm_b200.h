@@ -122,6 +122,10 @@ int ergm_ln_bwd(const void* dy, int dy_is_f32, const float* x, const float* mean
                 float dropout_p, uint64_t seed, uint64_t offset, void* stream);
 /* out[N] += column sums of a bf16 [rows, N] matrix (Conv1D bias gradients)   */
 int ergm_colsum_bf16(const void* src, int64_t ld, int rows, int N, float* out, void* stream);
+/* MLP backward through gelu_new (model.py:264): dg (bf16 [rows, ld]) is overwritten with
+ * dg * gelu_new'(u); colsum[N] += column sums of the result (c_fc bias gradient).   */
+int ergm_gelu_bwd_colsum(void* dg_bf16, const void* u_bf16, int64_t ld, int rows, int N, float* colsum,
+                         int exact, void* stream);
 int ergm_cast_f32_bf16_2d(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int rows,
                           int N, float* colsum, void* stream);
 int ergm_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);

@@ -16,18 +16,17 @@ def run(M, N, K, a_mn, b_mn, bn, out_dtype=torch.bfloat16, iters=20, nbuf=4, **k
     for i in range(iters): f(i % nbuf)
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / iters
-    print("M=%5d N=%5d K=%5d a_mn=%d b_mn=%d bn=%4d %-8s %8.1f us %7.1f TF %s" % (M, N, K, a_mn, b_mn, bn, str(out_dtype)[6:], us, 2.0 * M * N * K / us / 1e6, kw if kw else ""), flush=True)
+    print("M=%5d N=%5d K=%5d a_mn=%d b_mn=%d bn=%4d %-8s %8.1f us %7.1f TF %s" % (M, N, K, a_mn, b_mn, bn, str(out_dtype)[6:], us, 2.0 * M * N * K / us / 1e6, sorted(kw)), flush=True)
 NOST = 1 << 30
 NOGL = 1 << 29
+u = torch.randn(8192, 3072, device=dev).bfloat16()
 for bn in (256, 2256, 128):
-    run(8192, 2304, 768, 0, 1, bn)
-    run(8192, 2304, 768, 0, 1, bn, out_dtype=torch.float32)
-run(8192, 2304, 768, 0, 1, 256, epilogue=NOGL)
-bias = torch.randn(3072, device=dev)
-for bn in (256, 2256):
-    run(8192, 3072, 768, 0, 1, bn, epilogue=L.EPI_GELU)
-    run(8192, 768, 3072, 0, 1, bn, out_dtype=torch.float32)
+    run(8192, 3072, 768, 0, 0, bn)
+    run(8192, 3072, 768, 0, 0, bn, gelu_grad_of=u)
+    run(8192, 3072, 768, 0, 0, bn, epilogue=L.EPI_GELU)
+res = torch.randn(8192, 768, device=dev)
+bias = torch.randn(768, device=dev)
 for bn in (128, 2128):
     run(8192, 768, 768, 0, 1, bn, out_dtype=torch.float32)
-for bn in (256, 2256):
-    run(8192, 50260, 768, 0, 0, bn, iters=4, nbuf=2)
+    run(8192, 768, 768, 0, 1, bn, out_dtype=torch.float32, residual=res)
+    run(8192, 768, 768, 0, 1, bn, out_dtype=torch.float32, residual=res, bias=bias, dropout_p=0.1, seed=1, offset=2)

@@ -359,3 +359,18 @@ def test_attn_dropout_fwd_bwd_consistent(cuda_device):
     dv_sum = dqkv[:, 2 * H:].float().view(T, nh, 64).sum(0)
     want = (dout.float().view(T, nh, 64) * o1.float().view(T, nh, 64)[:, :, :1]).sum(0)
     assert (dv_sum - want).abs().max().item() < 0.05 * want.abs().max().item() + 0.5
+
+
+def test_gelu_bwd_colsum(cuda_device):
+    from ergm_b200 import ops
+    g = _g(12)
+    M, N = 1000, 3072
+    dg = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    u = (torch.randn(M, N, device="cuda", generator=g) * 2).bfloat16()
+    ur = u.float().requires_grad_(True)
+    torch.nn.functional.gelu(ur, approximate="tanh").backward(dg.float())
+    cs = torch.zeros(N, device="cuda")
+    out = dg.clone()
+    ops.gelu_bwd_colsum(out, u, cs)
+    assert (out.float() - ur.grad).abs().max().item() < 3e-2
+    assert (cs - out.float().sum(0)).abs().max().item() < 1e-2
