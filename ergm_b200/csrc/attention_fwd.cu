@@ -6,21 +6,17 @@
 // [rows, ld] projection outputs with 3-D TMA maps (col, row-in-sequence, batch) and the
 // context is written merged as [B*Tq, nh*64].
 //
-// One CTA = one (batch, head, PAIR of 128-query blocks).  Two softmax groups of 8 warps work
-// ping-pong on the two query blocks against the same K/V stream, so the tensor core computes
-// one block's S = QK^T / O_j = PV while the other block is in its exp phase:
-//   warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-//   warps 4..11  = softmax group 0 (query block 2*pair),
-//   warps 12..19 = softmax group 1 (query block 2*pair + 1).
-// Inside a group two threads share a query row (TMEM lane): each owns 64 of the 128 key columns
-// of the current block and 32 of the 64 output columns; the row maximum is exchanged through
-// shared memory once per key block, the row sum once at the end.
-//   S_g  = Q_g K_j^T          SS MMA M128 N128 K64   -> TMEM cols [128g, 128g+128)
-//   P_g  = exp2(S c - m c)    -> bf16, hand-swizzled K-major SW128 tile in smem
-//   O_gj = P_g V_j            SS MMA M128 N64 K128   -> TMEM cols [256+64g, ...)
-//   O_g  = O_g * alpha + O_gj (registers)
-// Masks are only evaluated on key blocks that need them (the diagonal block of a causal query
-// block, or a block crossing the key length).
+// One CTA = one (batch, head, 128-query block); TWO CTAs are resident per SM (82 KB smem, 256 TMEM
+// columns, <= 80 registers x 384 threads each) so that one CTA's exp phase (MUFU-bound) overlaps
+// the other's load / MMA / barrier latencies.  Warp roles: 0 = TMA, 1 = MMA issuer, 2 = TMEM
+// allocator, 4..11 = softmax.  Two softmax threads share a query row (TMEM lane): each owns 64 of
+// the 128 key columns of the current block and 32 of the 64 output columns; the row maximum is
+// exchanged through shared memory once per key block, the row sum once at the end.
+//   S   = Q K_j^T           SS MMA M128 N128 K64    -> TMEM cols [0,128)
+//   P   = exp2(S c - m c)   -> bf16 pairs, tcgen05.st -> TMEM cols [128,192)   (never touches smem)
+//   O_j = P V_j             TS MMA (A from TMEM) M128 N64 K128 -> TMEM cols [192,256)
+//   O   = O * alpha + O_j   (registers)
+// Masks are only evaluated on key blocks that need them (diagonal block / key-length tail).
 #include "../../include/ergm_b200.h"
 #include "common.cuh"
 #include "dropout.cuh"
@@ -29,16 +25,16 @@ namespace ergm {
 
 #ifdef ERGM_TRACE
 __device__ long long g_attn_trace[64];
-#define TRACE(slot) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && trace_thread) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_attn_trace[slot] = t_; } } while (0)
+#define TRACE(slot) do { if (blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && trace_thread) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_attn_trace[slot] = t_; } } while (0)
 #else
 #define TRACE(slot) do { } while (0)
 #endif
 
 constexpr int AT_D = 64;
-constexpr int AT_THREADS = 640;
+constexpr int AT_THREADS = 384;
 constexpr int AT_TILE = 128 * 64 * 2;  // 16 KB: one [128 rows x 64 d] bf16 tile
-// Q0,Q1 | K x2 | V x2 | P0 (2 tiles) | P1 (2 tiles) | xch 2 KB | barriers
-constexpr int AT_SMEM = 10 * AT_TILE + 2048 + 256 + 1024;
+// Q | K x2 | V x2 | xch 1 KB | barriers ; + 1 KB alignment slack
+constexpr int AT_SMEM = 5 * AT_TILE + 1024 + 128 + 1024;
 
 struct AttnFwdParams {
   __nv_bfloat16* out;  // [B*Tq, ld_out], head h at columns [h*64, h*64+64)
@@ -55,74 +51,58 @@ struct AttnFwdParams {
 };
 
 template <bool CAUSAL>
-__global__ void __launch_bounds__(AT_THREADS, 1)
+__global__ void __launch_bounds__(AT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const AttnFwdParams p_in) {
   extern __shared__ uint8_t smem_raw[];
   AttnFwdParams p = p_in;
   p.drop = p_in.drop.resolved();
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = base, sK = base + 2 * AT_TILE, sV = base + 4 * AT_TILE, sP = base + 6 * AT_TILE;
-  const uint32_t sX = base + 10 * AT_TILE;  // float xch[2 groups][2 halves][128]
-  const uint32_t bars = sX + 2048;
-  auto bar_q = [&](int g) { return bars + 8u * g; };
-  auto bar_s = [&](int g) { return bars + 16 + 8u * g; };
-  auto bar_p = [&](int g) { return bars + 32 + 8u * g; };
-  auto bar_o = [&](int g) { return bars + 48 + 8u * g; };
-  auto kv_full = [&](int s) { return bars + 64 + 8u * s; };
-  auto kv_empty = [&](int s) { return bars + 80 + 8u * s; };
-  const uint32_t tmem_slot = bars + 96;
+  const uint32_t sQ = base, sK = base + AT_TILE, sV = base + 3 * AT_TILE;
+  const uint32_t sX = base + 5 * AT_TILE;  // float xch[2 halves][128]
+  const uint32_t bars = sX + 1024;
+  const uint32_t bar_q = bars, bar_s = bars + 8, bar_p = bars + 16, bar_o = bars + 24;
+  auto kv_full = [&](int s) { return bars + 32 + 8u * s; };
+  auto kv_empty = [&](int s) { return bars + 48 + 8u * s; };
+  const uint32_t tmem_slot = bars + 64;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pair = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = qb * 128;
 #ifdef ERGM_TRACE
-  const bool trace_thread = (threadIdx.x == 12 * 32);  // group 1, half 0, row 0
+  const bool trace_thread = (threadIdx.x == 4 * 32);
 #endif
   TRACE(0);
   int kv_len = p.Tk;
   if (p.kv_lens) kv_len = min(kv_len, p.kv_lens[b]);
-  const int n_kv_all = max(1, (kv_len + 127) / 128);
-  // number of key blocks each query block needs (0 = query block does not exist)
-  int nkv[2];
-#pragma unroll
-  for (int g = 0; g < 2; ++g) {
-    const int q0 = (2 * pair + g) * 128;
-    if (q0 >= p.Tq) { nkv[g] = 0; continue; }
-    int n = n_kv_all;
-    if (CAUSAL) {
-      const int last_key = min(q0 + 127, p.Tq - 1) + p.causal_off;
-      n = min(n, max(0, last_key) / 128 + 1);
-    }
-    nkv[g] = max(n, 1);
+  int n_kv = max(1, (kv_len + 127) / 128);
+  if (CAUSAL) {
+    const int last_key = min(q0 + 127, p.Tq - 1) + p.causal_off;  // largest visible key
+    n_kv = max(1, min(n_kv, max(0, last_key) / 128 + 1));
   }
-  const int n_iter = max(nkv[0], nkv[1]);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
   }
   if (warp == 1 && lane == 0) {
-    for (int g = 0; g < 2; ++g) {
-      mbar_init(bar_q(g), 1); mbar_init(bar_s(g), 1); mbar_init(bar_p(g), 256); mbar_init(bar_o(g), 1);
-      mbar_init(kv_full(g), 1); mbar_init(kv_empty(g), 1);
-    }
+    mbar_init(bar_q, 1); mbar_init(bar_s, 1); mbar_init(bar_p, 256); mbar_init(bar_o, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
     fence_mbar_init();
   }
-  if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 2) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
+  const uint32_t tS = tmem, tP = tmem + 128, tO = tmem + 192;
   TRACE(1);
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int g = 0; g < 2; ++g)
-        if (nkv[g] > 0) {
-          mbar_expect_tx(bar_q(g), AT_TILE);
-          tma_load_3d(sQ + g * AT_TILE, &tm_q, bar_q(g), p.q_col0 + h * AT_D, (2 * pair + g) * 128, b);
-        }
-      for (int j = 0; j < n_iter; ++j) {
+      mbar_expect_tx(bar_q, AT_TILE);
+      tma_load_3d(sQ, &tm_q, bar_q, p.q_col0 + h * AT_D, q0, b);
+      for (int j = 0; j < n_kv; ++j) {
         const int st = j & 1;
         mbar_wait(kv_empty(st), ((j >> 1) & 1) ^ 1);
         mbar_expect_tx(kv_full(st), 2 * AT_TILE);
@@ -134,212 +114,174 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
       const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
-      auto issue_s = [&](int g, int j) {
+      auto issue_s = [&](int j) {
         const uint32_t k_t = sK + (j & 1) * AT_TILE;
 #pragma unroll
         for (int ks = 0; ks < AT_D / 16; ++ks)
-          umma_ss(tmem + 128 * g, make_smem_desc_sw128(sQ + g * AT_TILE + ks * 32, 16, 1024),
+          umma_ss(tS, make_smem_desc_sw128(sQ + ks * 32, 16, 1024),
                   make_smem_desc_sw128(k_t + ks * 32, 16, 1024), idesc_s, ks > 0);
-        umma_commit(bar_s(g));
+        umma_commit(bar_s);
       };
-      for (int g = 0; g < 2; ++g)
-        if (nkv[g] > 0) mbar_wait(bar_q(g), 0);
+      mbar_wait(bar_q, 0);
       mbar_wait(kv_full(0), 0);
       tc_fence_after();
-      for (int g = 0; g < 2; ++g)
-        if (nkv[g] > 0) issue_s(g, 0);
-      // Service whichever softmax group is ready first (no head-of-line blocking between the two
-      // query blocks).  Per group the order is PV_g(j) then S_g(j+1); nothing here blocks, so a
-      // group waiting for the next K/V stage can never stall the other group's PV (which is what
-      // frees that stage).
-      int jg[2] = {0, 0};                                   // next key block whose PV is pending
-      int sg[2] = {nkv[0] > 0 ? 1 : 0, nkv[1] > 0 ? 1 : 0};  // next key block whose S is to be issued
-      int released = 0;   // key blocks whose smem stage has been handed back to the producer
-      int kv_seen = 1;    // key blocks [0, kv_seen) observed complete on kv_full
-      while (jg[0] < nkv[0] || jg[1] < nkv[1]) {
+      issue_s(0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        const uint32_t v_t = sV + st * AT_TILE;
+        mbar_wait(bar_p, j & 1);  // P_j in TMEM, S consumed
+        tc_fence_after();
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          if (sg[g] < nkv[g] && jg[g] >= sg[g]) {  // S buffer consumed (bar_p seen) -> next S
-            const int jb = sg[g];
-            if (kv_seen <= jb && mbar_try_wait(kv_full(jb & 1), (jb >> 1) & 1)) {
-              tc_fence_after();
-              kv_seen = jb + 1;
-            }
-            if (kv_seen > jb) {
-              issue_s(g, jb);
-              sg[g] = jb + 1;
-            }
-          }
-          const int j = jg[g];
-          if (j < nkv[g] && mbar_try_wait(bar_p(g), j & 1)) {
-            tc_fence_after();
-            const uint32_t v_t = sV + (j & 1) * AT_TILE;
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks)
-              umma_ss(tmem + 256 + 64 * g,
-                      make_smem_desc_sw128(sP + (2 * g + (ks >> 2)) * AT_TILE + (ks & 3) * 32, 16, 1024),
-                      make_smem_desc_sw128(v_t + ks * 2048, 8192, 1024), idesc_o, ks > 0);
-            umma_commit(bar_o(g));
-            jg[g] = j + 1;
-            // a stage is free once every group that needs block `released` has issued its PV
-            while (released < n_iter && (nkv[0] <= released || jg[0] > released) &&
-                   (nkv[1] <= released || jg[1] > released)) {
-              umma_commit(kv_empty(released & 1));
-              ++released;
-            }
-          }
+        for (int ks = 0; ks < 8; ++ks)   // A = P (TMEM, 8 columns = 16 bf16 per K step)
+          umma_ts(tO, tP + ks * 8, make_smem_desc_sw128(v_t + ks * 2048, 8192, 1024), idesc_o, ks > 0);
+        umma_commit(bar_o);
+        umma_commit(kv_empty(st));
+        if (j + 1 < n_kv) {
+          mbar_wait(kv_full((j + 1) & 1), ((j + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_s(j + 1);
         }
       }
     }
   } else if (warp >= 4) {
-    const int g = (warp - 4) >> 3;                 // softmax group = query block inside the pair
-    const int hf = ((warp - 4) >> 2) & 1;          // which half of the key columns / output columns
-    const int r = (warp & 3) * 32 + lane;          // query row inside the block == TMEM lane
-    const int n_mine = nkv[g];
-    if (n_mine > 0) {
-      const int q0 = (2 * pair + g) * 128;
-      const int qi = q0 + r;
-      const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-      const uint32_t tS = tmem + 128 * g + lane_addr + 64 * hf;
-      const uint32_t tO = tmem + 256 + 64 * g + lane_addr + 32 * hf;
-      const float c = p.scale * 1.4426950408889634f;  // exp(x*scale) = exp2(x*c)
-      const uint32_t thr16 = p.drop.thr16();
-      const float keep_scale = p.do_drop ? 65536.f / (65536.f - (float)thr16) : 1.f;
-      const uint32_t drop_row = (uint32_t)((b * p.nh + h) * p.Tq + qi);
-      const int vis = CAUSAL ? min(kv_len - 1, qi + p.causal_off) : kv_len - 1;  // last visible key
-      const uint32_t xch_mine = sX + ((g * 2 + hf) * 128 + r) * 4;
-      const uint32_t xch_other = sX + ((g * 2 + (hf ^ 1)) * 128 + r) * 4;
-      const uint32_t p_row = sP + (2 * g + hf) * AT_TILE + r * 128;
-      float m = -INFINITY, l = 0.f;
-      float o[32];
+    const int hf = (warp - 4) >> 2;          // which half of the key columns / output columns
+    const int r = (warp & 3) * 32 + lane;    // query row inside the block == TMEM lane
+    const int qi = q0 + r;
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tS_mine = tS + lane_addr + 64 * hf;
+    const uint32_t tP_mine = tP + lane_addr + 32 * hf;
+    const uint32_t tO_mine = tO + lane_addr + 32 * hf;
+    const float c = p.scale * 1.4426950408889634f;  // exp(x*scale) = exp2(x*c)
+    const uint32_t thr16 = p.drop.thr16();
+    const float keep_scale = p.do_drop ? p.drop.keep_scale() : 1.f;
+    const uint32_t drop_row = (uint32_t)((b * p.nh + h) * p.Tq + qi);
+    const int vis = CAUSAL ? min(kv_len - 1, qi + p.causal_off) : kv_len - 1;  // last visible key
+    const uint32_t xch_mine = sX + (hf * 128 + r) * 4;
+    const uint32_t xch_other = sX + ((hf ^ 1) * 128 + r) * 4;
+    float m = -INFINITY, l = 0.f;
+    float o[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o[i] = 0.f;
-      for (int j = 0; j < n_mine; ++j) {
-        const int k0 = j * 128 + 64 * hf;  // first key column this thread owns in block j
-        // warp-uniform: does any row of this warp need masking in this block?
-        const bool need_mask = (j * 128 + 127 > kv_len - 1) ||
-                               (CAUSAL && (j * 128 + 127 > q0 + (warp & 3) * 32 + p.causal_off));
-        TRACE(2 + 8 * j);
-        mbar_wait(bar_s(g), j & 1);
-        tc_fence_after();
-        TRACE(3 + 8 * j);
-        float mx = -INFINITY;
+    for (int i = 0; i < 32; ++i) o[i] = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      const int k0 = j * 128 + 64 * hf;  // first key column this thread owns in block j
+      // warp-uniform: does any row of this warp need masking in this block?
+      const bool need_mask = (j * 128 + 127 > kv_len - 1) ||
+                             (CAUSAL && (j * 128 + 127 > q0 + (warp & 3) * 32 + p.causal_off));
+      TRACE(2 + 8 * j);
+      mbar_wait(bar_s, j & 1);
+      tc_fence_after();
+      TRACE(3 + 8 * j);
+      float mx = -INFINITY;
 #pragma unroll
-        for (int cc = 0; cc < 64; cc += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tS + cc, v);
-          tmem_ld_wait();
-          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-          if (need_mask) {
+      for (int cc = 0; cc < 64; cc += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tS_mine + cc, v);
+        tmem_ld_wait();
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        if (need_mask) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (k0 + cc + i <= vis) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[i]));
-          } else {
+          for (int i = 0; i < 32; ++i)
+            if (k0 + cc + i <= vis) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[i]));
+        } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[i]));
-          }
-          mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+          for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[i]));
         }
-        TRACE(4 + 8 * j);
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch_mine), "f"(mx) : "memory");
-        asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
-        float mo;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(mo) : "r"(xch_other) : "memory");
-        const float m_new = fmaxf(m, fmaxf(mx, mo));
-        const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-        const float alpha = ex2_fast((m - m_use) * c);  // m = -inf -> 0
-        const float mc = m_use * c;
-        float s4[4] = {0.f, 0.f, 0.f, 0.f};
-        TRACE(5 + 8 * j);
-#pragma unroll
-        for (int cc = 0; cc < 64; cc += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tS + cc, v);
-          tmem_ld_wait();
-          float pr[32];
-          if (need_mask) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float e = ex2_fast(fmaf(__uint_as_float(v[i]), c, -mc));
-              pr[i] = (k0 + cc + i <= vis) ? e : 0.f;
-              s4[i & 3] += pr[i];
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              pr[i] = ex2_fast(fmaf(__uint_as_float(v[i]), c, -mc));
-              s4[i & 3] += pr[i];
-            }
-          }
-          if (p.do_drop) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const uint32_t hsh = p.drop.hash2(drop_row, (uint32_t)(k0 + cc + i) >> 1);
-              pr[i] = ((hsh & 0xffffu) >= thr16) ? pr[i] * keep_scale : 0.f;
-              pr[i + 1] = ((hsh >> 16) >= thr16) ? pr[i + 1] * keep_scale : 0.f;
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            const uint32_t piece = (uint32_t)((cc + i) >> 3);
-            const uint32_t addr = p_row + ((piece ^ (uint32_t)(r & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
-                         "r"(pack_bf16x2(pr[i], pr[i + 1])), "r"(pack_bf16x2(pr[i + 2], pr[i + 3])),
-                         "r"(pack_bf16x2(pr[i + 4], pr[i + 5])), "r"(pack_bf16x2(pr[i + 6], pr[i + 7]))
-                         : "memory");
-          }
-        }
-        l = l * alpha + ((s4[0] + s4[1]) + (s4[2] + s4[3]));
-        m = m_new;
-        TRACE(6 + 8 * j);
-        fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core
-        tc_fence_before();
-        mbar_arrive(bar_p(g));
-        TRACE(7 + 8 * j);
-        mbar_wait(bar_o(g), j & 1);
-        tc_fence_after();
-        TRACE(8 + 8 * j);
-        {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tO, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], alpha, __uint_as_float(v[i]));
-        }
-        tc_fence_before();
-        TRACE(9 + 8 * j);
+        mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
       }
-      // combine the two half-row sums
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch_mine), "f"(l) : "memory");
-      asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
-      float lo;
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(lo) : "r"(xch_other) : "memory");
-      l += lo;
-      if (qi < p.Tq) {
-        const float inv = l > 0.f ? 1.f / l : 0.f;
-        __nv_bfloat16* op = p.out + ((int64_t)b * p.Tq + qi) * p.ld_out + h * AT_D + 32 * hf;
+      TRACE(4 + 8 * j);
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch_mine), "f"(mx) : "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      float mo;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(mo) : "r"(xch_other) : "memory");
+      const float m_new = fmaxf(m, fmaxf(mx, mo));
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float alpha = ex2_fast((m - m_use) * c);  // m = -inf -> 0
+      const float mc = m_use * c;
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+      TRACE(5 + 8 * j);
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          const uint4 u = make_uint4(pack_bf16x2(o[i] * inv, o[i + 1] * inv), pack_bf16x2(o[i + 2] * inv, o[i + 3] * inv),
-                                     pack_bf16x2(o[i + 4] * inv, o[i + 5] * inv), pack_bf16x2(o[i + 6] * inv, o[i + 7] * inv));
-          *reinterpret_cast<uint4*>(op + i) = u;
-        }
-        if (p.out_f32) {
-          float* of = p.out_f32 + ((int64_t)b * p.Tq + qi) * (p.nh * AT_D) + h * AT_D + 32 * hf;
+      for (int cc = 0; cc < 64; cc += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tS_mine + cc, v);
+        tmem_ld_wait();
+        float pr[32];
+        if (need_mask) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            *reinterpret_cast<float4*>(of + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
+          for (int i = 0; i < 32; ++i) {
+            const float e = ex2_fast(fmaf(__uint_as_float(v[i]), c, -mc));
+            pr[i] = (k0 + cc + i <= vis) ? e : 0.f;
+            s4[i & 3] += pr[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            pr[i] = ex2_fast(fmaf(__uint_as_float(v[i]), c, -mc));
+            s4[i & 3] += pr[i];
+          }
         }
-        if (p.lse && hf == 0)
-          p.lse[((int64_t)b * p.nh + h) * p.Tq + qi] = (m == -INFINITY ? 0.f : m) * p.scale + logf(l);
+        if (p.do_drop) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const uint32_t hsh = p.drop.hash2(drop_row, (uint32_t)(k0 + cc + i) >> 1);
+            pr[i] = ((hsh & 0xffffu) >= thr16) ? pr[i] * keep_scale : 0.f;
+            pr[i + 1] = ((hsh >> 16) >= thr16) ? pr[i + 1] * keep_scale : 0.f;
+          }
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(pr[2 * i], pr[2 * i + 1]);
+        tmem_st_32x32b_x16(tP_mine + (cc >> 1), pk);   // 32 keys -> 16 packed columns
       }
+      l = l * alpha + ((s4[0] + s4[1]) + (s4[2] + s4[3]));
+      m = m_new;
+      tmem_st_wait();
+      TRACE(6 + 8 * j);
+      tc_fence_before();
+      mbar_arrive(bar_p);
+      TRACE(7 + 8 * j);
+      mbar_wait(bar_o, j & 1);
+      tc_fence_after();
+      TRACE(8 + 8 * j);
+      {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tO_mine, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], alpha, __uint_as_float(v[i]));
+      }
+      tc_fence_before();
+      TRACE(9 + 8 * j);
+    }
+    // combine the two half-row sums
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch_mine), "f"(l) : "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    float lo;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(lo) : "r"(xch_other) : "memory");
+    l += lo;
+    if (qi < p.Tq) {
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      __nv_bfloat16* op = p.out + ((int64_t)b * p.Tq + qi) * p.ld_out + h * AT_D + 32 * hf;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        const uint4 u = make_uint4(pack_bf16x2(o[i] * inv, o[i + 1] * inv), pack_bf16x2(o[i + 2] * inv, o[i + 3] * inv),
+                                   pack_bf16x2(o[i + 4] * inv, o[i + 5] * inv), pack_bf16x2(o[i + 6] * inv, o[i + 7] * inv));
+        *reinterpret_cast<uint4*>(op + i) = u;
+      }
+      if (p.out_f32) {
+        float* of = p.out_f32 + ((int64_t)b * p.Tq + qi) * (p.nh * AT_D) + h * AT_D + 32 * hf;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<float4*>(of + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
+      }
+      if (p.lse && hf == 0)
+        p.lse[((int64_t)b * p.nh + h) * p.Tq + qi] = (m == -INFINITY ? 0.f : m) * p.scale + logf(l);
     }
   }
   TRACE(40);
   tc_fence_before();
   __syncthreads();
   TRACE(41);
-  if (warp == 2) tmem_dealloc(tmem, 512);
+  if (warp == 2) tmem_dealloc(tmem, 256);
 }
 
 }  // namespace ergm
@@ -385,9 +327,14 @@ extern "C" int ergm_attn_fwd(const void* q, int64_t ld_q, int q_col0, const void
   if (!attr) {
     ERGM_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
     ERGM_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    // two CTAs per SM need 2 x 83 KB of shared memory: ask for the maximum shared-memory carve-out
+    ERGM_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared));
+    ERGM_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared));
     attr = true;
   }
-  dim3 grid(((Tq + 127) / 128 + 1) / 2, nh, B);
+  dim3 grid((Tq + 127) / 128, nh, B);
   if (causal)
     attn_fwd_kernel<true><<<grid, AT_THREADS, AT_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
   else

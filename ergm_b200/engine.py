@@ -303,6 +303,106 @@ class Engine:
             self.saved = sv
         return out
 
+    # ------------------------------------------------------------------
+    # fp32 mode: forward-only verification path (north_star: logits within 1e-4, greedy ids exact)
+    # ------------------------------------------------------------------
+    def _w6(self, name, linear=False):
+        """6x split-expanded bf16 copy of an fp32 weight (cached per parameter version)."""
+        cache = self.__dict__.setdefault("_w6_cache", {})
+        w = self.p(name)
+        ver = self.store.params[name]._version
+        hit = cache.get(name)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        if linear:   # nn.Linear weight [N, K]: reduction dim = cols -> [N, 6K], K-major operand
+            out = torch.empty(w.shape[0], 6 * w.shape[1], dtype=torch.bfloat16, device=self.device)
+            ops.split3_expand(w, out, side=1, kdim=1)
+        else:        # Conv1D weight [K, N]: reduction dim = rows -> [6K, N], MN-major operand
+            out = torch.empty(6 * w.shape[0], w.shape[1], dtype=torch.bfloat16, device=self.device)
+            ops.split3_expand(w, out, side=1, kdim=0)
+        cache[name] = (ver, out)
+        return out
+
+    def _gemm32(self, x32, wname, out, bias=None, residual=None, gelu=False, linear=False, N=None):
+        """out[M,N] (fp32) = x32[M,K] @ W (+bias) (+gelu) (+residual) at fp32 accuracy on the bf16 tensor cores."""
+        M, K = x32.shape
+        a6 = self.ws_eval.get("a6", (M, 6 * K), torch.bfloat16)
+        ops.split3_expand(x32, a6, side=0, kdim=1)
+        w6 = self._w6(wname, linear)
+        if N is None:
+            N = w6.shape[0] if linear else w6.shape[1]
+        epi = (L.EPI_GELU | L.EPI_EXACT) if gelu else 0
+        ops.gemm(a6, w6, out, M=M, N=N, K=6 * K, a_major=K_MAJOR, b_major=K_MAJOR if linear else MN_MAJOR,
+                 bias=bias, residual=residual, epilogue=epi)
+
+    def forward_fp32(self, input_ids, token_type_ids=None, labels=None, emotion_labels=None, imgs=None, auds=None,
+                     caption_ids=None, position_ids=None, kv_lens=None):
+        """Same dataflow as forward() with every product at fp32 accuracy; eval / no-grad only."""
+        self.ensure_params()
+        cfg, H, nh, Lyr, I, V = self.cfg, self.H, self.nh, self.L, self.I, self.V
+        B, T = input_ids.shape
+        M = B * T
+        ws = self.ws_eval
+        f32 = torch.float32
+        eps = cfg.layer_norm_epsilon
+        img2 = aud2 = None
+        if imgs is not None:
+            img2 = self._feature_rows(imgs, B, H, "imgs")
+            aud2 = self._feature_rows(auds, B, H, "auds")
+        x = ws.get("f32_x", (M, H), f32)
+        ops.embed_fuse_fwd(input_ids, token_type_ids, position_ids, self.p("transformer.wte.weight"),
+                           self.p("transformer.wpe.weight"), img2, aud2, x)
+        enc = None
+        if caption_ids is not None:
+            caption_ids = caption_ids.reshape(B, -1)
+            Tc = caption_ids.shape[1]
+            enc = self.p("transformer.wte.weight").index_select(0, caption_ids.reshape(-1))  # gather only
+        a = ws.get("f32_a", (M, H), f32)
+        qkv = ws.get("f32_qkv", (M, 3 * H), f32)
+        ctx = ws.get("f32_ctx", (M, H), f32)
+        g = ws.get("f32_g", (M, I), f32)
+        for l in range(Lyr):
+            pfx = "transformer.h.%d." % l
+            ops.ln_fwd(x, self.p(pfx + "ln_1.weight"), self.p(pfx + "ln_1.bias"), None, a, None, None, eps)
+            self._gemm32(a, pfx + "attn.c_attn.weight", qkv, bias=self.p(pfx + "attn.c_attn.bias"))
+            ops.attn_fwd_f32(qkv, qkv, qkv, ctx, B=B, nh=nh, Tq=T, Tk=T, q_col0=0, k_col0=H, v_col0=2 * H,
+                             causal=True, kv_lens=kv_lens)
+            self._gemm32(ctx, pfx + "attn.c_proj.weight", x, bias=self.p(pfx + "attn.c_proj.bias"), residual=x)
+            if enc is not None:
+                q2 = ws.get("f32_q2", (M, H), f32)
+                kv2 = ws.get("f32_kv2", (B * Tc, 2 * H), f32)
+                ops.ln_fwd(x, self.p(pfx + "ln_cross_attn.weight"), self.p(pfx + "ln_cross_attn.bias"), None, a, None,
+                           None, eps)
+                self._gemm32(a, pfx + "crossattention.q_attn.weight", q2, bias=self.p(pfx + "crossattention.q_attn.bias"))
+                self._gemm32(enc, pfx + "crossattention.c_attn.weight", kv2,
+                             bias=self.p(pfx + "crossattention.c_attn.bias"))
+                ops.attn_fwd_f32(q2, kv2, kv2, ctx, B=B, nh=nh, Tq=T, Tk=Tc, q_col0=0, k_col0=0, v_col0=H, causal=False)
+                self._gemm32(ctx, pfx + "crossattention.c_proj.weight", x,
+                             bias=self.p(pfx + "crossattention.c_proj.bias"), residual=x)
+            ops.ln_fwd(x, self.p(pfx + "ln_2.weight"), self.p(pfx + "ln_2.bias"), None, a, None, None, eps)
+            self._gemm32(a, pfx + "mlp.c_fc.weight", g, bias=self.p(pfx + "mlp.c_fc.bias"), gelu=True)
+            self._gemm32(g, pfx + "mlp.c_proj.weight", x, bias=self.p(pfx + "mlp.c_proj.bias"), residual=x)
+        meanf = ws.get("meanf", (M,), f32)
+        rstdf = ws.get("rstdf", (M,), f32)
+        ops.ln_fwd(x, self.p("transformer.ln_f.weight"), self.p("transformer.ln_f.bias"), None, a, meanf, rstdf, eps)
+        ldl = (V + 63) // 64 * 64
+        logits = ws.get("logits32", (M, ldl), f32)
+        self._gemm32(a, "transformer.wte.weight", logits, linear=True, N=V)
+        sums = ws.get("loss_sums", (4,), f32)
+        sums.zero_()
+        losses = ws.get("losses", (5,), f32)
+        hlast = ws.get("hlast", (B, H), f32)
+        emo_logits = ws.get("emo_logits", (B, 7), f32)
+        emo_dlog = ws.get("emo_dlog", (B, 7), f32)
+        ops.emotion_head_fwd(x, meanf, rstdf, self.p("transformer.ln_f.weight"), self.p("transformer.ln_f.bias"),
+                             self.p("emotion_head.weight"), emotion_labels, hlast, emo_logits, emo_dlog, sums, B=B, T=T)
+        if labels is not None:
+            lse = ws.get("ce_lse", (M,), f32)
+            row_loss = ws.get("ce_row_loss", (M,), f32)
+            ops.ce_fwd(logits, labels, lse, row_loss, sums, T=T, V=V)
+        return dict(logits=logits, emotion_logits=emo_logits, loss_sums=sums, losses=losses, hidden=a,
+                    has_lm=labels is not None, has_emo=emotion_labels is not None, kv_present=None, B=B, T=T)
+
     def finalize_loss(self, out):
         """loss = CE_lm + CE_emotion (model.py:704-721) from the (possibly all-reduced) sums."""
         ops.loss_finalize(out["loss_sums"], out["has_lm"], out["has_emo"], out["losses"])

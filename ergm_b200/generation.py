@@ -100,6 +100,9 @@ def generate(model, input_ids, token_type_ids=None, max_new_tokens=64, do_sample
     """input_ids [B, T] right-padded prompts, prompt_lens [B] their true lengths (default T).
     Every generated token gets speaker type sp2_id (main.py:277-279).  Returns int64 [B,
     max_new_tokens]; after a sequence emits eos it keeps emitting eos."""
+    if getattr(model, "ergm_precision", "bf16") == "fp32":
+        return _generate_fp32(model, input_ids, token_type_ids, max_new_tokens, eos_token_id, sp2_id, imgs, auds,
+                              caption_ids, prompt_lens)
     if top_p < 1.0:
         raise L.ErgmError("top-p sampling is a 'next' row (SURVEY.md §8f N2) and is not implemented yet; "
                           "use greedy or top_k")
@@ -160,6 +163,36 @@ def generate(model, input_ids, token_type_ids=None, max_new_tokens=64, do_sample
     if return_state:
         return st.out_ids, st
     return st.out_ids
+
+
+def _generate_fp32(model, input_ids, token_type_ids, max_new_tokens, eos_token_id, sp2_id, imgs, auds, caption_ids,
+                   prompt_lens):
+    """fp32-mode greedy decoding: full recompute per token exactly like main.py:255-279 (no KV cache,
+    no bf16 anywhere), arg-max on device.  Uniform prompt lengths only."""
+    if prompt_lens is not None and not bool((prompt_lens == input_ids.shape[1]).all()):
+        raise L.ErgmError("fp32-mode generation needs uniform prompt lengths")
+    eng = model.engine
+    dev = eng.device
+    ids = input_ids.to(dev, torch.int64)
+    tt = token_type_ids.to(dev, torch.int64) if token_type_ids is not None else None
+    B = ids.shape[0]
+    out_ids = torch.zeros(B, max_new_tokens, dtype=torch.int64, device=dev)
+    nxt = torch.zeros(B, dtype=torch.int64, device=dev)
+    finished = torch.zeros(B, dtype=torch.int32, device=dev)
+    step = torch.zeros(1, dtype=torch.int32, device=dev)
+    cap = caption_ids.to(dev, torch.int64) if caption_ids is not None else None
+    for t in range(max_new_tokens):
+        T = ids.shape[1]
+        o = eng.forward_fp32(ids.contiguous(), tt.contiguous() if tt is not None else None, None, None, imgs, auds, cap)
+        last = o["logits"].view(B, T, -1)[:, T - 1].contiguous()
+        ops.sample(last, V=eng.V, step=step, out_ids=out_ids, next_ids=nxt, finished=finished,
+                   eos_id=int(eos_token_id) if eos_token_id is not None else -1)
+        ops.int_add(step, 1)
+        ids = torch.cat([ids, nxt[:, None]], 1)
+        if tt is not None:
+            tt = torch.cat([tt, torch.full((B, 1), int(sp2_id if sp2_id is not None else 0), dtype=torch.int64,
+                                           device=dev)], 1)
+    return out_ids
 
 
 def legacy_cached_forward(model, input_ids, token_type_ids, pos, past_key_values, attention_mask, caption_ids,

@@ -234,6 +234,9 @@ class GPT2LMHeadModel(GPT2PreTrainedModel):
         self._engine = None
         self._dp = None  # set by ergm_b200.parallel.DataParallel
         self.fp32_logits = False
+        # "bf16" = bf16 tensor-core operands, fp32 accumulation / residual / statistics (throughput mode);
+        # "fp32" = split-operand fp32-accurate products (forward only; logits within 1e-4 of the reference)
+        self.ergm_precision = "bf16"
 
     # -- HF plumbing ---------------------------------------------------------------------
     def get_output_embeddings(self):
@@ -359,9 +362,17 @@ class GPT2LMHeadModel(GPT2PreTrainedModel):
             if attention_mask is not None:
                 kv_lens = self._kv_lens_from_mask(attention_mask.to(dev), B, T)
             save = training and (labels is not None or emotion_labels is not None)
-            out = eng.forward(input_ids, token_type_ids, labels, emotion_labels, imgs, auds, caption_ids, pos,
-                              past_len=0, kv_lens=kv_lens, training=self.training, save=save,
-                              want_logits=True, logits_fp32=self.fp32_logits)
+            if self.ergm_precision == "fp32":
+                if save:
+                    raise L.ErgmError("ergm_precision='fp32' is a forward-only verification mode: call it under "
+                                      "torch.no_grad() / model.eval()")
+                out = eng.forward_fp32(input_ids, token_type_ids, labels, emotion_labels, imgs, auds, caption_ids,
+                                       pos, kv_lens=kv_lens)
+                use_cache = False
+            else:
+                out = eng.forward(input_ids, token_type_ids, labels, emotion_labels, imgs, auds, caption_ids, pos,
+                                  past_len=0, kv_lens=kv_lens, training=self.training, save=save,
+                                  want_logits=True, logits_fp32=self.fp32_logits)
             loss = lm_loss = emo_loss = None
             if labels is not None or emotion_labels is not None:
                 if self._dp is not None:

@@ -270,3 +270,16 @@ def int_add(t, inc):
 
 def rng_step_advance(t, inc=1):
     _call("ergm_rng_step_advance", t.data_ptr(), inc)
+
+
+def split3_expand(src, dst, *, side, kdim):
+    rows, cols = src.shape
+    _call("ergm_split3_expand", src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), rows, cols, side, kdim)
+
+
+def attn_fwd_f32(q, k, v, out, *, B, nh, Tq, Tk, q_col0=0, k_col0=0, v_col0=0, causal=True, causal_off=None,
+                 kv_lens=None):
+    if causal_off is None:
+        causal_off = Tk - Tq
+    _call("ergm_attn_fwd_f32", q.data_ptr(), q.stride(0), q_col0, k.data_ptr(), k.stride(0), k_col0, v.data_ptr(),
+          v.stride(0), v_col0, out.data_ptr(), out.stride(0), _p(kv_lens), B, nh, Tq, Tk, 64, int(causal), causal_off)

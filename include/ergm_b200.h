@@ -183,6 +183,21 @@ int ergm_loss_finalize(const float* sums, int has_lm, int has_emotion, float* ou
 int ergm_scalar_mul(const float* a, const float* b, float* dst, void* stream);
 
 /* ------------------------------------------------------------------------ */
+/* fp32 mode (logits within 1e-4, bit-exact greedy ids): fp32 operands are split
+ * exactly into three bf16 pieces and expanded 6x along the reduction dimension
+ * so that ONE ergm_gemm_bf16 call computes an fp32-accurate product
+ * (see csrc/fp32_mode.cu).  side 0 = A operand, 1 = B operand; kdim = which
+ * dimension of src is the reduction dimension (1: cols -> dst [rows, 6*cols];
+ * 0: rows -> dst [6*rows, cols]).                                            */
+int ergm_split3_expand(const float* src, int64_t ld_src, void* dst_bf16, int64_t ld_dst, int rows,
+                       int cols, int side, int kdim, void* stream);
+/* fp32 CUDA-core attention (verification path of model.py:119-148)            */
+int ergm_attn_fwd_f32(const float* q, int64_t ld_q, int q_col0, const float* k, int64_t ld_k,
+                      int k_col0, const float* v, int64_t ld_v, int v_col0, float* out, int64_t ld_out,
+                      const int* kv_lens, int B, int nh, int Tq, int Tk, int head_dim, int causal,
+                      int causal_off, void* stream);
+
+/* ------------------------------------------------------------------------ */
 /* Decode: paged KV cache + one-query attention + on-device sampling.  Replaces
  * the torch.cat cache growth of model.py:228-236 and the per-token sampling /
  * host sync of main.py:253-282.  Pool layout (bf16):

@@ -19,13 +19,20 @@ M = B * T
 
 
 def timeit(name, fn, nbuf, flops=None, bytes_=None, iters=args.iters):
+    """GPU time per launch: the launches are captured into a CUDA graph so that host-side work
+    (tensor-map encoding, ctypes) cannot leave the GPU idle between them."""
     for i in range(3):
         fn(i % nbuf)
     torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(iters):
+            fn(i % nbuf)
+    g.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(iters):
-        fn(i % nbuf)
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / iters

@@ -187,3 +187,16 @@ def test_decode_attention_kernels_vs_torch(cuda_device):
         w = torch.softmax(torch.einsum("hd,thd->ht", q[b].float().view(nh, 64), k) / 8.0, -1)
         ref = torch.einsum("ht,thd->hd", w, v).reshape(H)
         assert (out[b].float() - ref).abs().max().item() < 2e-2
+
+
+def test_fp32_mode_greedy_ids_bit_exact(cuda_device):
+    """north_star: greedy-decoded token ids bit-exact in fp32 mode — against the ids the unmodified
+    reference produced (tests/golden/tiny_generate.npz)."""
+    g = np.load(os.path.join(GOLD, "tiny_generate.npz"))
+    cfg = tiny_cfg()
+    sd = O.init_state_dict(cfg, seed=5, perturb=True)
+    m = build_model(cfg, sd)
+    m.ergm_precision = "fp32"
+    b = synthetic.make_batch(4, 24, seed=21, vocab=cfg.vocab_size, feat_dim=cfg.n_embd, ragged=False)
+    ids = m.generate(b["input_ids"].cuda(), b["token_type_ids"].cuda(), max_new_tokens=12, sp2_id=cfg.vocab_size - 1)
+    assert np.array_equal(ids.cpu().numpy(), g["greedy_ids"])

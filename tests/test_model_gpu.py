@@ -201,3 +201,45 @@ def test_grad_accumulation_and_adamw_step(cuda_device):
     # the bf16 shadow the GEMMs read was refreshed by the optimiser kernel
     st = m.engine.store
     assert torch.equal(st.shadow_view("transformer.wte.weight"), m.transformer.wte.weight.detach().bfloat16())
+
+
+def test_fp32_mode_logits_1e4_and_loss(cuda_device):
+    """north_star fp32 mode: logits within 1e-4 relative, loss within 1e-4 (split-operand tcgen05
+    GEMMs, fp32 attention), against the oracle in fp64."""
+    cfg = tiny_cfg()
+    sd = O.init_state_dict(cfg, seed=3, perturb=True)
+    m = build_model(cfg, sd).eval()
+    m.ergm_precision = "fp32"
+    b = synthetic.make_batch(3, 48, seed=11, vocab=cfg.vocab_size, feat_dim=cfg.n_embd, tc=29)
+    kw = cuda_batch(b)
+    with torch.no_grad():
+        out = m(**kw)
+    sd64 = {k: v.double() for k, v in sd.items()}
+    o = O.forward(sd64, cfg, b["input_ids"], b["token_type_ids"], b["labels"], b["emotion_labels"],
+                  b["imgs"].double(), b["auds"].double(), b["caption_ids"])
+    r = rel(out.logits, o["logits"])
+    print("fp32-mode logits rel err %.3e, loss diff %.3e" % (r, abs(out.loss.item() - o["loss"].item())))
+    assert r < 1e-4
+    assert abs(out.loss.item() - o["loss"].item()) < 1e-4
+    assert rel(out.emotion_logits, o["emotion_logits"]) < 1e-4
+
+
+def test_fp32_mode_small_gv1_vs_golden(cuda_device):
+    """BASELINE config 1 in fp32 mode against the reference fixture: loss within 1e-4, logits 1e-4,
+    arg-max map identical wherever the reference's own top-1/top-2 margin exceeds 1e-4."""
+    g = np.load(os.path.join(GOLD, "small_gv1.npz"))
+    cfg = O.OracleConfig()
+    sd = O.init_state_dict(cfg, seed=0, perturb=True)
+    m = build_model(cfg, sd).eval()
+    m.ergm_precision = "fp32"
+    b = synthetic.gv1_inputs()
+    with torch.no_grad():
+        out = m(**cuda_batch(b))
+    assert abs(out.loss.item() - float(g["caption/loss"])) < 1e-4, out.loss.item()
+    lg = out.logits
+    assert rel(lg[3, 127], torch.from_numpy(g["caption/logits_b3_t127"])) < 1e-4
+    assert rel(lg[1, ::8, ::64], torch.from_numpy(g["caption/logits_b1_stride"])) < 1e-4
+    am = lg.argmax(-1).cpu().numpy()
+    safe = g["caption/top_margin"] > 1e-4
+    assert (am[safe] == g["caption/argmax"][safe]).all()
+    assert safe.mean() > 0.99
