@@ -236,88 +236,109 @@ struct LnBwdParams {
   int do_drop;
 };
 
-template <int NV>
-__global__ void __launch_bounds__(ROW_WARPS * 32) ln_bwd_kernel(const LnBwdParams p_in) {
-  constexpr int H = NV * 128;
+// Thread t owns float4 column t of every row; a CTA walks a contiguous slab of rows, RB rows at a
+// time (RB x 3 independent 16-byte loads in flight per thread), so the three per-column sums
+// (dgamma, dbeta, dbias_next) live in 12 registers instead of 72 and several CTAs fit per SM
+// (the first version, one warp per row, was register-bound to 8 warps / SM: 2.3 TB/s).
+constexpr int LN_RB = 4;
+
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) ln_bwd_kernel(const LnBwdParams p_in, int H, int rows_per_cta) {
+  __shared__ float red[2][32][2 * LN_RB];
   LnBwdParams p = p_in;
   p.drop = p_in.drop.resolved();
-  __shared__ float red[ROW_WARPS][H];
+  const int c = threadIdx.x;  // float4 column; blockDim.x == H / 4
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (blockDim.x + 31) >> 5;
+  const float invH = 1.f / (float)H;
   const float keep_scale = p.do_drop ? p.drop.keep_scale() : 1.f;
-  float4 gm[NV], ag[NV], ab[NV], an[NV];
+  const float4 gm = __ldg(reinterpret_cast<const float4*>(p.gamma) + c);
+  float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag, an = ag;
+  const int r0 = blockIdx.x * rows_per_cta;
+  const int r1 = min(r0 + rows_per_cta, p.rows);
+  int buf = 0;
+  for (int rb = r0; rb < r1; rb += LN_RB, buf ^= 1) {
+    float4 dy[LN_RB], xh[LN_RB], rs[LN_RB];
+    float rstd[LN_RB];
+    float part[2 * LN_RB];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    gm[i] = __ldg(reinterpret_cast<const float4*>(p.gamma) + lane + 32 * i);
-    ag[i] = ab[i] = an[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  for (int row = blockIdx.x * ROW_WARPS + warp; row < p.rows; row += gridDim.x * ROW_WARPS) {
-    const float mean = p.mean[row], rstd = p.rstd[row];
-    float4 dy[NV], xh[NV];
-    float c1 = 0.f, c2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      if (p.dy_f32) {
-        dy[i] = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.dy) + (int64_t)row * H)[lane + 32 * i];
+    for (int i = 0; i < LN_RB; ++i) {
+      const int row = rb + i;
+      if (row < r1) {
+        const int64_t off = (int64_t)row * H;
+        if (p.dy_f32) {
+          dy[i] = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.dy) + off)[c];
+        } else {
+          const uint2 u = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.dy) + off)[c];
+          const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+          dy[i] = make_float4(a.x, a.y, b.x, b.y);
+        }
+        xh[i] = reinterpret_cast<const float4*>(p.x + off)[c];
+        rs[i] = p.dres_in ? reinterpret_cast<const float4*>(p.dres_in + off)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
       } else {
-        const uint2 u = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.dy) + (int64_t)row * H)[lane + 32 * i];
-        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
-        dy[i] = make_float4(a.x, a.y, b.x, b.y);
+        dy[i] = xh[i] = rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      const float4 xv = reinterpret_cast<const float4*>(p.x + (int64_t)row * H)[lane + 32 * i];
-      xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
-      const float gx = dy[i].x * gm[i].x, gy = dy[i].y * gm[i].y, gz = dy[i].z * gm[i].z, gw = dy[i].w * gm[i].w;
-      c1 += (gx + gy) + (gz + gw);
-      c2 += (gx * xh[i].x + gy * xh[i].y) + (gz * xh[i].z + gw * xh[i].w);
-      ag[i].x += dy[i].x * xh[i].x; ag[i].y += dy[i].y * xh[i].y; ag[i].z += dy[i].z * xh[i].z; ag[i].w += dy[i].w * xh[i].w;
-      ab[i].x += dy[i].x; ab[i].y += dy[i].y; ab[i].z += dy[i].z; ab[i].w += dy[i].w;
     }
-    c1 = warp_sum(c1) * (1.f / H);
-    c2 = warp_sum(c2) * (1.f / H);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
+    for (int i = 0; i < LN_RB; ++i) {
+      const int row = min(rb + i, r1 - 1);
+      const float mean = __ldg(p.mean + row);
+      rstd[i] = __ldg(p.rstd + row);
+      xh[i].x = (xh[i].x - mean) * rstd[i]; xh[i].y = (xh[i].y - mean) * rstd[i];
+      xh[i].z = (xh[i].z - mean) * rstd[i]; xh[i].w = (xh[i].w - mean) * rstd[i];
+      const float gx = dy[i].x * gm.x, gy = dy[i].y * gm.y, gz = dy[i].z * gm.z, gw = dy[i].w * gm.w;
+      part[2 * i] = (gx + gy) + (gz + gw);
+      part[2 * i + 1] = (gx * xh[i].x + gy * xh[i].y) + (gz * xh[i].z + gw * xh[i].w);
+    }
+#pragma unroll
+    for (int k = 0; k < 2 * LN_RB; ++k) part[k] = warp_sum(part[k]);
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 2 * LN_RB; ++k) red[buf][warp][k] = part[k];
+    }
+    __syncthreads();  // double-buffered `red`: one barrier per row batch
+#pragma unroll
+    for (int k = 0; k < 2 * LN_RB; ++k) {
+      float s = 0.f;
+      for (int w = 0; w < nwarps; ++w) s += red[buf][w][k];
+      part[k] = s * invH;
+    }
+#pragma unroll
+    for (int i = 0; i < LN_RB; ++i) {
+      const int row = rb + i;
+      if (row >= r1) break;
+      const float c1 = part[2 * i], c2 = part[2 * i + 1];
       float4 dx;
-      dx.x = rstd * (dy[i].x * gm[i].x - c1 - xh[i].x * c2);
-      dx.y = rstd * (dy[i].y * gm[i].y - c1 - xh[i].y * c2);
-      dx.z = rstd * (dy[i].z * gm[i].z - c1 - xh[i].z * c2);
-      dx.w = rstd * (dy[i].w * gm[i].w - c1 - xh[i].w * c2);
-      if (p.dres_in) {
-        const float4 r = reinterpret_cast<const float4*>(p.dres_in + (int64_t)row * H)[lane + 32 * i];
-        dx.x += r.x; dx.y += r.y; dx.z += r.z; dx.w += r.w;
-      }
-      if (p.dx_out) reinterpret_cast<float4*>(p.dx_out + (int64_t)row * H)[lane + 32 * i] = dx;
+      dx.x = rstd[i] * (dy[i].x * gm.x - c1 - xh[i].x * c2) + rs[i].x;
+      dx.y = rstd[i] * (dy[i].y * gm.y - c1 - xh[i].y * c2) + rs[i].y;
+      dx.z = rstd[i] * (dy[i].z * gm.z - c1 - xh[i].z * c2) + rs[i].z;
+      dx.w = rstd[i] * (dy[i].w * gm.w - c1 - xh[i].w * c2) + rs[i].w;
+      ag.x += dy[i].x * xh[i].x; ag.y += dy[i].y * xh[i].y; ag.z += dy[i].z * xh[i].z; ag.w += dy[i].w * xh[i].w;
+      ab.x += dy[i].x; ab.y += dy[i].y; ab.z += dy[i].z; ab.w += dy[i].w;
+      const int64_t off = (int64_t)row * H;
+      if (p.dx_out) reinterpret_cast<float4*>(p.dx_out + off)[c] = dx;
       if (p.dx_bf16) {
         if (p.do_drop) {
-          const uint32_t k = p.drop.keep4((uint32_t)row, (uint32_t)(lane + 32 * i));
+          const uint32_t k = p.drop.keep4((uint32_t)row, (uint32_t)c);
           dx.x = (k & 1u) ? dx.x * keep_scale : 0.f; dx.y = (k & 2u) ? dx.y * keep_scale : 0.f;
           dx.z = (k & 4u) ? dx.z * keep_scale : 0.f; dx.w = (k & 8u) ? dx.w * keep_scale : 0.f;
         }
         const uint2 u = make_uint2(pack_bf16x2(dx.x, dx.y), pack_bf16x2(dx.z, dx.w));
-        reinterpret_cast<uint2*>(p.dx_bf16 + (int64_t)row * H)[lane + 32 * i] = u;
+        reinterpret_cast<uint2*>(p.dx_bf16 + off)[c] = u;
         if (p.dbias_next) {
           const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
-          an[i].x += a.x; an[i].y += a.y; an[i].z += b.x; an[i].w += b.y;
+          an.x += a.x; an.y += a.y; an.z += b.x; an.w += b.y;
         }
       }
     }
   }
-  // cross-warp reduction of the three column sums, one quantity at a time through smem
-  float* outs[3] = {p.dgamma, p.dbeta, p.dbias_next};
-#pragma unroll
-  for (int qn = 0; qn < 3; ++qn) {
-    if (!outs[qn]) continue;  // uniform
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const float4 v = qn == 0 ? ag[i] : (qn == 1 ? ab[i] : an[i]);
-      reinterpret_cast<float4*>(&red[warp][0])[lane + 32 * i] = v;
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < H; c += ROW_WARPS * 32) {
-      float s = 0.f;
-#pragma unroll
-      for (int w = 0; w < ROW_WARPS; ++w) s += red[w][c];
-      atomicAdd(outs[qn] + c, s);
-    }
+  float* gp = p.dgamma + 4 * c;
+  atomicAdd(gp, ag.x); atomicAdd(gp + 1, ag.y); atomicAdd(gp + 2, ag.z); atomicAdd(gp + 3, ag.w);
+  float* bp = p.dbeta + 4 * c;
+  atomicAdd(bp, ab.x); atomicAdd(bp + 1, ab.y); atomicAdd(bp + 2, ab.z); atomicAdd(bp + 3, ab.w);
+  if (p.dbias_next && p.dx_bf16) {
+    float* np_ = p.dbias_next + 4 * c;
+    atomicAdd(np_, an.x); atomicAdd(np_ + 1, an.y); atomicAdd(np_ + 2, an.z); atomicAdd(np_ + 3, an.w);
   }
 }
 
@@ -519,12 +540,17 @@ extern "C" int ergm_ln_bwd(const void* dy, int dy_is_f32, const float* x, const 
   LnBwdParams p{dy, x, mean, rstd, gamma, dres_in, dx_out, reinterpret_cast<__nv_bfloat16*>(dx_bf16),
                 dgamma, dbeta, dbias_next, rows, dy_is_f32,
                 make_site(seed, offset, dropout_p, (uint32_t)H), dropout_p > 0.f};
-  return dispatch_nv(H, [&](auto nv) {
-    const int need = (rows + ROW_WARPS - 1) / ROW_WARPS;
-    const int grid = need < 2 * num_sms() ? need : 2 * num_sms();
-    ln_bwd_kernel<decltype(nv)::value><<<grid, ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
-    return (int)cudaGetLastError();
-  });
+  if (H / 4 > 512) return ERGM_ERR_UNSUPPORTED;
+  int grid = (rows + 4 * LN_RB - 1) / (4 * LN_RB);  // at least 4 row batches per CTA
+  if (grid > 4 * num_sms()) grid = 4 * num_sms();
+  if (grid < 1) grid = 1;
+  const int rpc = (rows + grid - 1) / grid;
+  grid = (rows + rpc - 1) / rpc;
+  if (H / 4 <= 256)
+    ln_bwd_kernel<256, 3><<<grid, H / 4, 0, (cudaStream_t)stream>>>(p, H, rpc);
+  else
+    ln_bwd_kernel<512, 1><<<grid, H / 4, 0, (cudaStream_t)stream>>>(p, H, rpc);
+  return (int)cudaGetLastError();
 }
 
 extern "C" int ergm_colsum_bf16(const void* src, int64_t ld, int rows, int N, float* out,

@@ -243,3 +243,29 @@ def test_fp32_mode_small_gv1_vs_golden(cuda_device):
     safe = g["caption/top_margin"] > 1e-4
     assert (am[safe] == g["caption/argmax"][safe]).all()
     assert safe.mean() > 0.99
+
+
+def test_medium_width_long_context_step(cuda_device):
+    """BASELINE config 5 shape family: GPT-2-medium width (H=1024, 16 heads), T=512 (four 128-key
+    blocks per head: exercises the multi-block causal / cross attention paths), reduced to 2 layers so
+    the CPU oracle finishes in seconds.  Forward + backward against the oracle."""
+    cfg = O.OracleConfig(vocab_size=2048, n_positions=512, n_embd=1024, n_layer=2, n_head=16)
+    sd = O.init_state_dict(cfg, seed=13, perturb=True)
+    m = build_model(cfg, sd).train()
+    b = synthetic.make_batch(2, 512, seed=14, vocab=cfg.vocab_size, feat_dim=cfg.n_embd, tc=512)
+    b["labels"] = b["input_ids"].clone()  # score every position: ~1000 targets keep the mean's bf16 noise < 1e-3
+    kw = cuda_batch(b)
+    out = m(**kw)
+    out.loss.backward()
+    sdo = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k != "lm_head.weight"}
+    sdo["lm_head.weight"] = sdo["transformer.wte.weight"]
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    o = O.forward(sdo, cfg, b["input_ids"], b["token_type_ids"], b["labels"], b["emotion_labels"], b["imgs"],
+                  b["auds"], b["caption_ids"])
+    o["loss"].backward()
+    assert abs(out.lm_loss.item() - o["lm_loss"].item()) < LOSS_TOL
+    assert rel(out.logits, o["logits"]) < LOGITS_REL_TOL
+    for name in ("transformer.h.0.attn.c_attn.weight", "transformer.h.1.mlp.c_fc.weight", "transformer.wpe.weight",
+                 "transformer.h.0.ln_1.weight", "transformer.h.1.attn.c_proj.bias"):
+        p = dict(m.named_parameters())[name]
+        assert rel(p.grad, sdo[name].grad) < 3e-2, (name, rel(p.grad, sdo[name].grad))
