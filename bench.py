@@ -353,7 +353,7 @@ def main():
                            "per_gpu_batch": B_PER_GPU, "seq_len": SEQ, "parallelism": "dp%d" % world,
                            "l2": "no flush needed: the step streams >5 GB of activations/weights/grads per "
                                  "iteration, far above the 126 MB L2",
-                           "cuda_graph": not args.no_graph},
+                           "cuda_graph": bool(step.use_graph)},
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": step.h2d_bytes * world, "d2h_bytes_per_step": 20 * world,
                         "api": "ergm_b200.trainer.GraphedTrainStep(model, FusedAdamW)(pinned_host_batch) -> loss"},
@@ -364,7 +364,13 @@ def main():
                 "generation": gen}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # the JSON line is out; never let a teardown hang keep the launcher waiting
+        sys.stdout.flush()
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        step.close()
+        dist.barrier()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 if __name__ == "__main__":

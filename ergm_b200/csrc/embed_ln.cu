@@ -477,6 +477,59 @@ static int row_grid(int rows) {
   return need < cap ? (need > 0 ? need : 1) : cap;
 }
 
+// ------------------------------------------------------------------------------------------
+// Modality pooling (SURVEY §8 A3 extension): per-utterance feature SEQUENCES -> time mean.
+// feature_extraction.py:63,69 pools audio [1,113,768] / key-frame visual [1,197,768] features to
+// one vector offline; here the raw sequences [B, T, D] stay on the device and the mean is taken
+// in-kernel, before the D -> H projection GEMM (mean and Linear commute, so pooling first makes
+// the projection an M = B GEMM instead of an M = B*T one).  HBM-bound: B*T*D*4 bytes read once.
+// grid (B, ceil(D/128)); 256 threads = 32 float4 column lanes x 8 time lanes; fixed-order
+// reduction across the time lanes -> bitwise deterministic.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mm_pool_kernel(const float* __restrict__ seq, int64_t ld_b, int64_t ld_t, const int* __restrict__ lens,
+               int T, int D, float* __restrict__ pooled_f32, int64_t ld_f32,
+               __nv_bfloat16* __restrict__ pooled_bf16, int64_t ld_bf16) {
+  __shared__ float4 red[8][32];
+  const int b = blockIdx.x;
+  const int cl = threadIdx.x & 31, tl = threadIdx.x >> 5;
+  const int c4 = blockIdx.y * 32 + cl;  // float4 column
+  const bool ok = c4 * 4 < D;
+  int n = lens ? min(T, max(lens[b], 0)) : T;
+  const float* base = seq + (int64_t)b * ld_b + 4 * (int64_t)c4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ok) {
+    int t = tl;
+    for (; t + 24 < n; t += 32) {  // 4 independent 16-byte loads in flight per thread
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(base + (int64_t)t * ld_t));
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(base + (int64_t)(t + 8) * ld_t));
+      const float4 v2 = __ldg(reinterpret_cast<const float4*>(base + (int64_t)(t + 16) * ld_t));
+      const float4 v3 = __ldg(reinterpret_cast<const float4*>(base + (int64_t)(t + 24) * ld_t));
+      acc.x += (v0.x + v1.x) + (v2.x + v3.x); acc.y += (v0.y + v1.y) + (v2.y + v3.y);
+      acc.z += (v0.z + v1.z) + (v2.z + v3.z); acc.w += (v0.w + v1.w) + (v2.w + v3.w);
+    }
+    for (; t < n; t += 8) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(base + (int64_t)t * ld_t));
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  red[tl][cl] = acc;
+  __syncthreads();
+  if (tl == 0 && ok) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+      const float4 o = red[i][cl];
+      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    }
+    const float inv = n > 0 ? 1.f / (float)n : 0.f;
+    acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+    if (pooled_f32) *reinterpret_cast<float4*>(pooled_f32 + (int64_t)b * ld_f32 + 4 * c4) = acc;
+    if (pooled_bf16)
+      *reinterpret_cast<uint2*>(pooled_bf16 + (int64_t)b * ld_bf16 + 4 * c4) =
+          make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
+  }
+}
+
 }  // namespace ergm
 
 using namespace ergm;
@@ -597,5 +650,17 @@ extern "C" int ergm_cast_f32_bf16(const float* src, void* dst, int64_t n, void* 
   if (blocks > num_sms() * 16) blocks = num_sms() * 16;
   cast_f32_bf16_flat_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
       src, reinterpret_cast<__nv_bfloat16*>(dst), n4);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int ergm_mm_pool_fwd(const float* seq, int64_t ld_b, int64_t ld_t, const int* lens, int B,
+                                int T, int D, float* pooled_f32, int64_t ld_f32, void* pooled_bf16,
+                                int64_t ld_bf16, void* stream) {
+  if (!seq || B <= 0 || T <= 0 || D <= 0 || D % 4 || (!pooled_f32 && !pooled_bf16)) return ERGM_ERR_ARG;
+  if (ld_b % 4 || ld_t % 4 || (reinterpret_cast<uintptr_t>(seq) & 15)) return ERGM_ERR_ARG;
+  if (pooled_f32 && (ld_f32 % 4 || (reinterpret_cast<uintptr_t>(pooled_f32) & 15))) return ERGM_ERR_ARG;
+  if (pooled_bf16 && (ld_bf16 % 4 || (reinterpret_cast<uintptr_t>(pooled_bf16) & 7))) return ERGM_ERR_ARG;
+  mm_pool_kernel<<<dim3(B, (D + 127) / 128), 256, 0, (cudaStream_t)stream>>>(
+      seq, ld_b, ld_t, lens, T, D, pooled_f32, ld_f32, reinterpret_cast<__nv_bfloat16*>(pooled_bf16), ld_bf16);
   return (int)cudaGetLastError();
 }

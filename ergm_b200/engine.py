@@ -166,9 +166,10 @@ class Engine:
         if imgs is not None and auds is None:
             raise ValueError("imgs given without auds (model.py:495-498 uses both)")
         img2 = aud2 = None
+        proj_saved = {}
         if fuse:
-            img2 = self._feature_rows(imgs, B, H, "imgs")
-            aud2 = self._feature_rows(auds, B, H, "auds")
+            img2 = self._fused_feature(imgs, B, H, "imgs", "visual_proj", ws, proj_saved)
+            aud2 = self._fused_feature(auds, B, H, "auds", "audio_proj", ws, proj_saved)
         x = ws.get(lname("x", 0), (M, H), f32)
         ops.embed_fuse_fwd(input_ids, token_type_ids, position_ids, self.p("transformer.wte.weight"),
                            self.p("transformer.wpe.weight"), img2, aud2, x, past_len=past_len,
@@ -184,7 +185,8 @@ class Engine:
 
         sv = dict(B=B, T=T, Tc=Tc, layers=[], site0=site0, seed=seed, pd=(pd_embd, pd_attn, pd_res),
                   past_len=past_len, kv_lens=kv_lens, ids=input_ids, tts=token_type_ids, pos=position_ids,
-                  cap=caption_ids, enc=enc, labels=labels, emo=emotion_labels, fuse=fuse) if save else None
+                  cap=caption_ids, enc=enc, labels=labels, emo=emotion_labels, fuse=fuse,
+                  proj=proj_saved) if save else None
         kv_present = []
         for l in range(Lyr):
             pfx = "transformer.h.%d." % l
@@ -347,8 +349,8 @@ class Engine:
         eps = cfg.layer_norm_epsilon
         img2 = aud2 = None
         if imgs is not None:
-            img2 = self._feature_rows(imgs, B, H, "imgs")
-            aud2 = self._feature_rows(auds, B, H, "auds")
+            img2 = self._fused_feature(imgs, B, H, "imgs", "visual_proj", ws, None, fp32=True)
+            aud2 = self._fused_feature(auds, B, H, "auds", "audio_proj", ws, None, fp32=True)
         x = ws.get("f32_x", (M, H), f32)
         ops.embed_fuse_fwd(input_ids, token_type_ids, position_ids, self.p("transformer.wte.weight"),
                            self.p("transformer.wpe.weight"), img2, aud2, x)
@@ -407,6 +409,42 @@ class Engine:
         """loss = CE_lm + CE_emotion (model.py:704-721) from the (possibly all-reduced) sums."""
         ops.loss_finalize(out["loss_sums"], out["has_lm"], out["has_emo"], out["losses"])
         return out["losses"]
+
+    def _fused_feature(self, feat, B, H, what, proj, ws, saved, fp32=False):
+        """The [B, H] fp32 vector added at position 0 (imgs) / 1 (auds) (model.py:497-498).
+        Reference layout (no `<proj>.weight` parameter in the model): the pooled H-wide feature is
+        used as is.  A3 extension (model built with config.ergm_visual_dim / ergm_audio_dim): `feat`
+        is the raw feature SEQUENCE [B, T, D] (audio [B,113,768], visual [B,197*Kf,768],
+        text_feature.py:44,49): time-mean (feature_extraction.py:63,69) -> Linear(D -> H)."""
+        wname = proj + ".weight"
+        if wname not in self.P:
+            return self._feature_rows(feat, B, H, what)
+        if isinstance(feat, (list, tuple)):
+            feat = torch.stack([torch.as_tensor(f) for f in feat])
+        feat = feat.to(self.device)
+        if feat.dim() == 2:
+            feat = feat[:, None, :]
+        D = self.p(wname).shape[1]
+        if feat.dim() != 3 or feat.shape[0] != B or feat.shape[2] != D:
+            raise ValueError("%s must be a feature sequence [B=%d, T, D=%d] for the %s projection (got %s)"
+                             % (what, B, D, proj, tuple(feat.shape)))
+        if feat.dtype != torch.float32 or feat.stride(2) != 1 or feat.stride(0) % 4 or feat.stride(1) % 4 \
+                or feat.data_ptr() % 16:
+            feat = feat.float().contiguous()
+        f32, bf16 = torch.float32, torch.bfloat16
+        out = ws.get(what + "_proj_out", (B, H), f32)
+        if fp32:
+            pooled = ws.get(what + "_pooled32", (B, D), f32)
+            ops.mm_pool_fwd(feat, pooled, None)
+            self._gemm32(pooled, wname, out, bias=self.p(proj + ".bias"), linear=True)
+            return out
+        pooled = ws.get(what + "_pooled", (B, D), bf16)
+        ops.mm_pool_fwd(feat, None, pooled)
+        ops.gemm(pooled, self.pb(wname), out, M=B, N=H, K=D, a_major=K_MAJOR, b_major=K_MAJOR,
+                 bias=self.p(proj + ".bias"))
+        if saved is not None:
+            saved[what] = (proj, pooled, D)
+        return out
 
     def _feature_rows(self, feat, B, H, what):
         """imgs: [B, >=1, H] (first row used, model.py:497 `imgs[i][0]`) or [B, H]; auds: [B, H] or
@@ -543,9 +581,20 @@ class Engine:
                 # layer l+1's ln_1 backward, and this layer's ln_1 backward only touched layer l-1's slot
                 on_layer_done(l)
         # ---- embedding backward (model.py:459, 500-506) ----
+        proj = sv.get("proj") or {}
+        dfeat = {}
+        for what in proj:
+            dfeat[what] = ws.get("d" + what, (B, H), f32)
+            dfeat[what].zero_()
         ops.embed_bwd(dx, sv["ids"], sv["tts"], sv["pos"], self.pg("transformer.wte.weight"),
-                      self.pg("transformer.wpe.weight"), T=T, past_len=sv["past_len"], dropout_p=pd_embd,
-                      seed=seed, offset=site0)
+                      self.pg("transformer.wpe.weight"), T=T, past_len=sv["past_len"], dimgs=dfeat.get("imgs"),
+                      dauds=dfeat.get("auds"), dropout_p=pd_embd, seed=seed, offset=site0)
+        for what, (pname, pooled, D) in proj.items():
+            # Linear(D -> H) backward: dW[H, D] += dfeat^T @ pooled, db += colsum(dfeat)
+            dfb = ws.get("d" + what + "_bf16", (B, H), bf16)
+            ops.cast_f32_bf16_2d(dfeat[what], dfb, self.pg(pname + ".bias"))
+            ops.gemm(dfb, pooled, self.pg(pname + ".weight"), M=H, N=D, K=B, a_major=MN_MAJOR, b_major=MN_MAJOR,
+                     epilogue=L.EPI_ATOMIC, block_n=128)
         if denc is not None:
             ops.embed_bwd(denc, sv["cap"], None, None, self.pg("transformer.wte.weight"), None, T=Tc)
         if on_layer_done is not None:

@@ -227,6 +227,17 @@ class GPT2LMHeadModel(GPT2PreTrainedModel):
         self.lm_head = nn.Linear(config.n_embd, config.vocab_size, bias=False)
         self.num_emotions = NUM_EMOTIONS
         self.emotion_head = nn.Linear(config.n_embd, self.num_emotions, bias=False)
+        # A3 extension (absent from the reference): with
+        # config.ergm_visual_dim / ergm_audio_dim set, `imgs` / `auds` are raw feature SEQUENCES
+        # [B, T, D] that are mean-pooled (feature_extraction.py:63,69) and projected D -> n_embd
+        # on the device.  Without them the reference layout (pooled n_embd-wide vectors) applies
+        # and state_dict() has exactly the reference's keys.
+        vd, ad = getattr(config, "ergm_visual_dim", None), getattr(config, "ergm_audio_dim", None)
+        if bool(vd) != bool(ad):
+            raise ValueError("set both config.ergm_visual_dim and config.ergm_audio_dim (model.py:495-498 fuses both)")
+        if vd:
+            self.visual_proj = nn.Linear(int(vd), config.n_embd)
+            self.audio_proj = nn.Linear(int(ad), config.n_embd)
         self.model_parallel = False
         self.device_map = None
         self.post_init()

@@ -137,6 +137,15 @@ def gather_rows_bf16(ids, table, out):
           table.shape[0], err_flag(ids.device).data_ptr())
 
 
+def mm_pool_fwd(seq, pooled_f32, pooled_bf16, lens=None):
+    """seq fp32 [B, T, D] (last dim contiguous) -> time mean [B, D] in fp32 and/or bf16."""
+    B, T, D = seq.shape
+    assert seq.dtype == torch.float32 and seq.stride(2) == 1
+    _call("ergm_mm_pool_fwd", seq.data_ptr(), seq.stride(0), seq.stride(1), _p(lens), B, T, D, _p(pooled_f32),
+          pooled_f32.stride(0) if pooled_f32 is not None else 0, _p(pooled_bf16),
+          pooled_bf16.stride(0) if pooled_bf16 is not None else 0)
+
+
 def embed_bwd(dh, ids, tts, pos_ids, dwte, dwpe, *, T, past_len=0, dimgs=None, dauds=None, dropout_p=0.0, seed=0, offset=0):
     rows, H = dh.shape
     _call("ergm_embed_bwd", dh.data_ptr(), _p(ids), _p(tts), _p(pos_ids), _pos_stride(pos_ids, T), _p(dwte), _p(dwpe), _p(dimgs), _p(dauds),

@@ -25,10 +25,10 @@ class GraphedTrainStep:
         self.model = model
         self.opt = optimizer
         self.dp = dp if dp is not None else getattr(model, "_dp", None)
-        # NCCL collectives are kept out of CUDA-graph capture: under DataParallel the step runs eagerly
-        # (the host stays ahead of the GPU: ~900 C-ABI calls/step at a few us each vs >10 ms of GPU work)
-        # so that the bucketed all-reduces are ordinary async NCCL launches overlapping the backward.
-        if self.dp is not None and getattr(self.dp, "world", 1) > 1 and os.environ.get("ERGM_DP_GRAPH", "0") != "1":
+        # Under DataParallel the bucketed NCCL all-reduces are captured into the same graph (side stream
+        # fork/join per bucket, see parallel.py); ERGM_DP_GRAPH=0 falls back to eager launches.  Call
+        # close() before dist.destroy_process_group(): a live graph pins NCCL resources.
+        if self.dp is not None and getattr(self.dp, "world", 1) > 1 and os.environ.get("ERGM_DP_GRAPH", "1") == "0":
             use_graph = False
         self.use_graph = use_graph
         self.graphs = {}
@@ -103,11 +103,18 @@ class GraphedTrainStep:
             self.losses = self._device_step(st)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()  # capture executes nothing: the hyper buffer is re-staged before each replay
-            with torch.cuda.graph(g):
+            # thread_local: the NCCL watchdog thread polls its events while we capture
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 self.losses = self._device_step(st)
             self.graphs[key] = g
             return
         g.replay()
+
+    def close(self):
+        """Drops the captured graphs (needed before tearing down the process group)."""
+        torch.cuda.synchronize()
+        self.graphs.clear()
+        torch.cuda.synchronize()
 
     def __call__(self, batch):
         key, st = self.copy_in(batch)

@@ -96,6 +96,16 @@ int ergm_embed_fuse_fwd(const int64_t* ids, const int64_t* token_type_ids,
                         float* out, int B, int T, int H, int past_len, int vocab, int n_pos,
                         float dropout_p, uint64_t seed, uint64_t offset, int* err_flag,
                         void* stream);
+/* A3 extension (north_star "projects per-utterance audio and keyframe-visual   */
+/* feature sequences into the hidden space"; the reference pools offline,        */
+/* feature_extraction.py:63,69, and has no projection - SURVEY Appendix A D7):   */
+/* time-mean of fp32 feature sequences seq[b, t, 0:D] (strides ld_b, ld_t in     */
+/* elements; lens = nullable int32 [B] valid frames per sample) -> pooled        */
+/* [B, D] as fp32 and/or bf16 (the A operand of the D -> H projection            */
+/* ergm_gemm_bf16 whose fp32 output feeds ergm_embed_fuse_fwd's imgs / auds).    */
+int ergm_mm_pool_fwd(const float* seq, int64_t ld_b, int64_t ld_t, const int* lens, int B,
+                     int T, int D, float* pooled_f32, int64_t ld_f32, void* pooled_bf16,
+                     int64_t ld_bf16, void* stream);
 /* caption embeddings enc = wte[caption_ids] (model.py:460-463), bf16 output  */
 int ergm_gather_rows_bf16(const int64_t* ids, const float* table, void* out_bf16, int rows,
                           int H, int vocab, int* err_flag, void* stream);

@@ -32,7 +32,7 @@ class OracleConfig:
     """The GPT2Config fields the path reads (model.py:64-104, 271-284, 383-396)."""
 
     def __init__(self, vocab_size=50260, n_positions=1024, n_embd=768, n_layer=12, n_head=12,
-                 n_inner=None, layer_norm_epsilon=1e-5, initializer_range=0.02):
+                 n_inner=None, layer_norm_epsilon=1e-5, initializer_range=0.02, visual_dim=None, audio_dim=None):
         self.vocab_size = vocab_size
         self.n_positions = n_positions
         self.n_embd = n_embd
@@ -41,6 +41,7 @@ class OracleConfig:
         self.n_inner = n_inner if n_inner is not None else 4 * n_embd
         self.layer_norm_epsilon = layer_norm_epsilon
         self.initializer_range = initializer_range
+        self.visual_dim, self.audio_dim = visual_dim, audio_dim  # A3 extension (None = reference layout)
 
     @property
     def head_dim(self):
@@ -71,6 +72,9 @@ def param_shapes(cfg: OracleConfig) -> List[Tuple[str, Tuple[int, ...]]]:
         ]
     out += [("transformer.ln_f.weight", (H,)), ("transformer.ln_f.bias", (H,)),
             ("emotion_head.weight", (NUM_EMOTIONS, H))]
+    if cfg.visual_dim:  # A3 extension parameters (absent from the reference state dict)
+        out += [("visual_proj.weight", (H, cfg.visual_dim)), ("visual_proj.bias", (H,)),
+                ("audio_proj.weight", (H, cfg.audio_dim)), ("audio_proj.bias", (H,))]
     return out
 
 
@@ -193,6 +197,17 @@ def block(sd, i, cfg, x, enc, layer_past=None, attention_mask=None, enc_mask=Non
 # --------------------------------------------------------------------------------------
 # model
 # --------------------------------------------------------------------------------------
+def modality_pool_proj(sd, vis_seq, aud_seq):
+    """A3 EXTENSION — not in the reference model (parity unpinned for this function; SURVEY.md §8 A3,
+    Appendix A D7).  Restates the reference's OFFLINE pooling, feature_extraction.py:63 (audio
+    `last_hidden_state.mean(dim=1)`) and :69 (visual `.mean(dim=1)`), followed by a learned
+    Linear(D -> H) per modality (`visual_proj`, `audio_proj`) so that 768-wide features can feed a
+    1024-wide backbone.  Returns (imgs [B,1,H], auds [B,H]) in the layout model.py:497-498 indexes."""
+    v = F.linear(vis_seq.mean(dim=1), sd["visual_proj.weight"], sd["visual_proj.bias"])
+    a = F.linear(aud_seq.mean(dim=1), sd["audio_proj.weight"], sd["audio_proj.bias"])
+    return v[:, None, :], a
+
+
 def backbone(sd, cfg, input_ids, token_type_ids=None, imgs=None, auds=None, caption_ids=None,
              past_key_values=None, attention_mask=None, position_ids=None):
     """GPT2Model.forward, model.py:420-596.  caption_ids=None skips cross-attention (the
@@ -216,6 +231,8 @@ def backbone(sd, cfg, input_ids, token_type_ids=None, imgs=None, auds=None, capt
     enc_mask = None
     if enc is not None:  # :484-489: all-ones mask inverted -> additive zeros
         enc_mask = torch.zeros(B, 1, 1, enc.shape[1], dtype=wte.dtype)
+    if imgs is not None and "visual_proj.weight" in sd:
+        imgs, auds = modality_pool_proj(sd, imgs, auds)
     if imgs is not None:  # :495-498, in place on the wte output, before wpe / token types
         inputs_embeds = inputs_embeds.clone()
         for i in range(B):

@@ -35,5 +35,6 @@ if "--graph" in sys.argv:
     pinned = {k: v.cpu().pin_memory() for k, v in mine.items()}
     for i in range(3):
         l = step(pinned); say("graph step", i, l)
+    step.close(); say("closed")
 dist.destroy_process_group()
 say("done")

@@ -61,6 +61,8 @@ same = bool(torch.equal(t, t2))
 w0 = m2.transformer.h[1].mlp.c_fc.weight.detach().clone(); w1 = w0.clone(); dist.broadcast(w1, 0)
 print("RANK%%d loss_ok=%%s worst_grad_rel=%%.2e wdiff=%%.2e graph_losses=%%s same=%%s wsync=%%s" %% (rank, ok, worst, wdiff, ["%%.4f" %% x for x in losses], same, bool(torch.equal(w0, w1))), flush=True)
 assert ok and worst < 2e-3 and wdiff < 1e-5 and same and torch.equal(w0, w1) and losses[2] < losses[0]
+step.close()
+dist.barrier()
 dist.destroy_process_group()
 '''
 

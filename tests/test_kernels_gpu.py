@@ -374,3 +374,30 @@ def test_gelu_bwd_colsum(cuda_device):
     ops.gelu_bwd_colsum(out, u, cs)
     assert (out.float() - ur.grad).abs().max().item() < 3e-2
     assert (cs - out.float().sum(0)).abs().max().item() < 1e-2
+
+
+@pytest.mark.parametrize("B,T,D", [(4, 113, 768), (3, 788, 768), (2, 1, 128), (5, 37, 260)])
+def test_mm_pool_fwd(cuda_device, B, T, D):
+    from ergm_b200 import ops
+    """Time-mean of feature sequences (feature_extraction.py:63,69 restated as seq.mean(1)), with
+    ragged valid lengths, strided views and both output dtypes."""
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    seq = torch.randn(B, T, D, generator=g).cuda()
+    p32 = torch.empty(B, D, device="cuda")
+    pb = torch.empty(B, D, dtype=torch.bfloat16, device="cuda")
+    ops.mm_pool_fwd(seq, p32, pb)
+    want = seq.double().mean(1)
+    assert (p32.double() - want).abs().max().item() < 2e-6
+    assert torch.equal(pb, p32.to(torch.bfloat16))
+    lens = torch.randint(1, T + 1, (B,), generator=g).int().cuda()
+    ops.mm_pool_fwd(seq, p32, None, lens=lens)
+    for b in range(B):
+        w = seq[b, : int(lens[b])].double().mean(0)
+        assert (p32[b].double() - w).abs().max().item() < 2e-6
+    # run twice: fixed-order reduction -> bitwise reproducible
+    q32 = torch.empty_like(p32)
+    ops.mm_pool_fwd(seq, q32, None, lens=lens)
+    assert torch.equal(p32, q32)
+    if T >= 4:  # strided view: every second frame
+        ops.mm_pool_fwd(seq[:, ::2], p32, None)
+        assert (p32.double() - seq[:, ::2].double().mean(1)).abs().max().item() < 2e-6

@@ -29,6 +29,8 @@ def build_model(cfg, sd, dropout=0.0):
     hf = GPT2Config(vocab_size=cfg.vocab_size, n_positions=cfg.n_positions, n_embd=cfg.n_embd, n_layer=cfg.n_layer,
                     n_head=cfg.n_head, attn_pdrop=dropout, resid_pdrop=dropout, embd_pdrop=dropout,
                     initializer_range=cfg.initializer_range)
+    if getattr(cfg, "visual_dim", None):
+        hf.ergm_visual_dim, hf.ergm_audio_dim = cfg.visual_dim, cfg.audio_dim
     m = GPT2LMHeadModel(hf)
     m.load_state_dict(sd, strict=True)
     return m.to("cuda")
@@ -269,3 +271,39 @@ def test_medium_width_long_context_step(cuda_device):
                  "transformer.h.0.ln_1.weight", "transformer.h.1.attn.c_proj.bias"):
         p = dict(m.named_parameters())[name]
         assert rel(p.grad, sdo[name].grad) < 3e-2, (name, rel(p.grad, sdo[name].grad))
+
+
+def test_modality_sequence_projection_extension(cuda_device):
+    """A3 extension (768-wide features cannot feed a 1024-wide backbone in the
+    reference): raw audio [B,113,768] / 4-key-frame visual [B,788,768] sequences are mean-pooled and
+    projected 768 -> 1024 on the device.  Forward, loss and the projection gradients against the
+    oracle's restatement of feature_extraction.py:63,69 + Linear (parity unpinned by the reference:
+    the extension has no reference implementation)."""
+    cfg = O.OracleConfig(vocab_size=2048, n_positions=128, n_embd=1024, n_layer=2, n_head=16, visual_dim=768,
+                         audio_dim=768)
+    sd = O.init_state_dict(cfg, seed=21, perturb=True)
+    m = build_model(cfg, sd).train()
+    b = synthetic.make_batch(4, 64, seed=22, vocab=cfg.vocab_size, feat_dim=768, kf=4)
+    b["labels"] = b["input_ids"].clone()
+    kw = cuda_batch(b, fusion=False)
+    kw["imgs"], kw["auds"] = b["vis_seq"].cuda(), b["aud_seq"].cuda()
+    out = m(**kw)
+    out.loss.backward()
+    sdo = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k != "lm_head.weight"}
+    sdo["lm_head.weight"] = sdo["transformer.wte.weight"]
+    o = O.forward(sdo, cfg, b["input_ids"], b["token_type_ids"], b["labels"], b["emotion_labels"], b["vis_seq"],
+                  b["aud_seq"], b["caption_ids"])
+    o["loss"].backward()
+    assert abs(out.lm_loss.item() - o["lm_loss"].item()) < LOSS_TOL
+    assert rel(out.logits, o["logits"]) < LOGITS_REL_TOL
+    # the fused rows (positions 0 and 1) must carry the projected features: compare logits there alone
+    assert rel(out.logits[:, :2], o["logits"][:, :2]) < LOGITS_REL_TOL
+    for name in ("visual_proj.weight", "visual_proj.bias", "audio_proj.weight", "audio_proj.bias"):
+        p = dict(m.named_parameters())[name]
+        assert p.grad is not None and rel(p.grad, sdo[name].grad) < 4e-2, (name, rel(p.grad, sdo[name].grad))
+    # without the projection parameters the reference layout is untouched
+    assert "visual_proj.weight" not in build_model(O.OracleConfig(vocab_size=256, n_positions=64, n_embd=128, n_layer=1,
+                                                                   n_head=2),
+                                                   O.init_state_dict(O.OracleConfig(vocab_size=256, n_positions=64,
+                                                                                    n_embd=128, n_layer=1, n_head=2),
+                                                                     seed=1)).state_dict()

@@ -121,3 +121,19 @@ def test_oracle_bit_equal_to_reference_block():
         want = blk(x, encoder_hidden_states=enc, encoder_attention_mask=torch.zeros(2, 1, 1, 9))[0]
         got, _ = O.block(sd, 0, cfg, x, enc, enc_mask=torch.zeros(2, 1, 1, 9))
     assert torch.equal(want, got)
+
+
+def test_modality_pool_proj_extension_restates_offline_pooling():
+    """A3 extension oracle: time-mean (feature_extraction.py:63,69) then Linear; with an identity
+    projection it must reproduce the reference's pooled-feature layout exactly."""
+    g = torch.Generator().manual_seed(5)
+    vis, aud = torch.randn(3, 197, 16, generator=g), torch.randn(3, 113, 16, generator=g)
+    sd = {"visual_proj.weight": torch.eye(16), "visual_proj.bias": torch.zeros(16),
+          "audio_proj.weight": torch.eye(16), "audio_proj.bias": torch.zeros(16)}
+    v, a = O.modality_pool_proj(sd, vis, aud)
+    assert v.shape == (3, 1, 16) and a.shape == (3, 16)
+    assert torch.allclose(v[:, 0], vis.mean(1), atol=1e-7) and torch.allclose(a, aud.mean(1), atol=1e-7)
+    cfg = O.OracleConfig(vocab_size=64, n_positions=32, n_embd=32, n_layer=1, n_head=2, visual_dim=16, audio_dim=16)
+    keys = dict(O.param_shapes(cfg))
+    assert keys["visual_proj.weight"] == (32, 16) and keys["audio_proj.bias"] == (32,)
+    assert "visual_proj.weight" not in dict(O.param_shapes(O.OracleConfig(vocab_size=64, n_embd=32, n_layer=1, n_head=2)))
