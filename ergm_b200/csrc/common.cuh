@@ -185,6 +185,21 @@ ERGM_DEVINL uint32_t cluster_ctarank() {
 ERGM_DEVINL void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+ERGM_DEVINL void cluster_arrive() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+ERGM_DEVINL void cluster_wait() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+ERGM_DEVINL void st_cluster_v2(uint32_t cluster_addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(cluster_addr), "r"(a), "r"(b) : "memory");
+}
+// Programmatic dependent launch (PDL): launch_dependents lets the NEXT kernel of the stream start its
+// independent prologue (barrier init, weight / KV-cache prefetch) while this one is still running;
+// pdl_wait blocks until every kernel this one depends on has completed and flushed.  Both are no-ops
+// for kernels launched without the programmatic-serialization attribute.
+ERGM_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+ERGM_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 // shared::cta address of this CTA -> shared::cluster address of the same offset in CTA `rank`
 ERGM_DEVINL uint32_t mapa_cluster(uint32_t addr, uint32_t rank) {
   uint32_t r;
@@ -352,6 +367,29 @@ ERGM_DEVINL float warp_max(float v) {
   } while (0)
 
 namespace ergm {
+// Kernel launch with the PDL attribute (and an optional cluster dimension along x).
+// ERGM_PDL=0 in the environment turns the attribute off (plain stream order).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attrs[2];
+  unsigned n = 0;
+  if (pdl_enabled()) {
+    attrs[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster_x > 1) {
+    attrs[n].id = cudaLaunchAttributeClusterDimension;
+    attrs[n].val.clusterDim.x = (unsigned)cluster_x; attrs[n].val.clusterDim.y = 1; attrs[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = attrs; cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 // Encodes a 2-D bf16/fp32 tiled tensor map (128B swizzle).  dims/strides follow the
 // cuTensorMapEncodeTiled convention: dim0 is the contiguous one.
 int encode_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t dim0,

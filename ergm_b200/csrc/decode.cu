@@ -21,7 +21,6 @@ namespace ergm {
 
 constexpr int PAGE = 16;           // tokens per KV page
 constexpr int DEC_THREADS = 128;   // 16 groups of 8 lanes; a group owns one token at a time
-constexpr int DEC_MAX_CTX = 2048;  // scores staged in smem
 
 struct DecodeAttnParams {
   const __nv_bfloat16* q;    // [B, ld_q]: head h at q_col0 + 64h
@@ -44,95 +43,133 @@ ERGM_DEVINL float dot8(const uint4 a, const uint4 b) {
   return a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y + a3.x * b3.x + a3.y * b3.y;
 }
 
+// One CTA per (head, sequence).  16 groups of 8 lanes; a group owns tokens grp, grp+16, ... and keeps
+// its OWN online-softmax state (running max, sum, 8 output dims per lane), so the token loop has no
+// block-wide synchronisation and every thread keeps 16 independent 16-byte K/V loads in flight
+// (8 tokens x {K, V}); the 16 partial states are merged once at the end (flash-decoding inside a CTA).
+// The cached K/V of the context do not depend on the kernel that produced q: their first 128 tokens
+// are fetched BEFORE the programmatic-dependency wait, i.e. while the QKV projection is still running.
+constexpr int DEC_UNROLL = 8;
+constexpr int DEC_GROUPS = DEC_THREADS / 8;
+constexpr int DEC_BT_SMEM = 256;   // block-table entries staged in smem (4096 tokens)
+
 template <bool PAGED>
 __global__ void __launch_bounds__(DEC_THREADS) attn_decode_kernel(const DecodeAttnParams p) {
-  __shared__ float s_score[DEC_MAX_CTX];
-  __shared__ float s_red[DEC_THREADS / 32];
-  __shared__ float s_acc[DEC_THREADS / 8][64];
+  __shared__ float s_m[DEC_GROUPS], s_l[DEC_GROUPS];
+  __shared__ float s_acc[DEC_GROUPS][64];
+  __shared__ int s_bt[DEC_BT_SMEM];
   const int h = blockIdx.x, b = blockIdx.y;
   const int grp = threadIdx.x >> 3, gl = threadIdx.x & 7;  // token group, lane inside the 128 B row
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint4 qv = *reinterpret_cast<const uint4*>(p.q + (int64_t)b * p.ld_q + p.q_col0 + h * 64 + gl * 8);
-  int ctx;
+  pdl_launch_dependents();
+  int n_old, pos = 0;  // cached tokens (the new one of paged mode is handled from registers)
   if (PAGED) {
-    const int pos = p.seq_lens[b];
-    ctx = pos + 1;
-    // append this head's new K / V row to the page pool (8 lanes x 16 B each)
-    if (grp < 2) {
-      const int page = p.block_table[b * p.max_pages + pos / PAGE];
-      const int col = (grp == 0 ? p.k_col0 : p.v_col0) + h * 64 + gl * 8;
-      const uint4 nv = *reinterpret_cast<const uint4*>(p.kv_new + (int64_t)b * p.ld_q + col);
-      __nv_bfloat16* dst = p.pool + ((((int64_t)page * 2 + grp) * p.nh + h) * PAGE + pos % PAGE) * 64 + gl * 8;
-      *reinterpret_cast<uint4*>(dst) = nv;
-    }
-    __syncthreads();  // the appended row is read back below by other groups
+    pos = p.seq_lens[b];
+    n_old = pos;
+    const int npages = min(pos / PAGE + 1, DEC_BT_SMEM);
+    for (int i = threadIdx.x; i < npages; i += DEC_THREADS) s_bt[i] = p.block_table[b * p.max_pages + i];
+    __syncthreads();
   } else {
-    ctx = p.kv_lens ? min(p.Tk, p.kv_lens[b]) : p.Tk;
+    n_old = p.kv_lens ? min(p.Tk, p.kv_lens[b]) : p.Tk;
   }
-  if (ctx > DEC_MAX_CTX) ctx = DEC_MAX_CTX;
-  auto k_row = [&](int t) -> const uint4* {
+  auto kv_row = [&](int t, int which) -> const uint4* {
     if (PAGED) {
-      const int page = p.block_table[b * p.max_pages + t / PAGE];
-      return reinterpret_cast<const uint4*>(p.pool + ((((int64_t)page * 2 + 0) * p.nh + h) * PAGE + t % PAGE) * 64) + gl;
+      const int pi = t / PAGE;
+      const int page = pi < DEC_BT_SMEM ? s_bt[pi] : p.block_table[b * p.max_pages + pi];
+      return reinterpret_cast<const uint4*>(p.pool + ((((int64_t)page * 2 + which) * p.nh + h) * PAGE + t % PAGE) * 64) + gl;
     }
-    return reinterpret_cast<const uint4*>(p.kc + ((int64_t)b * p.Tk + t) * p.ld_k + p.k_col0 + h * 64) + gl;
+    return reinterpret_cast<const uint4*>(p.kc + ((int64_t)b * p.Tk + t) * p.ld_k + (which ? p.v_col0 : p.k_col0) + h * 64) + gl;
   };
-  auto v_row = [&](int t) -> const uint4* {
-    if (PAGED) {
-      const int page = p.block_table[b * p.max_pages + t / PAGE];
-      return reinterpret_cast<const uint4*>(p.pool + ((((int64_t)page * 2 + 1) * p.nh + h) * PAGE + t % PAGE) * 64) + gl;
+  uint4 kk[DEC_UNROLL], vv[DEC_UNROLL];
+  auto load_chunk = [&](int tb) {
+#pragma unroll
+    for (int u = 0; u < DEC_UNROLL; ++u) {
+      const int t = tb + u * DEC_GROUPS + grp;
+      const bool ok = t < n_old;
+      kk[u] = ok ? __ldg(kv_row(t, 0)) : make_uint4(0u, 0u, 0u, 0u);
+      vv[u] = ok ? __ldg(kv_row(t, 1)) : make_uint4(0u, 0u, 0u, 0u);
     }
-    return reinterpret_cast<const uint4*>(p.kc + ((int64_t)b * p.Tk + t) * p.ld_k + p.v_col0 + h * 64) + gl;
   };
-  // phase 1: scores
-  float mx = -INFINITY;
+  load_chunk(0);
+  pdl_wait();  // q (and the new token's K / V) come from the projection kernel just before this one
+  const uint4 qv = *reinterpret_cast<const uint4*>(p.q + (int64_t)b * p.ld_q + p.q_col0 + h * 64 + gl * 8);
+  float m_run = -INFINITY, l_run = 0.f;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   // uniform trip count for the whole warp: the shuffles below are full-mask collectives
-  for (int tb = 0; tb < ctx; tb += DEC_THREADS / 8) {
-    const int t = tb + grp;
-    const bool ok = t < ctx;
-    float s = ok ? dot8(qv, *k_row(t)) : 0.f;
+  for (int tb = 0; tb < n_old; tb += DEC_GROUPS * DEC_UNROLL) {
+    if (tb > 0) load_chunk(tb);
+    float sc[DEC_UNROLL];
+    float m_new = m_run;
+#pragma unroll
+    for (int u = 0; u < DEC_UNROLL; ++u) {
+      float s = dot8(qv, kk[u]);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      sc[u] = (tb + u * DEC_GROUPS + grp < n_old) ? s * p.scale : -INFINITY;
+      m_new = fmaxf(m_new, sc[u]);
+    }
+    if (m_new > -INFINITY) {
+      const float corr = __expf(m_run - m_new);  // m_run = -inf -> 0
+      l_run *= corr;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] *= corr;
+#pragma unroll
+      for (int u = 0; u < DEC_UNROLL; ++u) {
+        const float w = __expf(sc[u] - m_new);  // masked tokens: exp(-inf) = 0
+        l_run += w;
+        const float2 v0 = unpack_bf16x2(vv[u].x), v1 = unpack_bf16x2(vv[u].y), v2 = unpack_bf16x2(vv[u].z),
+                     v3 = unpack_bf16x2(vv[u].w);
+        acc[0] += w * v0.x; acc[1] += w * v0.y; acc[2] += w * v1.x; acc[3] += w * v1.y;
+        acc[4] += w * v2.x; acc[5] += w * v2.y; acc[6] += w * v3.x; acc[7] += w * v3.y;
+      }
+      m_run = m_new;
+    }
+  }
+  if (PAGED && threadIdx.x < 32) {
+    // the new token: straight from the projection output; warp 0 computes its score (all four groups,
+    // redundantly, so the shuffles stay warp-uniform), group 0 folds it into its state, groups 0 / 1
+    // append K / V to the page pool (8 lanes x 16 B each)
+    const uint4 kn = *reinterpret_cast<const uint4*>(p.kv_new + (int64_t)b * p.ld_q + p.k_col0 + h * 64 + gl * 8);
+    const uint4 vn = *reinterpret_cast<const uint4*>(p.kv_new + (int64_t)b * p.ld_q + p.v_col0 + h * 64 + gl * 8);
+    float s = dot8(qv, kn);
     s += __shfl_xor_sync(0xffffffffu, s, 4);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s *= p.scale;
-    if (ok) {
-      if (gl == 0) s_score[t] = s;
-      mx = fmaxf(mx, s);
+    if (grp == 0) {
+      const float m_new = fmaxf(m_run, s);
+      const float corr = __expf(m_run - m_new), w = __expf(s - m_new);
+      l_run = l_run * corr + w;
+      const float2 v0 = unpack_bf16x2(vn.x), v1 = unpack_bf16x2(vn.y), v2 = unpack_bf16x2(vn.z), v3 = unpack_bf16x2(vn.w);
+      acc[0] = acc[0] * corr + w * v0.x; acc[1] = acc[1] * corr + w * v0.y;
+      acc[2] = acc[2] * corr + w * v1.x; acc[3] = acc[3] * corr + w * v1.y;
+      acc[4] = acc[4] * corr + w * v2.x; acc[5] = acc[5] * corr + w * v2.y;
+      acc[6] = acc[6] * corr + w * v3.x; acc[7] = acc[7] * corr + w * v3.y;
+      m_run = m_new;
+    }
+    if (grp < 2) {
+      const int pi = pos / PAGE;
+      const int page = pi < DEC_BT_SMEM ? s_bt[pi] : p.block_table[b * p.max_pages + pi];
+      __nv_bfloat16* dst = p.pool + ((((int64_t)page * 2 + grp) * p.nh + h) * PAGE + pos % PAGE) * 64 + gl * 8;
+      *reinterpret_cast<uint4*>(dst) = grp == 0 ? kn : vn;
     }
   }
-  mx = warp_max(mx);
-  if (lane == 0) s_red[warp] = mx;
-  __syncthreads();
-  mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
-  __syncthreads();
-  // phase 2: exp + sum
-  float sum = 0.f;
-  for (int t = threadIdx.x; t < ctx; t += DEC_THREADS) {
-    const float e = __expf(s_score[t] - mx);
-    s_score[t] = e;
-    sum += e;
-  }
-  sum = warp_sum(sum);
-  if (lane == 0) s_red[warp] = sum;
-  __syncthreads();
-  const float inv = 1.f / (s_red[0] + s_red[1] + s_red[2] + s_red[3]);
-  // phase 3: weighted sum of V rows (each lane owns 8 of the 64 dims)
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int t = grp; t < ctx; t += DEC_THREADS / 8) {
-    const float w = s_score[t];
-    const uint4 v = *v_row(t);
-    const float2 v0 = unpack_bf16x2(v.x), v1 = unpack_bf16x2(v.y), v2 = unpack_bf16x2(v.z), v3 = unpack_bf16x2(v.w);
-    acc[0] += w * v0.x; acc[1] += w * v0.y; acc[2] += w * v1.x; acc[3] += w * v1.y;
-    acc[4] += w * v2.x; acc[5] += w * v2.y; acc[6] += w * v3.x; acc[7] += w * v3.y;
-  }
+  if (gl == 0) { s_m[grp] = m_run; s_l[grp] = l_run; }
 #pragma unroll
   for (int i = 0; i < 8; ++i) s_acc[grp][gl * 8 + i] = acc[i];
   __syncthreads();
   if (threadIdx.x < 64) {
-    float o = 0.f;
+    float M = -INFINITY;
 #pragma unroll
-    for (int g = 0; g < DEC_THREADS / 8; ++g) o += s_acc[g][threadIdx.x];
-    p.out[(int64_t)b * p.ld_out + h * 64 + threadIdx.x] = __float2bfloat16_rn(o * inv);
+    for (int g = 0; g < DEC_GROUPS; ++g) M = fmaxf(M, s_m[g]);
+    float Lsum = 0.f, o = 0.f;
+#pragma unroll
+    for (int g = 0; g < DEC_GROUPS; ++g) {
+      const float w = s_m[g] > -INFINITY ? __expf(s_m[g] - M) : 0.f;
+      Lsum += s_l[g] * w;
+      o += s_acc[g][threadIdx.x] * w;
+    }
+    p.out[(int64_t)b * p.ld_out + h * 64 + threadIdx.x] = __float2bfloat16_rn(Lsum > 0.f ? o / Lsum : 0.f);
   }
 }
 
@@ -173,6 +210,8 @@ struct SampleParams {
   int* finished;         // [B]
   int* seq_lens;         // [B]: advanced by one (nullable)
   int64_t eos_id;        // < 0: never finishes
+  int* step_inc;         // nullable: incremented by one after EVERY row has been sampled (last block)
+  unsigned int* done_ctr; // device counter used to find the last block (self-resetting)
 };
 
 // order-preserving float -> uint key (larger float = larger key)
@@ -180,6 +219,9 @@ ERGM_DEVINL uint32_t fkey(float f) {
   const uint32_t u = __float_as_uint(f);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
+
+__device__ unsigned int g_sample_done_ctr = 0u;
+ERGM_DEVINL void sample_commit(const SampleParams& p, int b, int token, int step_now);  // last-block detection of sample_kernel (one stream per device)
 
 __global__ void __launch_bounds__(SMP_THREADS) sample_kernel(const SampleParams p) {
   __shared__ unsigned long long s_best[SMP_THREADS / 32];
@@ -192,6 +234,9 @@ __global__ void __launch_bounds__(SMP_THREADS) sample_kernel(const SampleParams 
   const float* row = p.logits + (int64_t)b * p.ld;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int token;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int step_now = p.step_ptr ? *p.step_ptr : 0;  // read before any block can bump it
   if (p.top_k <= 1) {
     // arg-max, lowest index on ties (torch.argmax semantics): pack (key, ~index) and take the max
     unsigned long long best = 0ull;
@@ -264,8 +309,7 @@ __global__ void __launch_bounds__(SMP_THREADS) sample_kernel(const SampleParams 
       for (int i = 0; i < n; ++i) mx = fmaxf(mx, s_cv[i]);
       float tot = 0.f;
       for (int i = 0; i < n; ++i) { s_cv[i] = __expf((s_cv[i] - mx) * p.inv_temperature); tot += s_cv[i]; }
-      const int step = p.step_ptr ? *p.step_ptr : 0;
-      Philox ph(p.seed, (uint64_t)step);
+      Philox ph(p.seed, (uint64_t)step_now);
       const float u = u01(ph((uint64_t)b).x) * tot;
       // candidates are in arbitrary (atomic) order: walk them in index order for determinism
       float cum = 0.f;
@@ -284,16 +328,80 @@ __global__ void __launch_bounds__(SMP_THREADS) sample_kernel(const SampleParams 
     __syncthreads();
     token = s_ci[0];
   }
-  if (threadIdx.x == 0) {
-    int64_t tok = token;
-    if (p.finished) {
-      if (p.finished[b]) tok = p.eos_id;
-      else if (p.eos_id >= 0 && tok == p.eos_id) p.finished[b] = 1;
+  if (threadIdx.x == 0) sample_commit(p, b, token, step_now);
+}
+
+// thread 0 of the row's block: finished / eos bookkeeping, output column, next input id, lengths,
+// and (last block to get here) the step counter
+ERGM_DEVINL void sample_commit(const SampleParams& p, int b, int token, int step_now) {
+  int64_t tok = token;
+  if (p.finished) {
+    if (p.finished[b]) tok = p.eos_id;
+    else if (p.eos_id >= 0 && tok == p.eos_id) p.finished[b] = 1;
+  }
+  if (p.out_ids) p.out_ids[(int64_t)b * p.out_ld + step_now] = tok;
+  if (p.next_ids) p.next_ids[b] = tok;
+  if (p.seq_lens) p.seq_lens[b] += 1;
+  if (p.step_inc) {
+    // every block read the step at its start; the last one to finish advances it
+    __threadfence();
+    if (atomicAdd(p.done_ctr, 1u) == gridDim.x - 1) {
+      *p.done_ctr = 0u;
+      *p.step_inc += 1;
     }
-    const int step = p.step_ptr ? *p.step_ptr : 0;
-    if (p.out_ids) p.out_ids[(int64_t)b * p.out_ld + step] = tok;
-    if (p.next_ids) p.next_ids[b] = tok;
-    if (p.seq_lens) p.seq_lens[b] += 1;
+  }
+}
+
+// greedy arg-max (torch.argmax semantics: lowest index on ties): 1024 threads per row, 16-byte loads
+constexpr int AMX_THREADS = 1024;
+__global__ void __launch_bounds__(AMX_THREADS) argmax_kernel(const SampleParams p) {
+  __shared__ unsigned long long s_best[AMX_THREADS / 32];
+  const int b = blockIdx.x;
+  const float* row = p.logits + (int64_t)b * p.ld;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int step_now = p.step_ptr ? *p.step_ptr : 0;
+  unsigned long long best = 0ull;
+  auto consider = [&](float v, int i) {
+    const unsigned long long cand = ((unsigned long long)fkey(v) << 32) | (uint32_t)(~(uint32_t)i);
+    best = cand > best ? cand : best;
+  };
+  int done = 0;
+  if ((reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+    const int n4 = p.V >> 2;
+    const float4* row4 = reinterpret_cast<const float4*>(row);
+    int i = threadIdx.x;
+    for (; i + 3 * AMX_THREADS < n4; i += 4 * AMX_THREADS) {
+      const float4 v0 = row4[i], v1 = row4[i + AMX_THREADS], v2 = row4[i + 2 * AMX_THREADS], v3 = row4[i + 3 * AMX_THREADS];
+      consider(v0.x, 4 * i); consider(v0.y, 4 * i + 1); consider(v0.z, 4 * i + 2); consider(v0.w, 4 * i + 3);
+      const int i1 = i + AMX_THREADS, i2 = i + 2 * AMX_THREADS, i3 = i + 3 * AMX_THREADS;
+      consider(v1.x, 4 * i1); consider(v1.y, 4 * i1 + 1); consider(v1.z, 4 * i1 + 2); consider(v1.w, 4 * i1 + 3);
+      consider(v2.x, 4 * i2); consider(v2.y, 4 * i2 + 1); consider(v2.z, 4 * i2 + 2); consider(v2.w, 4 * i2 + 3);
+      consider(v3.x, 4 * i3); consider(v3.y, 4 * i3 + 1); consider(v3.z, 4 * i3 + 2); consider(v3.w, 4 * i3 + 3);
+    }
+    for (; i < n4; i += AMX_THREADS) {
+      const float4 v = row4[i];
+      consider(v.x, 4 * i); consider(v.y, 4 * i + 1); consider(v.z, 4 * i + 2); consider(v.w, 4 * i + 3);
+    }
+    done = n4 << 2;
+  }
+  for (int i = done + threadIdx.x; i < p.V; i += AMX_THREADS) consider(row[i], i);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+    best = other > best ? other : best;
+  }
+  if (lane == 0) s_best[warp] = best;
+  __syncthreads();
+  if (warp == 0) {
+    best = s_best[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = other > best ? other : best;
+    }
+    if (lane == 0) sample_commit(p, b, (int)(~(uint32_t)(best & 0xffffffffu)), step_now);
   }
 }
 
@@ -319,8 +427,7 @@ extern "C" int ergm_attn_decode_paged(const void* qkv, int64_t ld_q, int q_col0,
   p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
   p.nh = nh; p.max_pages = max_pages;
   p.scale = 1.0f / sqrtf((float)head_dim);
-  attn_decode_kernel<true><<<dim3(nh, B), DEC_THREADS, 0, (cudaStream_t)stream>>>(p);
-  return (int)cudaGetLastError();
+  return (int)launch_pdl(attn_decode_kernel<true>, dim3(nh, B), dim3(DEC_THREADS), 0, (cudaStream_t)stream, 1, p);
 }
 
 extern "C" int ergm_attn_decode_contig(const void* q, int64_t ld_q, int q_col0, const void* kv,
@@ -329,7 +436,6 @@ extern "C" int ergm_attn_decode_contig(const void* q, int64_t ld_q, int q_col0, 
                                        int head_dim, void* stream) {
   if (!q || !kv || !out || B <= 0 || nh <= 0 || Tk <= 0) return ERGM_ERR_ARG;
   if (head_dim != 64) return ERGM_ERR_UNSUPPORTED;
-  if (Tk > DEC_MAX_CTX) return ERGM_ERR_UNSUPPORTED;
   if (ld_q % 8 || ld_k % 8 || q_col0 % 8 || k_col0 % 8 || v_col0 % 8) return ERGM_ERR_ARG;
   DecodeAttnParams p{};
   p.q = reinterpret_cast<const __nv_bfloat16*>(q);
@@ -340,8 +446,7 @@ extern "C" int ergm_attn_decode_contig(const void* q, int64_t ld_q, int q_col0, 
   p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
   p.nh = nh; p.Tk = Tk;
   p.scale = 1.0f / sqrtf((float)head_dim);
-  attn_decode_kernel<false><<<dim3(nh, B), DEC_THREADS, 0, (cudaStream_t)stream>>>(p);
-  return (int)cudaGetLastError();
+  return (int)launch_pdl(attn_decode_kernel<false>, dim3(nh, B), dim3(DEC_THREADS), 0, (cudaStream_t)stream, 1, p);
 }
 
 extern "C" int ergm_kv_to_pages(const void* kv, int64_t ld, int k_col0, int v_col0, void* pool,
@@ -356,15 +461,18 @@ extern "C" int ergm_kv_to_pages(const void* kv, int64_t ld, int k_col0, int v_co
 }
 
 extern "C" int ergm_sample(const float* logits, int64_t ld, int B, int V, int top_k,
-                           float temperature, uint64_t seed, const int* step_ptr, int64_t* out_ids,
+                           float temperature, uint64_t seed, int* step_ptr, int advance_step, int64_t* out_ids,
                            int64_t out_ld, int64_t* next_ids, int* finished, int* seq_lens,
                            int64_t eos_id, void* stream) {
   if (!logits || B <= 0 || V <= 0 || top_k < 0 || top_k > SMP_MAX_K) return ERGM_ERR_ARG;
   if (top_k > 1 && !(temperature > 0.f)) return ERGM_ERR_ARG;
+  if (advance_step && !step_ptr) return ERGM_ERR_ARG;
+  unsigned int* ctr = nullptr;
+  if (advance_step) ERGM_CUDA_TRY(cudaGetSymbolAddress(reinterpret_cast<void**>(&ctr), g_sample_done_ctr));
   SampleParams p{logits, ld, V, top_k, top_k > 1 ? 1.f / temperature : 1.f, seed, step_ptr, out_ids, out_ld,
-                 next_ids, finished, seq_lens, eos_id};
-  sample_kernel<<<B, SMP_THREADS, 0, (cudaStream_t)stream>>>(p);
-  return (int)cudaGetLastError();
+                 next_ids, finished, seq_lens, eos_id, advance_step ? step_ptr : nullptr, ctr};
+  if (top_k <= 1) return (int)launch_pdl(argmax_kernel, dim3((unsigned)B), dim3(AMX_THREADS), 0, (cudaStream_t)stream, 1, p);
+  return (int)launch_pdl(sample_kernel, dim3((unsigned)B), dim3(SMP_THREADS), 0, (cudaStream_t)stream, 1, p);
 }
 
 extern "C" int ergm_int_add(int* dev_ptr, int inc, void* stream) {

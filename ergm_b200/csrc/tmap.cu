@@ -3,6 +3,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include <cstdlib>
 
 namespace ergm {
 
@@ -59,6 +60,15 @@ int encode_tmap_3d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t 
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? ERGM_OK : ERGM_ERR_DRIVER;
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("ERGM_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
 }
 
 int num_sms() {

@@ -53,44 +53,77 @@ def _head_on_rows(eng, x, row_idx, logits):
     ops.gemm(hn, eng.pb("transformer.wte.weight"), logits, M=n, N=eng.V, K=eng.H, a_major=K_MAJOR, b_major=K_MAJOR)
 
 
+DEC_TILE = 64  # rows per ergm_dec_gemm call
+
+
+def packed_weights(eng):
+    """Decode-layout copies of the weights (bf16 16-column slabs in mma fragment order with the
+    preceding LayerNorm folded in, ergm_dec_pack_weight), cached per parameter version: generation
+    never re-packs unless the weights changed.  Values: (packed, bias)."""
+    ver = sum(p._version for p in eng.store._plist)
+    hit = eng.__dict__.get("_dec_pack")
+    if hit is not None and hit[0] == ver and hit[1] is eng.store.flat:
+        return hit[2]
+    H, I, V = eng.H, eng.I, eng.V
+    pk = {}
+    for l in range(eng.L):
+        pfx = "transformer.h.%d." % l
+        for name, K, N, ln in (("attn.c_attn", H, 3 * H, "ln_1"), ("attn.c_proj", H, H, None),
+                               ("crossattention.q_attn", H, H, "ln_cross_attn"), ("crossattention.c_proj", H, H, None),
+                               ("mlp.c_fc", H, I, "ln_2"), ("mlp.c_proj", I, H, None)):
+            pk[pfx + name] = ops.dec_pack_weight(
+                eng.p(pfx + name + ".weight"), K, N, gamma=eng.p(pfx + ln + ".weight") if ln else None,
+                beta=eng.p(pfx + ln + ".bias") if ln else None, bias=eng.p(pfx + name + ".bias"))
+    eng.__dict__["_dec_pack"] = (ver, eng.store.flat, pk)
+    return pk
+
+
 def decode_step(eng, st, sample_kw):
-    """One token for every sequence of the batch; pure device work (CUDA-graph capturable)."""
-    H, nh, I, B = eng.H, eng.nh, eng.I, st.B
+    """One token for every sequence of the batch; pure device work (CUDA-graph capturable).
+    Per layer: [LN1 + QKV] -> paged attention (+append) -> [out-proj += residual] -> ([LN + q] ->
+    cross attention -> [out-proj +=]) -> [LN2 + FC + gelu] -> [MLP proj +=]; every bracket is one
+    weight-streaming ergm_dec_gemm launch (programmatic dependent launch: its weight prefetch
+    overlaps the previous kernel)."""
+    H, nh, I, B, V = eng.H, eng.nh, eng.I, st.B, eng.V
     ws = eng.ws_eval
     f32, bf16 = torch.float32, torch.bfloat16
     eps = eng.cfg.layer_norm_epsilon
+    pk = st.packed
     x = ws.get("dec_x", (B, H), f32)
     ops.embed_fuse_fwd(st.next_ids, st.tt, None, eng.p("transformer.wte.weight"), eng.p("transformer.wpe.weight"),
                        None, None, x, past_lens=st.seq_lens)
-    a = ws.get("dec_a", (B, H), bf16)
     qkv = ws.get("dec_qkv", (B, 3 * H), bf16)
     ctx = ws.get("dec_ctx", (B, H), bf16)
     q2 = ws.get("dec_q2", (B, H), bf16)
     g = ws.get("dec_g", (B, I), bf16)
+    tiles = [(r0, min(B, r0 + DEC_TILE)) for r0 in range(0, B, DEC_TILE)]
+
+    def ln_gemm(out, name, K, N, **kw):
+        w, b = pk[name]
+        for r0, r1 in tiles:
+            ops.dec_gemm(out[r0:r1], w, M=r1 - r0, K=K, N=N, x=x[r0:r1], eps=eps, bias=b, **kw)
+
+    def res_gemm(a, name, K, N):
+        w, b = pk[name]
+        for r0, r1 in tiles:
+            ops.dec_gemm(x[r0:r1], w, M=r1 - r0, K=K, N=N, a=a[r0:r1], bias=b, out_mode=2)
+
     for l in range(eng.L):
         pfx = "transformer.h.%d." % l
-        ops.ln_fwd(x, eng.p(pfx + "ln_1.weight"), eng.p(pfx + "ln_1.bias"), a, None, None, None, eps)
-        eng._fwd_gemm(a, eng.pb(pfx + "attn.c_attn.weight"), qkv, B, 3 * H, H, bias=eng.p(pfx + "attn.c_attn.bias"))
+        ln_gemm(qkv, pfx + "attn.c_attn", H, 3 * H)
         ops.attn_decode_paged(qkv, st.pool[l], st.block_table, st.seq_lens, ctx, B=B, nh=nh, H=H)
-        eng._fwd_gemm(ctx, eng.pb(pfx + "attn.c_proj.weight"), x, B, H, H, bias=eng.p(pfx + "attn.c_proj.bias"),
-                      residual=x)
+        res_gemm(ctx, pfx + "attn.c_proj", H, H)
         if st.kv2 is not None:
-            ops.ln_fwd(x, eng.p(pfx + "ln_cross_attn.weight"), eng.p(pfx + "ln_cross_attn.bias"), a, None, None,
-                       None, eps)
-            eng._fwd_gemm(a, eng.pb(pfx + "crossattention.q_attn.weight"), q2, B, H, H,
-                          bias=eng.p(pfx + "crossattention.q_attn.bias"))
+            ln_gemm(q2, pfx + "crossattention.q_attn", H, H)
             ops.attn_decode_contig(q2, st.kv2[l], ctx, B=B, nh=nh, Tk=st.Tc, k_col0=0, v_col0=H)
-            eng._fwd_gemm(ctx, eng.pb(pfx + "crossattention.c_proj.weight"), x, B, H, H,
-                          bias=eng.p(pfx + "crossattention.c_proj.bias"), residual=x)
-        ops.ln_fwd(x, eng.p(pfx + "ln_2.weight"), eng.p(pfx + "ln_2.bias"), a, None, None, None, eps)
-        eng._fwd_gemm(a, eng.pb(pfx + "mlp.c_fc.weight"), g, B, I, H, bias=eng.p(pfx + "mlp.c_fc.bias"),
-                      epilogue=L.EPI_GELU)
-        eng._fwd_gemm(g, eng.pb(pfx + "mlp.c_proj.weight"), x, B, H, I, bias=eng.p(pfx + "mlp.c_proj.bias"),
-                      residual=x)
+            res_gemm(ctx, pfx + "crossattention.c_proj", H, H)
+        ln_gemm(g, pfx + "mlp.c_fc", H, I, gelu=True)
+        res_gemm(g, pfx + "mlp.c_proj", I, H)
+    # LM head (77 MB of weights, N = 50260): the 128x256-tile tcgen05 kernel streams it in 21.8 us, the
+    # slab kernel (3142 slabs, cross-warp reduction per slab) needs 40 us - measured, profiles/r1_decode.md
     _head_on_rows(eng, x, None, st.logits)
     ops.sample(st.logits, V=eng.V, step=st.step, out_ids=st.out_ids, next_ids=st.next_ids, finished=st.finished,
-               seq_lens=st.seq_lens, **sample_kw)
-    ops.int_add(st.step, 1)
+               seq_lens=st.seq_lens, advance_step=True, **sample_kw)
 
 
 @torch.no_grad()
@@ -125,6 +158,7 @@ def generate(model, input_ids, token_type_ids=None, max_new_tokens=64, do_sample
         raise ValueError("prompt + max_new_tokens = %d exceeds n_positions = %d" % (max_ctx, eng.n_pos))
     with torch.cuda.device(dev):
         st = GenState(eng, B, max_ctx, Tc, max_new_tokens)
+        st.packed = packed_weights(eng)
         if sp2_id is not None:
             st.tt = torch.full((B, 1), int(sp2_id), dtype=torch.int64, device=dev)
         k = int(top_k) if do_sample else 0

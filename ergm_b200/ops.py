@@ -260,16 +260,34 @@ def attn_decode_contig(q, kv, out, *, B, nh, Tk, k_col0, v_col0, kv_lens=None, q
           _p(kv_lens), out.data_ptr(), out.stride(0), B, nh, Tk, 64)
 
 
+def dec_pack_weight(w_f32, K, N, w_is_nk=False, gamma=None, beta=None, bias=None):
+    """Packs an fp32 weight (logical [K, N]) into the bf16 decode slab layout, folding a preceding
+    LayerNorm's gamma / beta in (see header).  Returns (packed, folded_bias or None)."""
+    assert w_f32.dtype == torch.float32
+    packed = torch.empty((N + 15) // 16 * 16 * K, dtype=torch.bfloat16, device=w_f32.device)
+    bias_out = torch.empty(N, dtype=torch.float32, device=w_f32.device) if (beta is not None or bias is not None) else None
+    _call("ergm_dec_pack_weight", w_f32.data_ptr(), w_f32.stride(0), K, N, int(w_is_nk), _p(gamma), _p(beta), _p(bias),
+          packed.data_ptr(), _p(bias_out))
+    return packed, bias_out
+
+
+def dec_gemm(out, w_packed, *, M, K, N, x=None, a=None, eps=1e-5, bias=None, out_mode=0, gelu=False):
+    """out[M,N] = epi(norm(x) @ Wp) or epi(a @ Wp); out_mode 0 bf16 store / 1 fp32 store / 2 fp32 += (see header)."""
+    src = x if x is not None else a
+    _call("ergm_dec_gemm", _p(x), _p(a), src.stride(0), float(eps), w_packed.data_ptr(), K, N,
+          _p(bias), out.data_ptr(), out.stride(0), out_mode, int(gelu), M)
+
+
 def kv_to_pages(kv, pool, block_table, lens, *, B, T, nh, k_col0, v_col0):
     _call("ergm_kv_to_pages", kv.data_ptr(), kv.stride(0), k_col0, v_col0, pool.data_ptr(), block_table.data_ptr(),
           _p(lens), block_table.shape[1], B, T, nh)
 
 
 def sample(logits, *, V, top_k=0, temperature=1.0, seed=0, step=None, out_ids=None, next_ids=None, finished=None,
-           seq_lens=None, eos_id=-1):
+           seq_lens=None, eos_id=-1, advance_step=False):
     B = logits.shape[0]
     _call("ergm_sample", logits.data_ptr(), logits.stride(0), B, V, top_k, float(temperature), seed, _p(step),
-          _p(out_ids), out_ids.stride(0) if out_ids is not None else 0, _p(next_ids), _p(finished), _p(seq_lens),
+          int(advance_step), _p(out_ids), out_ids.stride(0) if out_ids is not None else 0, _p(next_ids), _p(finished), _p(seq_lens),
           eos_id)
 
 

@@ -207,6 +207,26 @@ int ergm_attn_fwd_f32(const float* q, int64_t ld_q, int q_col0, const float* k, 
                       const int* kv_lens, int B, int nh, int Tq, int Tk, int head_dim, int causal,
                       int causal_off, void* stream);
 
+/* Decode-step GEMMs (M = batch <= 64 rows, one new token per sequence): every      */
+/* Conv1D / Linear of the block (model.py:218-222,244,263,265) and the tied LM head  */
+/* (model.py:698) is weight-streaming bound at this M.  ergm_dec_pack_weight re-packs */
+/* an fp32 weight (logical [K, N]: stored [K, ld] row-major as Conv1D does, or, with  */
+/* w_is_nk = 1, [N, ld] as nn.Linear / wte do) into bf16 16-column slabs in mma       */
+/* B-fragment order: packed holds ceil(N/16)*16*K bf16, K % 16 == 0.  When the GEMM   */
+/* consumes a LayerNorm output (model.py:298,318,332,578) the affine parameters are   */
+/* folded in here: packed = bf16(diag(gamma) W), bias_out = bias_in + beta @ W        */
+/* (gamma / beta / bias_in nullable; bias_out [N] required when beta or bias_in).     */
+int ergm_dec_pack_weight(const float* w_f32, int64_t ld, int K, int N, int w_is_nk, const float* gamma,
+                         const float* beta, const float* bias_in, void* packed, float* bias_out,
+                         void* stream);
+/* out[M, N] = epi(A @ Wp):  A = (x - mean) * rstd per row of x_f32[M, lda] computed  */
+/* in the prologue (x_f32 != NULL; gamma / beta live in Wp / bias), or the bf16       */
+/* matrix a_bf16[M, lda].  out_mode 0: bf16 store (+bias, +gelu_new if gelu);         */
+/* 1: fp32 store (+bias); 2: fp32 "+=" into out (residual stream, model.py:309,329,   */
+/* 334; bias added once; K split across CTAs, fp32 reductions; a_bf16 only).          */
+int ergm_dec_gemm(const float* x_f32, const void* a_bf16, int64_t lda, float eps, const void* w_packed,
+                  int K, int N, const float* bias, void* out, int64_t ldo, int out_mode, int gelu,
+                  int M, void* stream);
 /* ------------------------------------------------------------------------ */
 /* Decode: paged KV cache + one-query attention + on-device sampling.  Replaces
  * the torch.cat cache growth of model.py:228-236 and the per-token sampling /
@@ -230,9 +250,11 @@ int ergm_kv_to_pages(const void* kv, int64_t ld, int k_col0, int v_col0, void* p
  * on ties), else top-k / temperature sampling (Philox(seed, *step_ptr)).
  * Writes out_ids[b, *step_ptr], next_ids[b]; finished rows emit eos_id;
  * seq_lens[b] += 1.                                                          */
-int ergm_sample(const float* logits, int64_t ld, int B, int V, int top_k, float temperature,
-                uint64_t seed, const int* step_ptr, int64_t* out_ids, int64_t out_ld,
-                int64_t* next_ids, int* finished, int* seq_lens, int64_t eos_id, void* stream);
+int ergm_sample(const float* logits, int64_t ld, int B, int V, int top_k,
+                float temperature, uint64_t seed, int* step_ptr,
+                int advance_step /* 1: *step_ptr += 1 once every row has been sampled */,
+                int64_t* out_ids, int64_t out_ld, int64_t* next_ids, int* finished, int* seq_lens,
+                int64_t eos_id, void* stream);
 int ergm_int_add(int* dev_ptr, int inc, void* stream);
 
 /* ------------------------------------------------------------------------ */

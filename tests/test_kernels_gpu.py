@@ -401,3 +401,49 @@ def test_mm_pool_fwd(cuda_device, B, T, D):
     if T >= 4:  # strided view: every second frame
         ops.mm_pool_fwd(seq[:, ::2], p32, None)
         assert (p32.double() - seq[:, ::2].double().mean(1)).abs().max().item() < 2e-6
+
+
+@pytest.mark.parametrize("M,K,N,mode", [
+    (64, 768, 2304, "ln_bf16"), (37, 768, 3072, "ln_gelu"), (64, 1024, 1000, "ln_f32_nk"), (1, 128, 48, "ln_bf16"),
+    (64, 768, 50260, "ln_f32_nk"), (64, 768, 768, "red"), (50, 3072, 768, "red"), (64, 128, 128, "red"),
+    (64, 4096, 1024, "red"), (3, 320, 40, "red"), (64, 512, 96, "ln_bf16"), (17, 256, 520, "ln_f32_nk")])
+def test_dec_gemm(cuda_device, M, K, N, mode):
+    """Decode weight-streaming GEMM (ergm_dec_pack_weight + ergm_dec_gemm) against fp32 torch:
+    LayerNorm prologue with gamma / beta folded into the packed weight (model.py:298), Conv1D and
+    tied-LM-head weight layouts (model.py:222,698), bias / gelu_new / residual '+=' epilogues
+    (model.py:263-266,309)."""
+    from ergm_b200 import ops
+    g = torch.Generator().manual_seed(M * 7 + K + N)
+    bias = (0.1 * torch.randn(N, generator=g)).cuda()
+    nk = mode.endswith("_nk")
+    w = (0.05 * torch.randn((N, K) if nk else (K, N), generator=g)).cuda()
+    wl = w.t() if nk else w  # logical [K, N]
+    if mode.startswith("ln"):
+        x = (torch.randn(M, K, generator=g) * 2 + 0.5).cuda()
+        gamma = (1 + 0.1 * torch.randn(K, generator=g)).cuda()
+        beta = (0.1 * torch.randn(K, generator=g)).cuda()
+        packed, fb = ops.dec_pack_weight(w, K, N, w_is_nk=nk, gamma=gamma, beta=beta, bias=bias)
+        assert torch.allclose(fb, bias + beta @ wl, atol=1e-4, rtol=1e-4)
+        want = F.layer_norm(x, (K,), gamma, beta, 1e-5) @ wl + bias
+        if mode == "ln_gelu":
+            want = 0.5 * want * (1 + torch.tanh(math.sqrt(2 / math.pi) * (want + 0.044715 * want ** 3)))
+        f32 = mode.startswith("ln_f32")
+        ld = (N + 63) // 64 * 64
+        out = torch.full((M, ld), 7.0, dtype=torch.float32 if f32 else torch.bfloat16, device="cuda")
+        ops.dec_gemm(out, packed, M=M, K=K, N=N, x=x, eps=1e-5, bias=fb, out_mode=1 if f32 else 0,
+                     gelu=mode == "ln_gelu")
+        got = out[:, :N].float()
+        assert (out[:, N:].float() == 7.0).all()  # padding columns untouched
+        tol = 6e-3 if f32 else 1e-2   # bf16 operands (2^-9 relative each) against exact fp32
+    else:
+        packed, fb = ops.dec_pack_weight(w, K, N, bias=bias)
+        a_b = torch.randn(M, K, generator=g).cuda().to(torch.bfloat16)
+        res = torch.randn(M, N, generator=g).cuda()
+        out = res.clone()
+        ops.dec_gemm(out, packed, M=M, K=K, N=N, a=a_b, bias=fb, out_mode=2)
+        want = res + a_b.float() @ wl.to(torch.bfloat16).float() + bias
+        got = out
+        tol = 2e-3
+    err = ((got - want).norm() / want.norm()).item()
+    assert err < tol, err
+    assert (got - want).abs().max().item() < 20 * tol * want.abs().max().item()
