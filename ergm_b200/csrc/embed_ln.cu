@@ -236,109 +236,150 @@ struct LnBwdParams {
   int do_drop;
 };
 
-// Thread t owns float4 column t of every row; a CTA walks a contiguous slab of rows, RB rows at a
-// time (RB x 3 independent 16-byte loads in flight per thread), so the three per-column sums
-// (dgamma, dbeta, dbias_next) live in 12 registers instead of 72 and several CTAs fit per SM
-// (the first version, one warp per row, was register-bound to 8 warps / SM: 2.3 TB/s).
-constexpr int LN_RB = 4;
+// HBM-bound (dy + x + dres read, dx fp32 + dx bf16 written: 16 B / element at fp32 dy).  v1 (one warp
+// per row, demand loads) was register-bound to 8 warps / SM: 2.3 TB/s; v2 (thread-per-column, a block
+// barrier per 4 rows) 2.1 TB/s: both leave the memory pipe idle while they reduce.  v3: a producer warp
+// streams tiles of 8 consecutive rows (three contiguous cp.async.bulk copies per tile: rows are
+// contiguous) through a 2-3 stage shared-memory ring, so loads are in flight no matter what the 8
+// consumer warps are doing; a consumer warp owns one row of the tile (warp-shuffle statistics, no block
+// barrier in the loop) and keeps its share of the three column sums in registers.
+constexpr int LNB_ROWS = 8;            // rows per tile = consumer warps
+constexpr int LNB_THREADS = (LNB_ROWS + 1) * 32;
 
-template <int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) ln_bwd_kernel(const LnBwdParams p_in, int H, int rows_per_cta) {
-  __shared__ float red[2][32][2 * LN_RB];
+ERGM_DEVINL void lnb_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int NV>
+__global__ void __launch_bounds__(LNB_THREADS, 1) ln_bwd_kernel(const LnBwdParams p_in, int stages) {
+  constexpr int H = NV * 128;
+  extern __shared__ __align__(128) unsigned char lnb_smem[];
   LnBwdParams p = p_in;
   p.drop = p_in.drop.resolved();
-  const int c = threadIdx.x;  // float4 column; blockDim.x == H / 4
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nwarps = (blockDim.x + 31) >> 5;
-  const float invH = 1.f / (float)H;
-  const float keep_scale = p.do_drop ? p.drop.keep_scale() : 1.f;
-  const float4 gm = __ldg(reinterpret_cast<const float4*>(p.gamma) + c);
-  float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag, an = ag;
-  const int r0 = blockIdx.x * rows_per_cta;
-  const int r1 = min(r0 + rows_per_cta, p.rows);
-  int buf = 0;
-  for (int rb = r0; rb < r1; rb += LN_RB, buf ^= 1) {
-    float4 dy[LN_RB], xh[LN_RB], rs[LN_RB];
-    float rstd[LN_RB];
-    float part[2 * LN_RB];
+  const uint32_t dy_row = (uint32_t)H * (p.dy_f32 ? 4u : 2u), f_row = (uint32_t)H * 4u;
+  const uint32_t dy_bytes = LNB_ROWS * dy_row, f_bytes = LNB_ROWS * f_row;
+  const uint32_t stage_bytes = dy_bytes + f_bytes + (p.dres_in ? f_bytes : 0u);
+  const uint32_t bars = smem_u32(lnb_smem);            // full[s] at 8s, empty[s] at 64 + 8s
+  unsigned char* ring = lnb_smem + 128;
+  const int n_tiles = (p.rows + LNB_ROWS - 1) / LNB_ROWS;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(bars + 8 * s, 1); mbar_init(bars + 64 + 8 * s, LNB_ROWS); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  float4 ag[NV], ab[NV], an[NV];
 #pragma unroll
-    for (int i = 0; i < LN_RB; ++i) {
-      const int row = rb + i;
-      if (row < r1) {
-        const int64_t off = (int64_t)row * H;
-        if (p.dy_f32) {
-          dy[i] = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.dy) + off)[c];
-        } else {
-          const uint2 u = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.dy) + off)[c];
-          const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
-          dy[i] = make_float4(a.x, a.y, b.x, b.y);
-        }
-        xh[i] = reinterpret_cast<const float4*>(p.x + off)[c];
-        rs[i] = p.dres_in ? reinterpret_cast<const float4*>(p.dres_in + off)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
-      } else {
-        dy[i] = xh[i] = rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < NV; ++i) ag[i] = ab[i] = an[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (warp == LNB_ROWS) {
+    // ===================== producer =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int s = it % stages;
+        if (it >= stages) mbar_wait(bars + 64 + 8 * s, (uint32_t)((it / stages - 1) & 1));
+        const int row0 = tile * LNB_ROWS;
+        const uint32_t nr = (uint32_t)min(LNB_ROWS, p.rows - row0);
+        const uint32_t dst = smem_u32(ring + (size_t)s * stage_bytes);
+        mbar_expect_tx(bars + 8 * s, nr * (dy_row + f_row + (p.dres_in ? f_row : 0u)));
+        lnb_bulk_g2s(dst, reinterpret_cast<const unsigned char*>(p.dy) + (size_t)row0 * dy_row, nr * dy_row, bars + 8 * s);
+        lnb_bulk_g2s(dst + dy_bytes, p.x + (size_t)row0 * H, nr * f_row, bars + 8 * s);
+        if (p.dres_in) lnb_bulk_g2s(dst + dy_bytes + f_bytes, p.dres_in + (size_t)row0 * H, nr * f_row, bars + 8 * s);
       }
     }
+  } else {
+    // ===================== consumers: warp w owns row w of every tile =====================
+    const float keep_scale = p.do_drop ? p.drop.keep_scale() : 1.f;
+    float4 gm[NV];
 #pragma unroll
-    for (int i = 0; i < LN_RB; ++i) {
-      const int row = min(rb + i, r1 - 1);
-      const float mean = __ldg(p.mean + row);
-      rstd[i] = __ldg(p.rstd + row);
-      xh[i].x = (xh[i].x - mean) * rstd[i]; xh[i].y = (xh[i].y - mean) * rstd[i];
-      xh[i].z = (xh[i].z - mean) * rstd[i]; xh[i].w = (xh[i].w - mean) * rstd[i];
-      const float gx = dy[i].x * gm.x, gy = dy[i].y * gm.y, gz = dy[i].z * gm.z, gw = dy[i].w * gm.w;
-      part[2 * i] = (gx + gy) + (gz + gw);
-      part[2 * i + 1] = (gx * xh[i].x + gy * xh[i].y) + (gz * xh[i].z + gw * xh[i].w);
-    }
+    for (int i = 0; i < NV; ++i) gm[i] = __ldg(reinterpret_cast<const float4*>(p.gamma) + lane + 32 * i);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int s = it % stages;
+      const int row = tile * LNB_ROWS + warp;
+      const bool row_ok = row < p.rows;
+      const float mean = row_ok ? __ldg(p.mean + row) : 0.f, rstd = row_ok ? __ldg(p.rstd + row) : 0.f;
+      mbar_wait(bars + 8 * s, (uint32_t)((it / stages) & 1));
+      const unsigned char* st = ring + (size_t)s * stage_bytes;
+      float4 dy[NV], xh[NV], rs[NV];
+      if (row_ok) {
 #pragma unroll
-    for (int k = 0; k < 2 * LN_RB; ++k) part[k] = warp_sum(part[k]);
-    if (lane == 0) {
-#pragma unroll
-      for (int k = 0; k < 2 * LN_RB; ++k) red[buf][warp][k] = part[k];
-    }
-    __syncthreads();  // double-buffered `red`: one barrier per row batch
-#pragma unroll
-    for (int k = 0; k < 2 * LN_RB; ++k) {
-      float s = 0.f;
-      for (int w = 0; w < nwarps; ++w) s += red[buf][w][k];
-      part[k] = s * invH;
-    }
-#pragma unroll
-    for (int i = 0; i < LN_RB; ++i) {
-      const int row = rb + i;
-      if (row >= r1) break;
-      const float c1 = part[2 * i], c2 = part[2 * i + 1];
-      float4 dx;
-      dx.x = rstd[i] * (dy[i].x * gm.x - c1 - xh[i].x * c2) + rs[i].x;
-      dx.y = rstd[i] * (dy[i].y * gm.y - c1 - xh[i].y * c2) + rs[i].y;
-      dx.z = rstd[i] * (dy[i].z * gm.z - c1 - xh[i].z * c2) + rs[i].z;
-      dx.w = rstd[i] * (dy[i].w * gm.w - c1 - xh[i].w * c2) + rs[i].w;
-      ag.x += dy[i].x * xh[i].x; ag.y += dy[i].y * xh[i].y; ag.z += dy[i].z * xh[i].z; ag.w += dy[i].w * xh[i].w;
-      ab.x += dy[i].x; ab.y += dy[i].y; ab.z += dy[i].z; ab.w += dy[i].w;
-      const int64_t off = (int64_t)row * H;
-      if (p.dx_out) reinterpret_cast<float4*>(p.dx_out + off)[c] = dx;
-      if (p.dx_bf16) {
-        if (p.do_drop) {
-          const uint32_t k = p.drop.keep4((uint32_t)row, (uint32_t)c);
-          dx.x = (k & 1u) ? dx.x * keep_scale : 0.f; dx.y = (k & 2u) ? dx.y * keep_scale : 0.f;
-          dx.z = (k & 4u) ? dx.z * keep_scale : 0.f; dx.w = (k & 8u) ? dx.w * keep_scale : 0.f;
+        for (int i = 0; i < NV; ++i) {
+          if (p.dy_f32) {
+            dy[i] = reinterpret_cast<const float4*>(st + (size_t)warp * dy_row)[lane + 32 * i];
+          } else {
+            const uint2 u = reinterpret_cast<const uint2*>(st + (size_t)warp * dy_row)[lane + 32 * i];
+            const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+            dy[i] = make_float4(a.x, a.y, b.x, b.y);
+          }
+          xh[i] = reinterpret_cast<const float4*>(st + dy_bytes + (size_t)warp * f_row)[lane + 32 * i];
+          rs[i] = p.dres_in ? reinterpret_cast<const float4*>(st + dy_bytes + f_bytes + (size_t)warp * f_row)[lane + 32 * i]
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        const uint2 u = make_uint2(pack_bf16x2(dx.x, dx.y), pack_bf16x2(dx.z, dx.w));
-        reinterpret_cast<uint2*>(p.dx_bf16 + off)[c] = u;
-        if (p.dbias_next) {
-          const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
-          an.x += a.x; an.y += a.y; an.z += b.x; an.w += b.y;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + 64 + 8 * s);  // this warp's row is in registers: slot may be refilled
+      if (!row_ok) continue;
+      float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        xh[i].x = (xh[i].x - mean) * rstd; xh[i].y = (xh[i].y - mean) * rstd;
+        xh[i].z = (xh[i].z - mean) * rstd; xh[i].w = (xh[i].w - mean) * rstd;
+        const float gx = dy[i].x * gm[i].x, gy = dy[i].y * gm[i].y, gz = dy[i].z * gm[i].z, gw = dy[i].w * gm[i].w;
+        c1 += (gx + gy) + (gz + gw);
+        c2 += (gx * xh[i].x + gy * xh[i].y) + (gz * xh[i].z + gw * xh[i].w);
+      }
+      c1 = warp_sum(c1) * (1.f / H);
+      c2 = warp_sum(c2) * (1.f / H);
+      const int64_t off = (int64_t)row * H;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        float4 dx;
+        dx.x = rstd * (dy[i].x * gm[i].x - c1 - xh[i].x * c2) + rs[i].x;
+        dx.y = rstd * (dy[i].y * gm[i].y - c1 - xh[i].y * c2) + rs[i].y;
+        dx.z = rstd * (dy[i].z * gm[i].z - c1 - xh[i].z * c2) + rs[i].z;
+        dx.w = rstd * (dy[i].w * gm[i].w - c1 - xh[i].w * c2) + rs[i].w;
+        ag[i].x += dy[i].x * xh[i].x; ag[i].y += dy[i].y * xh[i].y; ag[i].z += dy[i].z * xh[i].z; ag[i].w += dy[i].w * xh[i].w;
+        ab[i].x += dy[i].x; ab[i].y += dy[i].y; ab[i].z += dy[i].z; ab[i].w += dy[i].w;
+        if (p.dx_out) reinterpret_cast<float4*>(p.dx_out + off)[c] = dx;
+        if (p.dx_bf16) {
+          if (p.do_drop) {
+            const uint32_t k = p.drop.keep4((uint32_t)row, (uint32_t)c);
+            dx.x = (k & 1u) ? dx.x * keep_scale : 0.f; dx.y = (k & 2u) ? dx.y * keep_scale : 0.f;
+            dx.z = (k & 4u) ? dx.z * keep_scale : 0.f; dx.w = (k & 8u) ? dx.w * keep_scale : 0.f;
+          }
+          const uint2 u = make_uint2(pack_bf16x2(dx.x, dx.y), pack_bf16x2(dx.z, dx.w));
+          reinterpret_cast<uint2*>(p.dx_bf16 + off)[c] = u;
+          if (p.dbias_next) {
+            const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+            an[i].x += a.x; an[i].y += a.y; an[i].z += b.x; an[i].w += b.y;
+          }
         }
       }
     }
   }
-  float* gp = p.dgamma + 4 * c;
-  atomicAdd(gp, ag.x); atomicAdd(gp + 1, ag.y); atomicAdd(gp + 2, ag.z); atomicAdd(gp + 3, ag.w);
-  float* bp = p.dbeta + 4 * c;
-  atomicAdd(bp, ab.x); atomicAdd(bp + 1, ab.y); atomicAdd(bp + 2, ab.z); atomicAdd(bp + 3, ab.w);
-  if (p.dbias_next && p.dx_bf16) {
-    float* np_ = p.dbias_next + 4 * c;
-    atomicAdd(np_, an.x); atomicAdd(np_ + 1, an.y); atomicAdd(np_ + 2, an.z); atomicAdd(np_ + 3, an.w);
+  // ---- column sums: 8 warps -> smem (the ring is drained) -> one atomic per column per CTA ----
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(ring);  // [3][LNB_ROWS][H]
+  if (warp < LNB_ROWS) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      reinterpret_cast<float4*>(red + ((size_t)0 * LNB_ROWS + warp) * H)[lane + 32 * i] = ag[i];
+      reinterpret_cast<float4*>(red + ((size_t)1 * LNB_ROWS + warp) * H)[lane + 32 * i] = ab[i];
+      reinterpret_cast<float4*>(red + ((size_t)2 * LNB_ROWS + warp) * H)[lane + 32 * i] = an[i];
+    }
+  }
+  __syncthreads();
+  const bool has_n = p.dbias_next && p.dx_bf16;
+  for (int idx = threadIdx.x; idx < 3 * H; idx += blockDim.x) {
+    const int q = idx / H, c = idx - q * H;
+    if (q == 2 && !has_n) break;
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < LNB_ROWS; ++w) sum += red[((size_t)q * LNB_ROWS + w) * H + c];
+    atomicAdd((q == 0 ? p.dgamma : q == 1 ? p.dbeta : p.dbias_next) + c, sum);
   }
 }
 
@@ -593,17 +634,35 @@ extern "C" int ergm_ln_bwd(const void* dy, int dy_is_f32, const float* x, const 
   LnBwdParams p{dy, x, mean, rstd, gamma, dres_in, dx_out, reinterpret_cast<__nv_bfloat16*>(dx_bf16),
                 dgamma, dbeta, dbias_next, rows, dy_is_f32,
                 make_site(seed, offset, dropout_p, (uint32_t)H), dropout_p > 0.f};
-  if (H / 4 > 512) return ERGM_ERR_UNSUPPORTED;
-  int grid = (rows + 4 * LN_RB - 1) / (4 * LN_RB);  // at least 4 row batches per CTA
-  if (grid > 4 * num_sms()) grid = 4 * num_sms();
-  if (grid < 1) grid = 1;
-  const int rpc = (rows + grid - 1) / grid;
-  grid = (rows + rpc - 1) / rpc;
-  if (H / 4 <= 256)
-    ln_bwd_kernel<256, 3><<<grid, H / 4, 0, (cudaStream_t)stream>>>(p, H, rpc);
-  else
-    ln_bwd_kernel<512, 1><<<grid, H / 4, 0, (cudaStream_t)stream>>>(p, H, rpc);
-  return (int)cudaGetLastError();
+  if (reinterpret_cast<uintptr_t>(dy) & 15 || reinterpret_cast<uintptr_t>(x) & 15 ||
+      (dres_in && (reinterpret_cast<uintptr_t>(dres_in) & 15)))
+    return ERGM_ERR_ARG;
+  const int stage_bytes = LNB_ROWS * H * ((dy_is_f32 ? 4 : 2) + 4 + (dres_in ? 4 : 0));
+  int stages = (232448 - 128) / stage_bytes;
+  if (stages > 4) stages = 4;
+  const int n_tiles = (rows + LNB_ROWS - 1) / LNB_ROWS;
+  int grid = n_tiles < num_sms() ? n_tiles : num_sms();
+  const int per_cta = (n_tiles + grid - 1) / grid;
+  if (stages > per_cta) stages = per_cta;
+  if (stages < 1) return ERGM_ERR_UNSUPPORTED;
+  int smem = 128 + stages * stage_bytes;
+  const int red_bytes = 128 + 3 * LNB_ROWS * H * 4;  // column-sum reduction reuses the ring
+  if (smem < red_bytes) smem = red_bytes;
+  if (smem > 232448) return ERGM_ERR_UNSUPPORTED;
+  auto launch = [&](auto kern) -> int {
+    ERGM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    kern<<<grid, LNB_THREADS, smem, (cudaStream_t)stream>>>(p, stages);
+    return (int)cudaGetLastError();
+  };
+  switch (H / 128) {
+    case 1: return launch(ln_bwd_kernel<1>);
+    case 2: return launch(ln_bwd_kernel<2>);
+    case 3: return launch(ln_bwd_kernel<3>);
+    case 4: return launch(ln_bwd_kernel<4>);
+    case 6: return launch(ln_bwd_kernel<6>);
+    case 8: return launch(ln_bwd_kernel<8>);
+  }
+  return ERGM_ERR_UNSUPPORTED;
 }
 
 extern "C" int ergm_colsum_bf16(const void* src, int64_t ld, int rows, int N, float* out,

@@ -17,6 +17,7 @@
 #include "../../include/ergm_b200.h"
 #include "common.cuh"
 #include "dropout.cuh"
+#include <cstdlib>
 
 namespace ergm {
 
@@ -227,7 +228,129 @@ ERGM_DEVINL void epilogue_chunk(const GemmParams& p, const EpiFlags& ep, int row
   }
 }
 
-template <int BN, int EC>
+
+// ------------------------------------------------------------------------------------------
+// Lean epilogues for the hot configurations.  ncu of the generic epilogue above (profiles/r1_gemm_epilogue.md):
+// ~670 warp instructions per 32x32 chunk, 60 of them branches and ~150 index / predicate arithmetic for
+// flags that are uniform per launch, and one exposed DRAM round trip per chunk for the residual operand;
+// with two epilogue warps per scheduler that made a 128x256 tile's epilogue take 8 us against a 4.5 us
+// mainloop.  The fast path is compiled per mode (no run-time flag tests), runs only on interior tiles
+// (no bounds tests; edge tiles take the generic path), strength-reduces the addressing and prefetches
+// the residual operand of chunk c+1 (and of the next tile's first chunk) while chunk c is processed.
+// ------------------------------------------------------------------------------------------
+enum { FM_NONE = 0, FM_BF16 = 1, FM_BF16_BIAS = 2, FM_F32 = 3, FM_F32_RES = 4, FM_GELU = 5, FM_ATOMIC = 6 };
+
+template <int FM>
+ERGM_DEVINL void fast_res_prefetch(const GemmParams& p, int row0, int col0, int lane, float4 (&res)[8]) {
+  if constexpr (FM == FM_F32_RES) {
+    const float* rp = p.residual + (int64_t)(row0 + (lane >> 3)) * p.ldr + col0 + 4 * (lane & 7);
+    const int64_t step = 4 * p.ldr;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) res[it] = *reinterpret_cast<const float4*>(rp + it * step);
+  }
+}
+
+template <int FM>
+ERGM_DEVINL void epilogue_chunk_fast(const GemmParams& p, const EpiFlags& ep, int row0, int col0,
+                                     const float (&v)[32], const float4 (&res)[8], uint32_t stage_smem, int lane) {
+  const int c4 = lane & 7, rsub = lane >> 3;
+  const int col = col0 + 4 * c4;
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if constexpr (FM == FM_BF16_BIAS || FM == FM_GELU) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+  if constexpr (FM == FM_F32_RES) {
+    if (ep.has_bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+  }
+  __syncwarp();  // previous chunk's reads of the staging tile are done
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint32_t addr = stage_smem + lane * 128 + ((uint32_t)(c ^ (lane & 7)) << 4);
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[4 * c]), "f"(v[4 * c + 1]),
+                 "f"(v[4 * c + 2]), "f"(v[4 * c + 3])
+                 : "memory");
+  }
+  __syncwarp();
+  const int64_t off0 = (int64_t)(row0 + rsub) * p.ldd + col;
+  const int64_t dstep = 4 * p.ldd;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = 4 * it + rsub;
+    float4 x;
+    {
+      const uint32_t addr = stage_smem + r * 128 + ((uint32_t)(c4 ^ (r & 7)) << 4);
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(addr));
+    }
+    const int64_t off = off0 + it * dstep;
+    if constexpr (FM == FM_BF16_BIAS || FM == FM_GELU || FM == FM_F32_RES) {
+      x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+    }
+    if constexpr (FM == FM_GELU) {
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.preact) + off) =
+          make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+      x.x = gelu_new<false>(x.x); x.y = gelu_new<false>(x.y); x.z = gelu_new<false>(x.z); x.w = gelu_new<false>(x.w);
+    }
+    if constexpr (FM == FM_F32_RES) {
+      if (ep.do_drop) {
+        const uint32_t keep = ep.site.keep4((uint32_t)(row0 + r), (uint32_t)col >> 2);
+        x.x = (keep & 1u) ? x.x * ep.keep_scale : 0.f;
+        x.y = (keep & 2u) ? x.y * ep.keep_scale : 0.f;
+        x.z = (keep & 4u) ? x.z * ep.keep_scale : 0.f;
+        x.w = (keep & 8u) ? x.w * ep.keep_scale : 0.f;
+      }
+      x.x += res[it].x; x.y += res[it].y; x.z += res[it].z; x.w += res[it].w;
+    }
+    if constexpr (FM == FM_F32 || FM == FM_F32_RES) {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.d) + off) = x;
+    } else if constexpr (FM == FM_ATOMIC) {
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(reinterpret_cast<float*>(p.d) + off), "f"(x.x),
+                   "f"(x.y), "f"(x.z), "f"(x.w)
+                   : "memory");
+    } else {
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.d) + off) =
+          make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+    }
+  }
+}
+
+// Epilogue of one warp's share (32 rows x BN/2 columns) of an accumulator tile.  `pre_valid`: res_pre
+// already holds the residual operand of the first chunk (prefetched before the accumulator was ready).
+template <int BN, int EC, int FM>
+ERGM_DEVINL void epilogue_tile(const GemmParams& p, const EpiFlags& ep, uint32_t tmem_tile, int row0, int n0, int half,
+                               bool first_split, uint32_t stage_smem, int lane, float4 (&res_pre)[8], bool fast) {
+  const int c_lo = half * (BN / 2), c_hi = (half + 1) * (BN / 2);
+  if (FM != FM_NONE && fast) {
+#pragma unroll 1
+    for (int c = c_lo; c < c_hi; c += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_tile + c, r);
+      float4 res_cur[8];
+      if constexpr (FM == FM_F32_RES) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) res_cur[it] = res_pre[it];
+        if (c + 32 < c_hi) fast_res_prefetch<FM>(p, row0, n0 + c + 32, lane, res_pre);
+      }
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+      epilogue_chunk_fast<FM>(p, ep, row0, n0 + c, v, res_cur, stage_smem, lane);
+    }
+    return;
+  }
+#pragma unroll 1
+  for (int c = c_lo; c < c_hi; c += 32) {
+    const int col0 = n0 + c;
+    if (col0 >= p.N) break;  // warp-uniform
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(tmem_tile + c, r);
+    tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    epilogue_chunk<EC>(p, ep, row0, col0, first_split, v, stage_smem, lane);
+  }
+}
+
+template <int BN, int EC, int FM>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
                  const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
@@ -356,28 +479,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const uint32_t stage_smem = stage_all + (warp - EPI_WARP0) * 4096;
     int acc = 0;
     uint32_t acc_phase = 0;
+    float4 res_pre[8];
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int split = tile / tiles_mn;
       const int mn = tile - split * tiles_mn;
       const int m0 = (mn % p.m_tiles) * BM;
       const int n0 = (mn / p.m_tiles) * BN;
+      const int row0 = m0 + q * 32;
+      const bool fast = FM != FM_NONE && row0 + 32 <= p.M && n0 + (half + 1) * (BN / 2) <= p.N;
+      if (fast) fast_res_prefetch<FM>(p, row0, n0 + half * (BN / 2), lane, res_pre);  // independent of the MMAs
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < p.M;
-      const bool first_split = (split == 0);
-#pragma unroll 1
-      for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
-        const int col0 = n0 + c;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c, r);
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        epilogue_chunk<EC>(p, ep, m0 + q * 32, col0, first_split, v, stage_smem, lane);
-      }
+      epilogue_tile<BN, EC, FM>(p, ep, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, row0, n0, half, split == 0,
+                                stage_smem, lane, res_pre, fast);
       // hand the accumulator buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -413,7 +527,7 @@ struct Gemm2Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGING + 1024 + 256;
 };
 
-template <int BN, int EC>
+template <int BN, int EC, int FM>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
                   const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
@@ -541,28 +655,19 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const uint32_t stage_smem = stage_all + (warp - EPI_WARP0) * 4096;
     int acc = 0;
     uint32_t acc_phase = 0;
+    float4 res_pre[8];
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
       const int split = tile / tiles_mn;
       const int mn = tile - split * tiles_mn;
       const int m0 = (mn % p.m_tiles) * 256 + (int)rank * 128;
       const int n0 = (mn / p.m_tiles) * BN;
+      const int row0 = m0 + q * 32;
+      const bool fast = FM != FM_NONE && row0 + 32 <= p.M && n0 + (half + 1) * (BN / 2) <= p.N;
+      if (fast) fast_res_prefetch<FM>(p, row0, n0 + half * (BN / 2), lane, res_pre);  // independent of the MMAs
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < p.M;
-      const bool first_split = (split == 0);
-#pragma unroll 1
-      for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
-        const int col0 = n0 + c;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c, r);
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        epilogue_chunk<EC>(p, ep, m0 + q * 32, col0, first_split, v, stage_smem, lane);
-      }
+      epilogue_tile<BN, EC, FM>(p, ep, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, row0, n0, half, split == 0,
+                                stage_smem, lane, res_pre, fast);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_cluster(tempty_bar(acc), 0));
@@ -575,7 +680,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp == 2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int BN, int EC>
+template <int BN, int EC, int FM>
 static int launch_gemm2(const ergm_gemm_args* a, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<BN>;
   CUtensorMap ta, tb;
@@ -608,7 +713,7 @@ static int launch_gemm2(const ergm_gemm_args* a, cudaStream_t stream) {
   p.site = make_site(a->seed, a->offset, a->dropout_p, (uint32_t)a->N);
   static bool attr_set = false;
   if (!attr_set) {
-    ERGM_CUDA_TRY(cudaFuncSetAttribute(gemm2_bf16_kernel<BN, EC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ERGM_CUDA_TRY(cudaFuncSetAttribute(gemm2_bf16_kernel<BN, EC, FM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::SMEM_BYTES));
     attr_set = true;
   }
@@ -627,10 +732,10 @@ static int launch_gemm2(const ergm_gemm_args* a, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return (int)cudaLaunchKernelEx(&cfg, gemm2_bf16_kernel<BN, EC>, ta, tb, p);
+  return (int)cudaLaunchKernelEx(&cfg, gemm2_bf16_kernel<BN, EC, FM>, ta, tb, p);
 }
 
-template <int BN, int EC>
+template <int BN, int EC, int FM>
 static int launch_gemm(const ergm_gemm_args* a, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   CUtensorMap ta, tb;
@@ -666,13 +771,13 @@ static int launch_gemm(const ergm_gemm_args* a, cudaStream_t stream) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    ERGM_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_kernel<BN, EC>,
+    ERGM_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_kernel<BN, EC, FM>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int total = p.m_tiles * p.n_tiles * p.split_k;
   const int grid = total < num_sms() ? total : num_sms();
-  gemm_bf16_kernel<BN, EC><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  gemm_bf16_kernel<BN, EC, FM><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
   return (int)cudaGetLastError();
 }
 
@@ -723,20 +828,54 @@ extern "C" int ergm_gemm_bf16(const ergm_gemm_args* a, void* stream) {
   else if (a->epilogue & ERGM_EPI_GELU) ec = EC_GELU;
   else if (a->epilogue & ERGM_EPI_GELU_GRAD) ec = EC_GELU_GRAD;
   else if (a->epilogue & ERGM_EPI_PREACT) ec = EC_GELU;
+  // lean per-mode epilogue (interior tiles) for the hot launch configurations
+  int fm = FM_NONE;
+  {
+    const int e = a->epilogue;
+    const bool f32 = a->d_dtype == ERGM_DT_F32;
+    const char* off = getenv("ERGM_GEMM_FAST_EPI");
+    const bool aligned = (reinterpret_cast<uintptr_t>(a->d) & 15) == 0 && a->ldd % (f32 ? 4 : 8) == 0;
+    if (!(off && off[0] == '0') && aligned && bn != 64) {
+      if (!f32 && e == 0) fm = FM_BF16;
+      else if (!f32 && e == ERGM_EPI_BIAS) fm = FM_BF16_BIAS;
+      else if (!f32 && e == (ERGM_EPI_BIAS | ERGM_EPI_GELU | ERGM_EPI_PREACT) && a->preact) fm = FM_GELU;
+      else if (f32 && e == 0) fm = FM_F32;
+      else if (f32 && (e & ERGM_EPI_RESIDUAL) &&
+               (e & ~(ERGM_EPI_BIAS | ERGM_EPI_RESIDUAL | ERGM_EPI_DROPOUT)) == 0) fm = FM_F32_RES;
+      else if (f32 && e == ERGM_EPI_ATOMIC) fm = FM_ATOMIC;
+    }
+  }
 #define ERGM_DISPATCH_EC(FN, BNV)                                   \
+  switch (fm) {                                                     \
+    case FM_BF16: return FN<BNV, EC_LINEAR, FM_BF16>(a, s);         \
+    case FM_BF16_BIAS: return FN<BNV, EC_LINEAR, FM_BF16_BIAS>(a, s); \
+    case FM_F32: return FN<BNV, EC_LINEAR, FM_F32>(a, s);           \
+    case FM_F32_RES: return FN<BNV, EC_LINEAR, FM_F32_RES>(a, s);   \
+    case FM_GELU: return FN<BNV, EC_GELU, FM_GELU>(a, s);           \
+    case FM_ATOMIC: return FN<BNV, EC_LINEAR, FM_ATOMIC>(a, s);     \
+    default: break;                                                 \
+  }                                                                 \
   switch (ec) {                                                     \
-    case EC_LINEAR: return FN<BNV, EC_LINEAR>(a, s);                \
-    case EC_GELU: return FN<BNV, EC_GELU>(a, s);                    \
-    case EC_GELU_GRAD: return FN<BNV, EC_GELU_GRAD>(a, s);          \
-    default: return FN<BNV, EC_EXACT>(a, s);                        \
+    case EC_LINEAR: return FN<BNV, EC_LINEAR, FM_NONE>(a, s);       \
+    case EC_GELU: return FN<BNV, EC_GELU, FM_NONE>(a, s);           \
+    case EC_GELU_GRAD: return FN<BNV, EC_GELU_GRAD, FM_NONE>(a, s); \
+    default: return FN<BNV, EC_EXACT, FM_NONE>(a, s);               \
+  }
+#define ERGM_DISPATCH_EC_SLOW(FN, BNV)                              \
+  switch (ec) {                                                     \
+    case EC_LINEAR: return FN<BNV, EC_LINEAR, FM_NONE>(a, s);       \
+    case EC_GELU: return FN<BNV, EC_GELU, FM_NONE>(a, s);           \
+    case EC_GELU_GRAD: return FN<BNV, EC_GELU_GRAD, FM_NONE>(a, s); \
+    default: return FN<BNV, EC_EXACT, FM_NONE>(a, s);               \
   }
   switch (bn) {
     case 2256: ERGM_DISPATCH_EC(launch_gemm2, 256)
     case 2128: ERGM_DISPATCH_EC(launch_gemm2, 128)
     case 256: ERGM_DISPATCH_EC(launch_gemm, 256)
     case 128: ERGM_DISPATCH_EC(launch_gemm, 128)
-    case 64: ERGM_DISPATCH_EC(launch_gemm, 64)
+    case 64: ERGM_DISPATCH_EC_SLOW(launch_gemm, 64)
     default: return ERGM_ERR_ARG;
   }
+#undef ERGM_DISPATCH_EC_SLOW
 #undef ERGM_DISPATCH_EC
 }
