@@ -12,6 +12,7 @@ struct DropoutSite {
   uint64_t seed, offset;
   float p;
   uint32_t ncol4;  // ceil(ncols / 4)
+  uint32_t key;    // (seed, offset [, step]) pre-mixed once per kernel: see resolved()
   // Optional device-resident step counter added to the seed, so that a CUDA-graph replay
   // (whose kernel arguments are frozen) still draws fresh masks every step.
   const uint64_t* step;
@@ -21,6 +22,7 @@ struct DropoutSite {
     DropoutSite r = *this;
     if (step) r.seed += __ldg(reinterpret_cast<const unsigned long long*>(step));
     r.step = nullptr;
+    r.key = mix_key(r.seed, r.offset);
     return r;
   }
 
@@ -59,16 +61,23 @@ struct DropoutSite {
   // counter keyed by seed/offset, "lowbias32" constants) yields two independent 16-bit uniforms:
   // element (row, col) is kept iff its 16-bit lane >= thr16 = round(p * 65536).
   ERGM_DEVINL uint32_t thr16() const { return (uint32_t)(p * 65536.f + 0.5f); }
-  ERGM_DEVINL uint32_t hash2(uint32_t row, uint32_t col2) const {
-    uint32_t h = (row * ncol4 * 2u + col2) ^ (uint32_t)seed;
-    h ^= h >> 16; h *= 0x7feb352du;
-    h ^= h >> 15; h *= 0x846ca68bu;
-    h ^= h >> 16;
-    h += (uint32_t)offset * 0x9E3779B9u + (uint32_t)(seed >> 32);
+  // key: two avalanche rounds over (seed, offset), computed ONCE per kernel by resolved(); the
+  // per-element work is then a single round on a Weyl-spread counter (8 integer instructions per
+  // two elements - the first version re-mixed seed and offset for every pair: 18).
+  static __host__ __device__ __forceinline__ uint32_t avalanche(uint32_t h) {
     h ^= h >> 16; h *= 0x7feb352du;
     h ^= h >> 15; h *= 0x846ca68bu;
     h ^= h >> 16;
     return h;
+  }
+  static __host__ __device__ __forceinline__ uint32_t mix_key(uint64_t seed, uint64_t offset) {
+    uint32_t k = avalanche((uint32_t)seed ^ 0x9E3779B9u);
+    k = avalanche(k + (uint32_t)(seed >> 32) * 0x85EBCA6Bu);
+    k = avalanche(k ^ ((uint32_t)offset * 0x9E3779B9u + (uint32_t)(offset >> 32)));
+    return k;
+  }
+  ERGM_DEVINL uint32_t hash2(uint32_t row, uint32_t col2) const {
+    return avalanche((row * ncol4 * 2u + col2) * 0x9E3779B1u + key);
   }
   ERGM_DEVINL bool keep_hash(uint32_t row, uint32_t col) const {
     const uint32_t h = hash2(row, col >> 1);
@@ -79,7 +88,8 @@ struct DropoutSite {
 // host side: library-global step pointer (set by ergm_set_rng_step_ptr, see api.cu)
 extern const uint64_t* g_rng_step_ptr;
 inline DropoutSite make_site(uint64_t seed, uint64_t offset, float p, uint32_t ncols) {
-  return DropoutSite{seed, offset, p, (ncols + 3) / 4, p > 0.f ? g_rng_step_ptr : nullptr};
+  return DropoutSite{seed, offset, p, (ncols + 3) / 4, DropoutSite::mix_key(seed, offset),
+                     p > 0.f ? g_rng_step_ptr : nullptr};
 }
 
 }  // namespace ergm

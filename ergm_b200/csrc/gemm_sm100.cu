@@ -807,14 +807,23 @@ extern "C" int ergm_gemm_bf16(const ergm_gemm_args* a, void* stream) {
   if (a->lda % 8 || a->ldb % 8) return ERGM_ERR_ARG;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   int bn = a->block_n;
-  if (bn == 0 && a->M >= 512 && a->N >= 128) {
-    // CTA-pair kernel (cta_group::2): 256-row tiles; pick the N tile that fills the 74 clusters best
-    const long mt2 = (a->M + 255) / 256;
+  if (bn == 0 && a->M >= 512 && a->N >= 256) {
+    // Measured on the model's shapes (profiles/r1_gemm_epilogue.md): the CTA-pair kernel with 256x256 tiles
+    // wins whenever its tiles fill the 74 clusters reasonably or the mainloop is long (K >= 1536: the
+    // wave-quantisation loss is outweighed by the halved B traffic per SM); short-K problems that would
+    // leave a third of the clusters idle (N = 768, K = 768: 96 tiles) run on single-CTA 128x128 / 128x256
+    // tiles; the 256x128 pair tiles never won.
     const int sk = a->split_k < 1 ? 1 : a->split_k;
-    const long t256 = mt2 * ((a->N + 255) / 256) * sk, t128 = mt2 * ((a->N + 127) / 128) * sk;
-    const int nc = num_sms() / 2;
-    auto eff = [&](long tiles) { return (double)tiles / (double)(((tiles + nc - 1) / nc) * nc); };
-    bn = (a->N >= 256 && eff(t256) >= eff(t128) - 0.08) ? 2256 : 2128;
+    const long t2 = (long)((a->M + 255) / 256) * ((a->N + 255) / 256) * sk;
+    const int nc = num_sms() / 2, ns = num_sms();
+    auto eff = [](long tiles, int slots) { return (double)tiles / (double)(((tiles + slots - 1) / slots) * slots); };
+    if (a->K >= 1536 || eff(t2, nc) >= 0.8) {
+      bn = 2256;
+    } else {
+      const long mt = (a->M + BM - 1) / BM;
+      const long t256 = mt * ((a->N + 255) / 256) * sk, t128 = mt * ((a->N + 127) / 128) * sk;
+      bn = eff(t256, ns) >= eff(t128, ns) - 0.05 ? 256 : 128;
+    }
   }
   if (bn == 0) {
     // auto: widest tile that still yields at least ~1 wave of CTAs
