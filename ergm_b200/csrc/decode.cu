@@ -201,6 +201,7 @@ struct SampleParams {
   int64_t ld;
   int V;
   int top_k;             // 0 = greedy arg-max
+  float top_p;           // < 1: nucleus sampling (main.py:253-282)
   float inv_temperature;
   uint64_t seed;
   const int* step_ptr;   // device step counter: output column and RNG subsequence
@@ -405,6 +406,158 @@ __global__ void __launch_bounds__(AMX_THREADS) argmax_kernel(const SampleParams 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Nucleus (top-p) sampling, main.py:258-270, one 1024-thread CTA per row, no host round trip:
+//   probs = softmax(logits); sort descending; remove[i] = cumsum[i-1] > top_p  (the mask is shifted
+//   right by one, :263-265, so the token that crosses top_p is KEPT); renormalise; multinomial.
+// Without a sort: e_i = exp(l_i - max) is cached in shared memory (V * 4 bytes), G(k) = sum of the
+// e_i whose bit pattern exceeds k is non-increasing in k, and the kept set is {i : G(bits(e_i)) <=
+// top_p * Z} = {bits(e_i) >= k_min}: ~30 bisection steps over the float bit patterns, each one pass
+// over shared memory + a block reduction.  Tokens tied at k_min are kept lowest-index first, as many as
+// the shifted rule admits.  The draw walks the kept tokens in INDEX order (deterministic for a given
+// (seed, step, row), independent of any sort order).
+// ------------------------------------------------------------------------------------------
+constexpr int NUC_THREADS = 1024;
+
+ERGM_DEVINL float block_sum_1024(float v, float* s_red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = s_red[threadIdx.x & 31];
+  t = warp_sum(t);
+  return t;
+}
+
+__global__ void __launch_bounds__(NUC_THREADS) nucleus_kernel(const SampleParams p) {
+  extern __shared__ float s_e[];          // [V]
+  __shared__ float s_red[32];
+  __shared__ float s_scan_f[NUC_THREADS / 32];
+  __shared__ int s_scan_i[NUC_THREADS / 32];
+  __shared__ int s_pick;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* row = p.logits + (int64_t)b * p.ld;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int step_now = p.step_ptr ? *p.step_ptr : 0;
+  // softmax numerator in smem
+  float mx = -INFINITY;
+  for (int i = tid; i < p.V; i += NUC_THREADS) mx = fmaxf(mx, row[i]);
+  mx = warp_max(mx);
+  __syncthreads();
+  if (lane == 0) s_red[warp] = mx;
+  __syncthreads();
+  mx = warp_max(s_red[lane]);
+  float z = 0.f;
+  for (int i = tid; i < p.V; i += NUC_THREADS) {
+    const float e = __expf((row[i] - mx) * p.inv_temperature);
+    s_e[i] = e;
+    z += e;
+  }
+  const float Z = block_sum_1024(z, s_red);
+  const float target = p.top_p * Z;
+  // bisection: smallest k in [0, bits(1.0f)] with G(k) <= target
+  uint32_t lo = 0u, hi = 0x3f800000u;
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    float g = 0.f;
+    for (int i = tid; i < p.V; i += NUC_THREADS) {
+      const float e = s_e[i];
+      g += (__float_as_uint(e) > mid) ? e : 0.f;
+    }
+    g = block_sum_1024(g, s_red);
+    if (g <= target) hi = mid; else lo = mid + 1u;
+  }
+  const uint32_t kmin = lo;
+  float mass_gt = 0.f;
+  int cnt_tie = 0;
+  for (int i = tid; i < p.V; i += NUC_THREADS) {
+    const float e = s_e[i];
+    const uint32_t u = __float_as_uint(e);
+    mass_gt += u > kmin ? e : 0.f;
+    cnt_tie += u == kmin ? 1 : 0;
+  }
+  mass_gt = block_sum_1024(mass_gt, s_red);
+  const int n_tie = (int)(block_sum_1024((float)cnt_tie, s_red) + 0.5f);
+  const float pstar = __uint_as_float(kmin);
+  int tie_keep = n_tie;
+  if (pstar > 0.f) tie_keep = min(n_tie, (int)floorf(fmaxf(target - mass_gt, 0.f) / pstar) + 1);
+  const float total = mass_gt + (float)tie_keep * pstar;
+  Philox ph(p.seed, (uint64_t)step_now);
+  const float u = u01(ph((uint64_t)b).x) * total;
+  // index-order walk: thread t owns the contiguous indices [t * npt, (t + 1) * npt)
+  const int npt = (p.V + NUC_THREADS - 1) / NUC_THREADS;
+  const int i0 = min(tid * npt, p.V), i1 = min(i0 + npt, p.V);
+  // (a) exclusive prefix of the tie counts
+  int my_ties = 0;
+  for (int i = i0; i < i1; ++i) my_ties += __float_as_uint(s_e[i]) == kmin ? 1 : 0;
+  int incl = my_ties;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += n;
+  }
+  __syncthreads();
+  if (lane == 31) s_scan_i[warp] = incl;
+  __syncthreads();
+  int wbase = 0;
+  for (int w = 0; w < warp; ++w) wbase += s_scan_i[w];
+  int tie_rank = wbase + incl - my_ties;
+  // (b) kept mass of my chunk, exclusive prefix over threads
+  float my_mass = 0.f;
+  {
+    int r = tie_rank;
+    for (int i = i0; i < i1; ++i) {
+      const float e = s_e[i];
+      const uint32_t k = __float_as_uint(e);
+      if (k > kmin) my_mass += e;
+      else if (k == kmin) { if (r < tie_keep) my_mass += e; ++r; }
+    }
+  }
+  float fincl = my_mass;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float n = __shfl_up_sync(0xffffffffu, fincl, o);
+    if (lane >= o) fincl += n;
+  }
+  if (tid == 0) s_pick = -1;
+  __syncthreads();
+  if (lane == 31) s_scan_f[warp] = fincl;
+  __syncthreads();
+  float fbase = 0.f;
+  for (int w = 0; w < warp; ++w) fbase += s_scan_f[w];
+  const float before = fbase + fincl - my_mass;
+  // (c) the thread whose kept-mass interval contains u walks its chunk; the last kept token overall is
+  //     the fallback if rounding leaves u just past the end
+  if (my_mass > 0.f && u >= before && u < before + my_mass) {
+    float c = before;
+    int r = tie_rank, pick = -1;
+    for (int i = i0; i < i1; ++i) {
+      const float e = s_e[i];
+      const uint32_t k = __float_as_uint(e);
+      bool kept = k > kmin;
+      if (k == kmin) { kept = r < tie_keep; ++r; }
+      if (kept) { pick = i; c += e; if (u < c) break; }
+    }
+    s_pick = pick;
+  }
+  __syncthreads();
+  if (s_pick < 0) {  // u == total after rounding: take the highest-index kept token
+    int last = -1;
+    int r = tie_rank;
+    for (int i = i0; i < i1; ++i) {
+      const uint32_t k = __float_as_uint(s_e[i]);
+      bool kept = k > kmin;
+      if (k == kmin) { kept = r < tie_keep; ++r; }
+      if (kept) last = i;
+    }
+    if (last >= 0) atomicMax(&s_pick, last);
+  }
+  __syncthreads();
+  if (tid == 0) sample_commit(p, b, max(s_pick, 0), step_now);
+}
+
 __global__ void int_add_kernel(int* p, int inc) { *p += inc; }
 
 }  // namespace ergm
@@ -460,19 +613,32 @@ extern "C" int ergm_kv_to_pages(const void* kv, int64_t ld, int k_col0, int v_co
   return (int)cudaGetLastError();
 }
 
-extern "C" int ergm_sample(const float* logits, int64_t ld, int B, int V, int top_k,
+extern "C" int ergm_sample(const float* logits, int64_t ld, int B, int V, int top_k, float top_p,
                            float temperature, uint64_t seed, int* step_ptr, int advance_step, int64_t* out_ids,
                            int64_t out_ld, int64_t* next_ids, int* finished, int* seq_lens,
                            int64_t eos_id, void* stream) {
   if (!logits || B <= 0 || V <= 0 || top_k < 0 || top_k > SMP_MAX_K) return ERGM_ERR_ARG;
-  if (top_k > 1 && !(temperature > 0.f)) return ERGM_ERR_ARG;
+  const bool nucleus = top_p < 1.0f;
+  if (nucleus && (!(top_p > 0.f) || top_k > 1)) return ERGM_ERR_ARG;  // top-k and top-p are alternatives
+  if ((top_k > 1 || nucleus) && !(temperature > 0.f)) return ERGM_ERR_ARG;
   if (advance_step && !step_ptr) return ERGM_ERR_ARG;
   unsigned int* ctr = nullptr;
   if (advance_step) ERGM_CUDA_TRY(cudaGetSymbolAddress(reinterpret_cast<void**>(&ctr), g_sample_done_ctr));
-  SampleParams p{logits, ld, V, top_k, top_k > 1 ? 1.f / temperature : 1.f, seed, step_ptr, out_ids, out_ld,
-                 next_ids, finished, seq_lens, eos_id, advance_step ? step_ptr : nullptr, ctr};
-  if (top_k <= 1) return (int)launch_pdl(argmax_kernel, dim3((unsigned)B), dim3(AMX_THREADS), 0, (cudaStream_t)stream, 1, p);
-  return (int)launch_pdl(sample_kernel, dim3((unsigned)B), dim3(SMP_THREADS), 0, (cudaStream_t)stream, 1, p);
+  SampleParams p{logits, ld, V, top_k, top_p, (top_k > 1 || nucleus) ? 1.f / temperature : 1.f, seed, step_ptr, out_ids,
+                 out_ld, next_ids, finished, seq_lens, eos_id, advance_step ? step_ptr : nullptr, ctr};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nucleus) {
+    const size_t smem = (size_t)V * 4;
+    if (smem > 220 * 1024) return ERGM_ERR_UNSUPPORTED;
+    static bool attr_set = false;
+    if (!attr_set) {
+      ERGM_CUDA_TRY(cudaFuncSetAttribute(nucleus_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      attr_set = true;
+    }
+    return (int)launch_pdl(nucleus_kernel, dim3((unsigned)B), dim3(NUC_THREADS), smem, st, 1, p);
+  }
+  if (top_k <= 1) return (int)launch_pdl(argmax_kernel, dim3((unsigned)B), dim3(AMX_THREADS), 0, st, 1, p);
+  return (int)launch_pdl(sample_kernel, dim3((unsigned)B), dim3(SMP_THREADS), 0, st, 1, p);
 }
 
 extern "C" int ergm_int_add(int* dev_ptr, int inc, void* stream) {

@@ -136,9 +136,8 @@ def generate(model, input_ids, token_type_ids=None, max_new_tokens=64, do_sample
     if getattr(model, "ergm_precision", "bf16") == "fp32":
         return _generate_fp32(model, input_ids, token_type_ids, max_new_tokens, eos_token_id, sp2_id, imgs, auds,
                               caption_ids, prompt_lens)
-    if top_p < 1.0:
-        raise L.ErgmError("top-p sampling is a 'next' row (SURVEY.md §8f N2) and is not implemented yet; "
-                          "use greedy or top_k")
+    if do_sample and top_p < 1.0 and top_k > 1:
+        raise L.ErgmError("top_k and top_p are alternatives (main.py:253-282 uses top-p only)")
     eng = model.engine
     eng.ensure_params()
     eng.store.refresh_shadow()
@@ -162,7 +161,7 @@ def generate(model, input_ids, token_type_ids=None, max_new_tokens=64, do_sample
         if sp2_id is not None:
             st.tt = torch.full((B, 1), int(sp2_id), dtype=torch.int64, device=dev)
         k = int(top_k) if do_sample else 0
-        sample_kw = dict(top_k=k, temperature=float(temperature), seed=int(seed),
+        sample_kw = dict(top_k=k, top_p=float(top_p) if do_sample else 1.0, temperature=float(temperature), seed=int(seed),
                          eos_id=int(eos_token_id) if eos_token_id is not None else -1)
         # ---- prefill: fused attention over the padded prompts, K/V -> pages, cross K/V cached ----
         out = eng.forward(input_ids, token_type_ids, None, None, imgs, auds, cap, None, kv_lens=lens,

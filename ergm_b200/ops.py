@@ -283,10 +283,10 @@ def kv_to_pages(kv, pool, block_table, lens, *, B, T, nh, k_col0, v_col0):
           _p(lens), block_table.shape[1], B, T, nh)
 
 
-def sample(logits, *, V, top_k=0, temperature=1.0, seed=0, step=None, out_ids=None, next_ids=None, finished=None,
-           seq_lens=None, eos_id=-1, advance_step=False):
+def sample(logits, *, V, top_k=0, top_p=1.0, temperature=1.0, seed=0, step=None, out_ids=None, next_ids=None,
+           finished=None, seq_lens=None, eos_id=-1, advance_step=False):
     B = logits.shape[0]
-    _call("ergm_sample", logits.data_ptr(), logits.stride(0), B, V, top_k, float(temperature), seed, _p(step),
+    _call("ergm_sample", logits.data_ptr(), logits.stride(0), B, V, top_k, float(top_p), float(temperature), seed, _p(step),
           int(advance_step), _p(out_ids), out_ids.stride(0) if out_ids is not None else 0, _p(next_ids), _p(finished), _p(seq_lens),
           eos_id)
 

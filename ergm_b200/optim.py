@@ -54,13 +54,17 @@ class FusedAdamW:
         h[5], h[6] = 1.0 - b1 ** self.step_count, 1.0 - b2 ** self.step_count
         self.state["hyper"].copy_(h, non_blocking=True)
 
-    def apply(self, grad_scale=None):
-        """Device part of a step (graph-capturable): one kernel over the flat buffers."""
+    def apply(self, grad_scale=None, lo=0, hi=None, last=True):
+        """Device part of a step (graph-capturable): one kernel over the flat buffers, or over the
+        element range [lo, hi) of them (DataParallel updates the layer parameters while the
+        embedding bucket is still being all-reduced).  `last`: this call completes the step."""
         eng, st = self._ensure()
-        ops.adamw_flat(st.flat, st.grad, self.state["m"], self.state["v"], st.shadow, self.state["hyper"], grad_scale)
-        for p in st._plist:  # keep tensor version counters honest for anything watching them
-            pass
-        st.mark_shadow_fresh()
+        hi = st.total if hi is None else hi
+        if hi > lo:
+            ops.adamw_flat(st.flat[lo:hi], st.grad[lo:hi], self.state["m"][lo:hi], self.state["v"][lo:hi],
+                           st.shadow[lo:hi], self.state["hyper"], grad_scale)
+        if last:
+            st.mark_shadow_fresh()
 
     @torch.no_grad()
     def step(self):

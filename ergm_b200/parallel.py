@@ -79,12 +79,24 @@ class DataParallel:
             if trig == layer and hi > lo:
                 self._pending.append(dist.all_reduce(g[lo:hi], group=self.group, async_op=True))
 
-    def backward(self, grad_loss, accumulate):
+    def backward(self, grad_loss, accumulate, defer_last=False):
+        """Backward + bucketed all-reduce.  With defer_last the final (embedding) bucket is left in
+        flight: call finish() before its range [0, split_point()) of the gradient buffer is read."""
         eng = self.model.engine
         self._pending = []
         if self.world > 1 and accumulate:
             raise RuntimeError("gradient accumulation across backward calls is not supported under DataParallel")
         eng.backward(grad_loss, accumulate=accumulate, on_layer_done=self._launch if self.world > 1 else None)
+        keep = 1 if (defer_last and self.world > 1 and self._pending) else 0
+        for w in self._pending[:len(self._pending) - keep]:
+            w.wait()
+        self._pending = self._pending[len(self._pending) - keep:]
+
+    def split_point(self):
+        """First element of the flat buffers that does NOT belong to the last bucket (wte / wpe)."""
+        return self.buckets[-1][2]
+
+    def finish(self):
         for w in self._pending:
             w.wait()
         self._pending = []

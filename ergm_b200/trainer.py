@@ -52,11 +52,20 @@ class GraphedTrainStep:
         if self.dp is not None:
             self.dp.reduce_loss_sums(out["loss_sums"])
         losses = eng.finalize_loss(out)
-        if self.dp is not None:
-            self.dp.backward(self.one, False)
+        if self.dp is not None and getattr(self.dp, "world", 1) > 1:
+            # AdamW on the layer / head parameters runs while the embedding bucket (wte + wpe, 25 % of the
+            # bytes, final only after the embedding backward) is still being all-reduced
+            self.dp.backward(self.one, False, defer_last=True)
+            cut = self.dp.split_point()
+            self.opt.apply(lo=cut, last=False)
+            self.dp.finish()
+            self.opt.apply(lo=0, hi=cut)
         else:
-            eng.backward(self.one, accumulate=False)
-        self.opt.apply()
+            if self.dp is not None:
+                self.dp.backward(self.one, False)
+            else:
+                eng.backward(self.one, accumulate=False)
+            self.opt.apply()
         L = ops.launch_count()
         ops.rng_step_advance(self.rng_step, 1)
         self.launches_per_step = L + 1

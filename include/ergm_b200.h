@@ -251,6 +251,7 @@ int ergm_kv_to_pages(const void* kv, int64_t ld, int k_col0, int v_col0, void* p
  * Writes out_ids[b, *step_ptr], next_ids[b]; finished rows emit eos_id;
  * seq_lens[b] += 1.                                                          */
 int ergm_sample(const float* logits, int64_t ld, int B, int V, int top_k,
+                float top_p /* < 1: nucleus sampling with main.py:263-265's shifted mask; 1 = off */,
                 float temperature, uint64_t seed, int* step_ptr,
                 int advance_step /* 1: *step_ptr += 1 once every row has been sampled */,
                 int64_t* out_ids, int64_t out_ld, int64_t* next_ids, int* finished, int* seq_lens,

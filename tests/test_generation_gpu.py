@@ -213,3 +213,56 @@ def test_fp32_mode_greedy_ids_bit_exact(cuda_device):
     b = synthetic.make_batch(4, 24, seed=21, vocab=cfg.vocab_size, feat_dim=cfg.n_embd, ragged=False)
     ids = m.generate(b["input_ids"].cuda(), b["token_type_ids"].cuda(), max_new_tokens=12, sp2_id=cfg.vocab_size - 1)
     assert np.array_equal(ids.cpu().numpy(), g["greedy_ids"])
+
+
+@pytest.mark.parametrize("top_p", [0.3, 0.8, 0.95])
+def test_nucleus_sampling_matches_reference_filter(cuda_device, top_p):
+    """On-device top-p (ergm_sample, top_p < 1) against the reference's filter (main.py:258-269, restated
+    in oracle.top_p_filter_reference, including the shift-right-by-one of the mask): every drawn token lies
+    in the reference's support, and the empirical distribution matches the re-normalised probabilities."""
+    from ergm_b200 import ops
+    V, ld, R, N = 997, 1024, 6, 3000
+    g = torch.Generator().manual_seed(11)
+    logits = (2.5 * torch.randn(R, ld, generator=g))
+    logits[1, :V] = 0.0                      # flat row: ties everywhere
+    logits[2, 5] = 12.0                      # one dominant token: the crossing token must be kept
+    logits[:, V:] = 50.0                     # padding must never be drawn
+    want = O.top_p_filter_reference(torch.softmax(logits[:, :V].double(), -1), top_p)
+    dl = logits.cuda()
+    step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    out = torch.zeros(R, N, dtype=torch.int64, device="cuda")
+    for _ in range(N):
+        ops.sample(dl, V=V, top_p=top_p, seed=123, step=step, out_ids=out, advance_step=True)
+    assert int(step.item()) == N
+    out = out.cpu()
+    for r in range(R):
+        assert out[r].max() < V
+        freq = torch.bincount(out[r], minlength=V).double() / N
+        if r == 1:  # ties: any subset of the right SIZE is a valid nucleus (torch.sort's tie order is unspecified)
+            assert int((freq > 0).sum()) <= int((want[r] > 0).sum())
+            assert int((freq > 0).sum()) >= min(int((want[r] > 0).sum()), 150)
+            continue
+        assert (want[r][freq > 0] > 0).all(), "row %d: token outside the reference nucleus" % r
+        tv = 0.5 * (freq - want[r]).abs().sum().item()
+        assert tv < 0.12, (r, tv)
+    assert freq.sum() > 0.999
+    # determinism: same (seed, step) -> same draw
+    step.zero_()
+    a = torch.zeros(R, 2, dtype=torch.int64, device="cuda")
+    ops.sample(dl, V=V, top_p=top_p, seed=123, step=step, out_ids=a)
+    assert torch.equal(a[:, 0].cpu(), out[:, 0])
+
+
+def test_generate_with_top_p_runs_in_graph(cuda_device):
+    cfg = tiny_cfg()
+    sd = O.init_state_dict(cfg, seed=5, perturb=True)
+    m = build_model(cfg, sd)
+    b = synthetic.make_batch(4, 24, seed=21, vocab=cfg.vocab_size, feat_dim=cfg.n_embd, ragged=False)
+    ids = m.generate(b["input_ids"].cuda(), b["token_type_ids"].cuda(), max_new_tokens=10, sp2_id=cfg.vocab_size - 1,
+                     do_sample=True, top_p=0.8, seed=7)
+    ids2 = m.generate(b["input_ids"].cuda(), b["token_type_ids"].cuda(), max_new_tokens=10, sp2_id=cfg.vocab_size - 1,
+                      do_sample=True, top_p=0.8, seed=7)
+    assert ids.shape == (4, 10) and int(ids.max()) < cfg.vocab_size and torch.equal(ids, ids2)
+    ids3 = m.generate(b["input_ids"].cuda(), b["token_type_ids"].cuda(), max_new_tokens=10, sp2_id=cfg.vocab_size - 1,
+                      do_sample=True, top_p=0.8, seed=8)
+    assert not torch.equal(ids, ids3)
