@@ -250,7 +250,7 @@ def main():
     dp = None
     if world > 1:
         from ergm_b200.parallel import DataParallel
-        dp = DataParallel(model, bucket_mb=float(os.environ.get("ERGM_BUCKET_MB", "32")))
+        dp = DataParallel(model, bucket_mb=float(os.environ.get("ERGM_BUCKET_MB", "128")))
     step = GraphedTrainStep(model, opt, dp=dp, use_graph=not args.no_graph)
     batch = host_batch(B_PER_GPU, SEQ, seed=1234 + rank)
     H, L = model.config.n_embd, model.config.n_layer

@@ -52,7 +52,7 @@ def shard_range(n, rank, world):
 class DataParallel:
     """Wraps an ergm_b200 GPT2LMHeadModel for one-process-per-GPU data parallelism."""
 
-    def __init__(self, model, bucket_mb=32, process_group=None, broadcast_params=True):
+    def __init__(self, model, bucket_mb=128, process_group=None, broadcast_params=True):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
         self.model = model
