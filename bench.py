@@ -104,21 +104,26 @@ def gemm_flops(info):
     return 2.0 * M * N * K
 
 
-def build(device, n_layer=12, n_embd=768, n_head=12, dropout=0.1, seed=0):
+def build(device, n_layer=12, n_embd=768, n_head=12, dropout=0.1, seed=0, feat_dim=None):
     from transformers import GPT2Config
     from ergm_b200.model import GPT2LMHeadModel
     torch.manual_seed(seed)
     cfg = GPT2Config(vocab_size=VOCAB, n_embd=n_embd, n_layer=n_layer, n_head=n_head,
                      attn_pdrop=dropout, resid_pdrop=dropout, embd_pdrop=dropout)
+    if feat_dim:  # A3 extension: raw feature sequences pooled + projected feat_dim -> n_embd on the device
+        cfg.ergm_visual_dim = cfg.ergm_audio_dim = feat_dim
     m = GPT2LMHeadModel(cfg).to(device)
     return m.train()
 
 
-def host_batch(B, T, seed, pin=True):
+def host_batch(B, T, seed, pin=True, sequences=False, kf=1):
     from oracle import synthetic
-    b = synthetic.make_batch(B, T, seed=seed)
+    b = synthetic.make_batch(B, T, seed=seed, kf=kf)
     out = {k: b[k] for k in ("input_ids", "token_type_ids", "labels", "emotion_labels", "caption_ids", "imgs", "auds")}
-    out["imgs"] = out["imgs"][:, 0].contiguous()
+    if sequences:  # [B, 197*kf, 768] key-frame features, [B, 113, 768] audio features (text_feature.py:44,49)
+        out["imgs"], out["auds"] = b["vis_seq"].contiguous(), b["aud_seq"].contiguous()
+    else:
+        out["imgs"] = out["imgs"][:, 0].contiguous()
     if pin:
         out = {k: v.pin_memory() for k, v in out.items()}
     return out
@@ -227,7 +232,13 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--dropout", type=float, default=0.1)
+    ap.add_argument("--config", default="small", choices=["small", "medium"],
+                    help="small = BASELINE configs[1] (the metric's config); medium = configs[4]: GPT-2 medium, "
+                         "T=512, B=8 per GPU, 4-key-frame 768-wide feature sequences pooled + projected on device")
     args = ap.parse_args()
+    global B_PER_GPU, SEQ
+    if args.config == "medium":
+        B_PER_GPU, SEQ = 8, 512
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -245,14 +256,15 @@ def main():
     from ergm_b200.trainer import GraphedTrainStep
     pk = peaks()
 
-    model = build(device, dropout=args.dropout)
+    medium = args.config == "medium"
+    model = build(device, dropout=args.dropout, **(dict(n_layer=24, n_embd=1024, n_head=16, feat_dim=768) if medium else {}))
     opt = FusedAdamW(model, lr=2e-5)
     dp = None
     if world > 1:
         from ergm_b200.parallel import DataParallel
         dp = DataParallel(model, bucket_mb=float(os.environ.get("ERGM_BUCKET_MB", "128")))
     step = GraphedTrainStep(model, opt, dp=dp, use_graph=not args.no_graph)
-    batch = host_batch(B_PER_GPU, SEQ, seed=1234 + rank)
+    batch = host_batch(B_PER_GPU, SEQ, seed=1234 + rank, sequences=medium, kf=4 if medium else 1)
     H, L = model.config.n_embd, model.config.n_layer
 
     def barrier():
@@ -332,13 +344,13 @@ def main():
     model_tf = value / world * fl_tok / 1e12
 
     gen = None
-    if rank == 0 and not args.no_gen:
+    if rank == 0 and not args.no_gen and not medium:
         try:
             gen = bench_generation(model, device)
         except Exception as e:  # generation is a secondary line; never lose the training number
             gen = {"error": "%s: %s" % (type(e).__name__, e)}
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and not medium:
         tps, ms_cpu, threads = cpu_reference_run(steps=2, warmup=1, B=2)
         cpu = {"value": tps, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": "oracle port fwd+bwd+AdamW, B=2 x T=256 caption mode, 2 timed steps (%.0f ms/step)" % ms_cpu}
@@ -346,10 +358,12 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": "ERGM GPT-2 small (152.8M params, V=50260) teacher-forced training step: "
-                                       "fwd + bwd + AdamW, caption mode (cross-attention) + img/aud fusion, "
-                                       "dropout %.2f, B=%d x T=%d per GPU, synthetic MELD-shaped, random init"
-                                       % (args.dropout, B_PER_GPU, SEQ),
+                "config": {"workload": "ERGM GPT-2 %s (%.1fM params, V=50260) teacher-forced training step: "
+                                       "fwd + bwd + AdamW, caption mode (cross-attention) + img/aud fusion%s, "
+                                       "dropout %.2f, B=%d x T=%d per GPU, synthetic %s-shaped, random init"
+                                       % (args.config, sum(p.numel() for p in model.parameters()) / 1e6,
+                                          " from on-device pooled + projected feature sequences" if medium else "",
+                                          args.dropout, B_PER_GPU, SEQ, "IEMOCAP/MEDIC" if medium else "MELD"),
                            "per_gpu_batch": B_PER_GPU, "seq_len": SEQ, "parallelism": "dp%d" % world,
                            "l2": "no flush needed: the step streams >5 GB of activations/weights/grads per "
                                  "iteration, far above the 126 MB L2",

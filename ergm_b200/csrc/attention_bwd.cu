@@ -78,11 +78,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const int n_iter = active ? n_q - i_min : 0;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_do);
+    // the producer owns the load barriers and fires K / V and the first Q / dO stage BEFORE the block-wide
+    // sync below: the first TMA round trip overlaps the 512-column TMEM allocation (one CTA per SM here,
+    // so nothing else hides the prologue)
+    mbar_init(bar_kv, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(qdo_full(s), 1); mbar_init(qdo_empty(s), 1); }
+    fence_mbar_init();
+    if (active) {
+      mbar_expect_tx(bar_kv, 2 * AB_TILE);
+      tma_load_3d(sK, &tm_k, bar_kv, p.k_col0 + h * 64, k0, b);
+      tma_load_3d(sV, &tm_v, bar_kv, p.v_col0 + h * 64, k0, b);
+      mbar_expect_tx(qdo_full(0), 2 * AB_TILE);
+      tma_load_3d(sQ, &tm_q, qdo_full(0), p.q_col0 + h * 64, i_min * 128, b);
+      tma_load_3d(sDO, &tm_do, qdo_full(0), h * 64, i_min * 128, b);
+    }
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(bar_kv, 1); mbar_init(bar_sdp, 1); mbar_init(bar_pds, 256); mbar_init(bar_dq, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(qdo_full(s), 1); mbar_init(qdo_empty(s), 1); }
+    mbar_init(bar_sdp, 1); mbar_init(bar_pds, 256); mbar_init(bar_dq, 1);
     fence_mbar_init();
   }
   if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -95,10 +107,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
   if (warp == 0) {
     if (lane == 0 && active) {
-      mbar_expect_tx(bar_kv, 2 * AB_TILE);
-      tma_load_3d(sK, &tm_k, bar_kv, p.k_col0 + h * 64, k0, b);
-      tma_load_3d(sV, &tm_v, bar_kv, p.v_col0 + h * 64, k0, b);
-      for (int it = 0; it < n_iter; ++it) {
+      for (int it = 1; it < n_iter; ++it) {
         const int st = it & 1;
         mbar_wait(qdo_empty(st), ((it >> 1) & 1) ^ 1);
         mbar_expect_tx(qdo_full(st), 2 * AB_TILE);

@@ -82,11 +82,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   }
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
+    // the producer owns the load barriers and fires Q / K_0 / V_0 BEFORE the block-wide sync below, so the
+    // first TMA round trip (~1 us) overlaps the TMEM allocation instead of following it
+    mbar_init(bar_q, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+    fence_mbar_init();
+    mbar_expect_tx(bar_q, AT_TILE);
+    tma_load_3d(sQ, &tm_q, bar_q, p.q_col0 + h * AT_D, q0, b);
+    mbar_expect_tx(kv_full(0), 2 * AT_TILE);
+    tma_load_3d(sK, &tm_k, kv_full(0), p.k_col0 + h * AT_D, 0, b);
+    tma_load_3d(sV, &tm_v, kv_full(0), p.v_col0 + h * AT_D, 0, b);
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(bar_q, 1); mbar_init(bar_s, 1); mbar_init(bar_p, 256); mbar_init(bar_o, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+    mbar_init(bar_s, 1); mbar_init(bar_p, 256); mbar_init(bar_o, 1);
     fence_mbar_init();
   }
   if (warp == 2) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
@@ -100,9 +108,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(bar_q, AT_TILE);
-      tma_load_3d(sQ, &tm_q, bar_q, p.q_col0 + h * AT_D, q0, b);
-      for (int j = 0; j < n_kv; ++j) {
+      for (int j = 1; j < n_kv; ++j) {
         const int st = j & 1;
         mbar_wait(kv_empty(st), ((j >> 1) & 1) ^ 1);
         mbar_expect_tx(kv_full(st), 2 * AT_TILE);

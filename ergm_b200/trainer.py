@@ -31,6 +31,8 @@ class GraphedTrainStep:
         if self.dp is not None and getattr(self.dp, "world", 1) > 1 and os.environ.get("ERGM_DP_GRAPH", "1") == "0":
             use_graph = False
         self.use_graph = use_graph
+        # A3 extension: imgs / auds are raw feature sequences [B, T, D] (pooled + projected on the device)
+        self.seq_features = hasattr(model, "visual_proj")
         self.graphs = {}
         self.static = {}
         eng = model.engine
@@ -78,7 +80,7 @@ class GraphedTrainStep:
             v = batch.get(k)
             if v is None:
                 continue
-            if k == "imgs" and v.dim() == 3:
+            if k == "imgs" and v.dim() == 3 and not self.seq_features:
                 v = v[:, 0]
             dt = torch.float32 if k in ("imgs", "auds") else torch.int64
             st[k] = torch.empty(tuple(v.shape), dtype=dt, device=self.eng.device)
@@ -95,7 +97,7 @@ class GraphedTrainStep:
         st = self.static.get(key) or self._stage(key, batch)
         for k, dst in st.items():
             src = batch[k]
-            if k == "imgs" and src.dim() == 3:
+            if k == "imgs" and src.dim() == 3 and not self.seq_features:
                 src = src[:, 0]
             dst.copy_(src, non_blocking=True)
         return key, st
