@@ -128,10 +128,14 @@ class Engine:
     @staticmethod
     def _wgrad_gemm(x, dy, dw, K_in, N_out, M_red):
         # dw[K_in, N_out] += x[M_red, K_in]^T @ dy[M_red, N_out]
-        tiles = ((K_in + 127) // 128) * ((N_out + 127) // 128)
-        split = max(1, min(16, round(148.0 / tiles)))
+        # 128x256 tiles, K (= tokens) split so that tiles * splits fills the 148 SMs once
+        # (measured, profiles/r1_gemm_epilogue.md: 768x3072 44.1 -> 32.4 us, 768x768 15.1 -> 12.9 us
+        # against 128x128 tiles with round(148 / tiles) splits)
+        bn = 256 if N_out >= 256 else 128
+        tiles = ((K_in + 127) // 128) * ((N_out + bn - 1) // bn)
+        split = max(1, min(16, 148 // tiles))
         ops.gemm(x, dy, dw, M=K_in, N=N_out, K=M_red, a_major=MN_MAJOR, b_major=MN_MAJOR,
-                 epilogue=L.EPI_ATOMIC, split_k=split, block_n=128)
+                 epilogue=L.EPI_ATOMIC, split_k=split, block_n=bn)
 
     # ------------------------------------------------------------------
     def forward(self, input_ids, token_type_ids=None, labels=None, emotion_labels=None, imgs=None, auds=None,
@@ -494,7 +498,7 @@ class Engine:
             ops.gemm(dlogits, wte_b, dhn, M=M, N=H, K=V, a_major=K_MAJOR, b_major=MN_MAJOR)
             # d wte += dlogits^T @ hn
             ops.gemm(dlogits, hn, self.pg("transformer.wte.weight"), M=V, N=H, K=M, a_major=MN_MAJOR,
-                     b_major=MN_MAJOR, epilogue=L.EPI_ATOMIC, block_n=128)
+                     b_major=MN_MAJOR, epilogue=L.EPI_ATOMIC, block_n=2256)  # pair 256x256: 0.785 -> 0.435 ms
         else:
             dhn.zero_()
         if sv["emo"] is not None:
