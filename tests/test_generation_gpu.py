@@ -266,3 +266,20 @@ def test_generate_with_top_p_runs_in_graph(cuda_device):
     ids3 = m.generate(b["input_ids"].cuda(), b["token_type_ids"].cuda(), max_new_tokens=10, sp2_id=cfg.vocab_size - 1,
                       do_sample=True, top_p=0.8, seed=8)
     assert not torch.equal(ids, ids3)
+
+
+def test_decode_more_than_one_row_tile(cuda_device):
+    """70 sequences = two 64-row tiles of the decode GEMMs: every row must decode exactly as it does in a
+    small batch (rows are independent; the weights are re-streamed per tile)."""
+    cfg = tiny_cfg()
+    sd = O.init_state_dict(cfg, seed=5, perturb=True)
+    m = build_model(cfg, sd)
+    b = synthetic.make_batch(70, 24, seed=33, vocab=cfg.vocab_size, feat_dim=cfg.n_embd, ragged=False)
+    ids, tt = b["input_ids"].cuda(), b["token_type_ids"].cuda()
+    full = m.generate(ids, tt, max_new_tokens=6, sp2_id=cfg.vocab_size - 1).cpu()
+    part = m.generate(ids[60:70], tt[60:70], max_new_tokens=6, sp2_id=cfg.vocab_size - 1).cpu()
+    # fp32 split-K reductions into the residual stream are order-dependent in the last bit: allow the rare
+    # near-tie flip, require the bulk to agree exactly
+    agree = (full[60:70] == part).float().mean().item()
+    assert agree >= 0.9, agree
+    assert full.shape == (70, 6)
