@@ -78,6 +78,36 @@ def packed_weights(eng):
     return pk
 
 
+def mega_table(eng, st):
+    """Device table of per-layer pointers for ergm_decode_layers (packed weights, folded biases, this
+    batch's K/V pools): 14 pointers per layer."""
+    pk = st.packed
+    rows = []
+    for l in range(eng.L):
+        pfx = "transformer.h.%d." % l
+
+        def pair(name):
+            w, b = pk[pfx + name]
+            return [w.data_ptr(), b.data_ptr() if b is not None else 0]
+
+        cross = st.kv2 is not None
+        rows.append(pair("attn.c_attn") + pair("attn.c_proj")
+                    + (pair("crossattention.q_attn") if cross else [0, 0])
+                    + (pair("crossattention.c_proj") if cross else [0, 0])
+                    + pair("mlp.c_fc") + pair("mlp.c_proj")
+                    + [st.pool[l].data_ptr(), st.kv2[l].data_ptr() if cross else 0])
+    return torch.tensor(rows, dtype=torch.int64).to(eng.device)
+
+
+def mega_supported(eng, B):
+    import os
+    # opt-in: measured 576-660 us / step against 533 us for the launch chain (profiles/r1_decode.md) - the
+    # in-kernel attention phase (4 groups per CTA, two rounds) and the 60 grid barriers still cost more than
+    # they save
+    return (os.environ.get("ERGM_DEC_MEGA", "0") == "1" and B <= DEC_TILE and eng.H in (128, 256, 512, 768, 1024)
+            and eng.I % 512 == 0)
+
+
 def decode_step(eng, st, sample_kw):
     """One token for every sequence of the batch; pure device work (CUDA-graph capturable).
     Per layer: [LN1 + QKV] -> paged attention (+append) -> [out-proj += residual] -> ([LN + q] ->
@@ -96,6 +126,15 @@ def decode_step(eng, st, sample_kw):
     ctx = ws.get("dec_ctx", (B, H), bf16)
     q2 = ws.get("dec_q2", (B, H), bf16)
     g = ws.get("dec_g", (B, I), bf16)
+    if st.mega is not None:
+        # all blocks in ONE persistent kernel (grid barriers instead of ~60 dependent launches)
+        ops.decode_layers(st.mega, L=eng.L, H=H, I=I, nh=nh, B=B, x=x, qkv=qkv, ctx=ctx, q2=q2 if st.kv2 is not None else None,
+                          g=g, block_table=st.block_table, seq_lens=st.seq_lens, Tc=st.Tc if st.kv2 is not None else 0,
+                          eps=eps, sync_ctr=st.sync_ctr)
+        _head_on_rows(eng, x, None, st.logits)
+        ops.sample(st.logits, V=eng.V, step=st.step, out_ids=st.out_ids, next_ids=st.next_ids, finished=st.finished,
+                   seq_lens=st.seq_lens, advance_step=True, **sample_kw)
+        return
     tiles = [(r0, min(B, r0 + DEC_TILE)) for r0 in range(0, B, DEC_TILE)]
 
     def ln_gemm(out, name, K, N, **kw):
@@ -158,6 +197,10 @@ def generate(model, input_ids, token_type_ids=None, max_new_tokens=64, do_sample
     with torch.cuda.device(dev):
         st = GenState(eng, B, max_ctx, Tc, max_new_tokens)
         st.packed = packed_weights(eng)
+        st.mega = None
+        if mega_supported(eng, B):
+            st.sync_ctr = torch.zeros(1, dtype=torch.int32, device=dev)
+            st.mega = mega_table(eng, st)
         if sp2_id is not None:
             st.tt = torch.full((B, 1), int(sp2_id), dtype=torch.int64, device=dev)
         k = int(top_k) if do_sample else 0

@@ -65,7 +65,7 @@ def gemm(a, b, d, *, M, N, K, a_major=L.ERGM_MAJOR_K, b_major=L.ERGM_MAJOR_MN, l
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim)
-_LAUNCHES = {"ergm_attn_bwd": 2}
+_LAUNCHES = {"ergm_attn_bwd": 2, "ergm_decode_layers": 1}
 _launch_count = 0
 PROFILE = None  # set to a list to collect (name, info, start_event, end_event) per call
 
@@ -276,6 +276,13 @@ def dec_gemm(out, w_packed, *, M, K, N, x=None, a=None, eps=1e-5, bias=None, out
     src = x if x is not None else a
     _call("ergm_dec_gemm", _p(x), _p(a), src.stride(0), float(eps), w_packed.data_ptr(), K, N,
           _p(bias), out.data_ptr(), out.stride(0), out_mode, int(gelu), M)
+
+
+def decode_layers(table, *, L, H, I, nh, B, x, qkv, ctx, q2, g, block_table, seq_lens, Tc, eps, sync_ctr):
+    """All transformer blocks of one decode step in one persistent kernel (see header)."""
+    _call("ergm_decode_layers", table.data_ptr(), L, H, I, nh, B, x.data_ptr(), qkv.data_ptr(), ctx.data_ptr(),
+          _p(q2), g.data_ptr(), block_table.data_ptr(), seq_lens.data_ptr(), block_table.shape[1], Tc, float(eps),
+          sync_ctr.data_ptr())
 
 
 def kv_to_pages(kv, pool, block_table, lens, *, B, T, nh, k_col0, v_col0):

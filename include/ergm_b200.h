@@ -207,6 +207,16 @@ int ergm_attn_fwd_f32(const float* q, int64_t ld_q, int q_col0, const float* k, 
                       const int* kv_lens, int B, int nh, int Tq, int Tk, int head_dim, int causal,
                       int causal_off, void* stream);
 
+/* The whole block stack of one decode step as ONE persistent cooperative kernel (148 CTAs, in-kernel grid */
+/* barriers instead of ~60 dependent launches; model.py:286-341 per block).  layer_table: device array of  */
+/* L records of 14 pointers each: {w_qkv, b_qkv, w_o, b_o, w_q2, b_q2, w_o2, b_o2, w_fc, b_fc, w_p2, b_p2,  */
+/* kv_pool, kv2} - packed weights / folded biases from ergm_dec_pack_weight, this layer's paged K/V pool,   */
+/* its cached cross-attention K/V [B*Tc, 2H] (NULL pointers when Tc == 0).  x: fp32 [B, H] residual stream  */
+/* (in: embeddings; out: last block's output).  qkv / ctx / q2 / g: bf16 scratch [B, 3H] / [B, H] / [B, H] / */
+/* [B, I].  sync_ctr: device uint32 used by the grid barrier.  B <= 64.                                      */
+int ergm_decode_layers(const void* layer_table, int L, int H, int I, int nh, int B, float* x, void* qkv,
+                       void* ctx, void* q2, void* g, const int* block_table, const int* seq_lens,
+                       int max_pages, int Tc, float eps, unsigned int* sync_ctr, void* stream);
 /* Decode-step GEMMs (M = batch <= 64 rows, one new token per sequence): every      */
 /* Conv1D / Linear of the block (model.py:218-222,244,263,265) and the tied LM head  */
 /* (model.py:698) is weight-streaming bound at this M.  ergm_dec_pack_weight re-packs */

@@ -283,3 +283,24 @@ def test_decode_more_than_one_row_tile(cuda_device):
     agree = (full[60:70] == part).float().mean().item()
     assert agree >= 0.9, agree
     assert full.shape == (70, 6)
+
+
+@pytest.mark.parametrize("caption", [False, True])
+def test_persistent_decode_kernel_matches_launch_chain(cuda_device, caption, monkeypatch):
+    """ERGM_DEC_MEGA=1: all blocks of a decode step in one cooperative kernel (ergm_decode_layers) must
+    produce the same tokens as the per-phase launch chain (same packed weights, same arithmetic; only the
+    fp32 split-K reduction order into the residual stream differs)."""
+    cfg = tiny_cfg()
+    sd = O.init_state_dict(cfg, seed=6, perturb=True)
+    m = build_model(cfg, sd)
+    b = synthetic.make_batch(5, 40, seed=22, vocab=cfg.vocab_size, feat_dim=cfg.n_embd, ragged=False, tc=17)
+    lens = torch.tensor([40, 23, 31, 40, 35]).cuda()
+    kw = dict(max_new_tokens=10, sp2_id=cfg.vocab_size - 1, prompt_lens=lens)
+    if caption:
+        kw.update(caption_ids=b["caption_ids"].cuda(), imgs=b["imgs"].cuda(), auds=b["auds"].cuda())
+    monkeypatch.setenv("ERGM_DEC_MEGA", "0")
+    chain = m.generate(b["input_ids"].cuda(), b["token_type_ids"].cuda(), **kw).cpu()
+    monkeypatch.setenv("ERGM_DEC_MEGA", "1")
+    mega = m.generate(b["input_ids"].cuda(), b["token_type_ids"].cuda(), **kw).cpu()
+    assert mega.shape == chain.shape
+    assert (mega == chain).float().mean().item() >= 0.9, (mega.tolist(), chain.tolist())
