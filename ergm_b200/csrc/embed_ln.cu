@@ -169,6 +169,8 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
               int rows, float eps, const int* __restrict__ row_idx) {
   constexpr int H = NV * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();  // the next kernel's blocks may be scheduled as ours drain ...
+  pdl_wait();               // ... and we touch nothing before everything upstream has completed
   float4 g[NV], bt[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -618,9 +620,9 @@ extern "C" int ergm_ln_fwd(const float* x, const float* gamma, const float* beta
                            const int* row_idx, void* stream) {
   if (!x || !gamma || !beta || rows <= 0 || H % 128) return ERGM_ERR_ARG;
   return dispatch_nv(H, [&](auto nv) {
-    ln_fwd_kernel<decltype(nv)::value><<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd, rows, eps, row_idx);
-    return (int)cudaGetLastError();
+    return (int)launch_pdl(ln_fwd_kernel<decltype(nv)::value>, dim3((unsigned)row_grid(rows)), dim3(ROW_WARPS * 32), 0,
+                           (cudaStream_t)stream, 1, x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y_bf16), y_f32, mean,
+                           rstd, rows, eps, row_idx);
   });
 }
 
