@@ -67,7 +67,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const uint32_t tmem_slot = bars + 64;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int jb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  // heaviest CTAs first: causal key block jb is visited by the query blocks >= jb, so key block 0 has the most
+  // work; blockIdx.z is the slowest-varying index of the block scheduler
+  const int jb = blockIdx.z, h = blockIdx.y, b = blockIdx.x;
   const int k0 = jb * 128;
   int kv_len = p.Tk;
   if (p.kv_lens) kv_len = min(kv_len, p.kv_lens[b]);
@@ -391,7 +393,7 @@ extern "C" int ergm_attn_bwd(const void* q, int64_t ld_q, int q_col0, const void
     ERGM_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
     attr = true;
   }
-  dim3 grid((Tk + 127) / 128, nh, B);
+  dim3 grid(B, nh, (Tk + 127) / 128);
   if (causal)
     attn_bwd_kernel<true><<<grid, AB_THREADS, AB_SMEM, s>>>(tq, tk, tv, tdo, p);
   else

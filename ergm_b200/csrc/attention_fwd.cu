@@ -25,7 +25,7 @@ namespace ergm {
 
 #ifdef ERGM_TRACE
 __device__ long long g_attn_trace[64];
-#define TRACE(slot) do { if (blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && trace_thread) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_attn_trace[slot] = t_; } } while (0)
+#define TRACE(slot) do { if (blockIdx.z == 0 && blockIdx.y == 0 && blockIdx.x == 0 && trace_thread) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_attn_trace[slot] = t_; } } while (0)
 #else
 #define TRACE(slot) do { } while (0)
 #endif
@@ -67,7 +67,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const uint32_t tmem_slot = bars + 64;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  // heaviest CTAs first: causal query block qb visits qb + 1 key blocks, so the LAST query blocks are scheduled
+  // first (blockIdx.z is the slowest-varying index of the block scheduler) and the light ones fill the tail
+  const int qb = (int)gridDim.z - 1 - (int)blockIdx.z, h = blockIdx.y, b = blockIdx.x;
   const int q0 = qb * 128;
 #ifdef ERGM_TRACE
   const bool trace_thread = (threadIdx.x == 4 * 32);
@@ -340,7 +342,7 @@ extern "C" int ergm_attn_fwd(const void* q, int64_t ld_q, int q_col0, const void
                                        cudaSharedmemCarveoutMaxShared));
     attr = true;
   }
-  dim3 grid((Tq + 127) / 128, nh, B);
+  dim3 grid(B, nh, (Tq + 127) / 128);
   if (causal)
     attn_fwd_kernel<true><<<grid, AT_THREADS, AT_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
   else
