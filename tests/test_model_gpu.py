@@ -307,3 +307,43 @@ def test_modality_sequence_projection_extension(cuda_device):
                                                    O.init_state_dict(O.OracleConfig(vocab_size=256, n_positions=64,
                                                                                     n_embd=128, n_layer=1, n_head=2),
                                                                      seed=1)).state_dict()
+
+
+@pytest.mark.parametrize("B,T,Tc", [(1, 17, 5), (3, 33, 1), (2, 130, 257), (5, 128, 129), (1, 1, 3)])
+def test_odd_shapes_forward_backward(cuda_device, B, T, Tc):
+    """Edge shapes: sequence / caption lengths that are not multiples of any tile (17, 33, 130 crosses the
+    128-row attention block, caption length 257 = two full key blocks + 1, a single token), batch 1.
+    Forward, loss and a few gradients against the oracle."""
+    cfg = O.OracleConfig(vocab_size=515, n_positions=300, n_embd=128, n_layer=2, n_head=2)
+    sd = O.init_state_dict(cfg, seed=17, perturb=True)
+    m = build_model(cfg, sd).train()
+    g = torch.Generator().manual_seed(B * 100 + T)
+    ids = torch.randint(0, cfg.vocab_size, (B, T), generator=g)
+    tt = torch.randint(cfg.vocab_size - 2, cfg.vocab_size, (B, T), generator=g)
+    lab = ids.clone()
+    if T > 2:
+        lab[:, : T // 3] = -100
+    emo = torch.randint(0, 7, (B,), generator=g)
+    cap = torch.randint(0, cfg.vocab_size, (B, Tc), generator=g)
+    imgs, auds = torch.randn(B, 1, 128, generator=g), torch.randn(B, 128, generator=g)
+    if T < 2:
+        imgs = auds = None  # model.py:497-498 indexes positions 0 and 1
+    kw = dict(input_ids=ids.cuda(), token_type_ids=tt.cuda(), labels=lab.cuda(), emotion_labels=emo.cuda(),
+              caption_ids=cap.cuda())
+    if imgs is not None:
+        kw.update(imgs=imgs.cuda(), auds=auds.cuda())
+    out = m(**kw)
+    out.loss.backward()
+    sdo = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k != "lm_head.weight"}
+    sdo["lm_head.weight"] = sdo["transformer.wte.weight"]
+    o = O.forward(sdo, cfg, ids, tt, lab, emo, imgs, auds, cap)
+    o["loss"].backward()
+    assert rel(out.logits, o["logits"]) < LOGITS_REL_TOL
+    if T > 1:  # T == 1: the shifted LM loss has no target (mean over zero labels is nan in the reference too)
+        assert abs(out.loss.item() - o["loss"].item()) < 5e-3
+    assert rel(out.emotion_logits, o["emotion_logits"]) < 2e-2
+    if T > 1:
+        for name in ("transformer.h.0.attn.c_attn.weight", "transformer.h.1.crossattention.c_attn.weight",
+                     "transformer.wpe.weight", "transformer.h.1.ln_2.bias"):
+            p = dict(m.named_parameters())[name]
+            assert rel(p.grad, sdo[name].grad) < 6e-2, (name, rel(p.grad, sdo[name].grad))
