@@ -16,6 +16,7 @@
 //     and advances the per-sequence lengths.
 #include "../../include/ergm_b200.h"
 #include "common.cuh"
+#include <cstdlib>
 
 namespace ergm {
 
@@ -49,11 +50,10 @@ ERGM_DEVINL float dot8(const uint4 a, const uint4 b) {
 // (8 tokens x {K, V}); the 16 partial states are merged once at the end (flash-decoding inside a CTA).
 // The cached K/V of the context do not depend on the kernel that produced q: their first 128 tokens
 // are fetched BEFORE the programmatic-dependency wait, i.e. while the QKV projection is still running.
-constexpr int DEC_UNROLL = 8;
 constexpr int DEC_GROUPS = DEC_THREADS / 8;
 constexpr int DEC_BT_SMEM = 256;   // block-table entries staged in smem (4096 tokens)
 
-template <bool PAGED>
+template <bool PAGED, int DEC_UNROLL>
 __global__ void __launch_bounds__(DEC_THREADS) attn_decode_kernel(const DecodeAttnParams p) {
   __shared__ float s_m[DEC_GROUPS], s_l[DEC_GROUPS];
   __shared__ float s_acc[DEC_GROUPS][64];
@@ -580,7 +580,10 @@ extern "C" int ergm_attn_decode_paged(const void* qkv, int64_t ld_q, int q_col0,
   p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
   p.nh = nh; p.max_pages = max_pages;
   p.scale = 1.0f / sqrtf((float)head_dim);
-  return (int)launch_pdl(attn_decode_kernel<true>, dim3(nh, B), dim3(DEC_THREADS), 0, (cudaStream_t)stream, 1, p);
+  static int unroll = 0;
+  if (!unroll) { const char* e = getenv("ERGM_DEC_UNROLL"); unroll = e ? atoi(e) : 8; }
+  if (unroll == 4) return (int)launch_pdl(attn_decode_kernel<true, 4>, dim3(nh, B), dim3(DEC_THREADS), 0, (cudaStream_t)stream, 1, p);
+  return (int)launch_pdl(attn_decode_kernel<true, 8>, dim3(nh, B), dim3(DEC_THREADS), 0, (cudaStream_t)stream, 1, p);
 }
 
 extern "C" int ergm_attn_decode_contig(const void* q, int64_t ld_q, int q_col0, const void* kv,
@@ -599,7 +602,7 @@ extern "C" int ergm_attn_decode_contig(const void* q, int64_t ld_q, int q_col0, 
   p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
   p.nh = nh; p.Tk = Tk;
   p.scale = 1.0f / sqrtf((float)head_dim);
-  return (int)launch_pdl(attn_decode_kernel<false>, dim3(nh, B), dim3(DEC_THREADS), 0, (cudaStream_t)stream, 1, p);
+  return (int)launch_pdl(attn_decode_kernel<false, 8>, dim3(nh, B), dim3(DEC_THREADS), 0, (cudaStream_t)stream, 1, p);
 }
 
 extern "C" int ergm_kv_to_pages(const void* kv, int64_t ld, int k_col0, int v_col0, void* pool,
