@@ -34,6 +34,8 @@ struct AttnBwdParams {
   float* dq_accum;      // fp32 [B*Tq, ld_dq], head h at columns [h*64, ...)
   __nv_bfloat16* dk;    // [B*Tk, ld_dk], head h at columns [dk_col0 + h*64, ...)
   __nv_bfloat16* dv;
+  float* dk_colsum;     // nullable [nh*64]: += column sums of dK as stored (bias gradient of the K projection)
+  float* dv_colsum;     // nullable [nh*64]
   const int* kv_lens;
   int64_t ld_dq, ld_dk, ld_dv;
   int dk_col0, dv_col0;
@@ -44,6 +46,29 @@ struct AttnBwdParams {
   DropoutSite drop;
   int do_drop;
 };
+
+// Bias gradient of the K / V projection: column sums of this warp's [32 keys x 32 columns] slab of dK / dV,
+// taken over the bf16-ROUNDED values that are stored (what a separate column-sum pass over dK / dV would
+// see), one fp32 atomic per column per warp.  Replaces a full extra read of dK / dV per attention.
+template <int N>
+ERGM_DEVINL void colsum_fold(float (&x)[32], int lane) {
+  // lanes with bit N set keep the upper N columns, the others the lower N; each adds what its partner held
+  const bool upper = (lane & N) != 0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const float send = upper ? x[i] : x[i + N];
+    const float recv = __shfl_xor_sync(0xffffffffu, send, N);
+    x[i] = (upper ? x[i + N] : x[i]) + recv;
+  }
+}
+ERGM_DEVINL void attn_bwd_colsum(const uint32_t (&v)[32], bool row_ok, float* dst, int lane) {
+  float x[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) x[i] = row_ok ? __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[i]))) : 0.f;
+  // transpose-reduce butterfly: 16 + 8 + 4 + 2 + 1 = 31 shuffles; lane l ends up with column l's total
+  colsum_fold<16>(x, lane); colsum_fold<8>(x, lane); colsum_fold<4>(x, lane); colsum_fold<2>(x, lane); colsum_fold<1>(x, lane);
+  atomicAdd(dst + lane, x[0]);
+}
 
 template <bool CAUSAL>
 __global__ void __launch_bounds__(AB_THREADS, 1)
@@ -280,6 +305,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
               pack_bf16x2(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])),
               pack_bf16x2(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])));
       }
+      if (p.dk_colsum) attn_bwd_colsum(v, kj < p.Tk, p.dk_colsum + h * 64 + 32 * half, lane);
       tmem_ld_32x32b_x32(tDV + lane_addr + 32 * half, v);
       tmem_ld_wait();
       if (kj < p.Tk) {
@@ -292,6 +318,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
               pack_bf16x2(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])),
               pack_bf16x2(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])));
       }
+      if (p.dv_colsum) attn_bwd_colsum(v, kj < p.Tk, p.dv_colsum + h * 64 + 32 * half, lane);
     }
   } else if (warp >= 4 && !active) {
     // keys that no query sees (or beyond kv_len): zero gradients
@@ -353,8 +380,8 @@ extern "C" int ergm_attn_bwd(const void* q, int64_t ld_q, int q_col0, const void
                              int k_col0, const void* v, int64_t ld_v, int v_col0, const void* out,
                              int64_t ld_out, const float* out_f32, const void* dout, int64_t ld_do, const float* lse,
                              float* delta, float* dq_accum, int64_t ld_dq, void* dk, int64_t ld_dk,
-                             int dk_col0, void* dv, int64_t ld_dv, int dv_col0, const int* kv_lens,
-                             int B, int nh, int Tq, int Tk, int head_dim, int causal, int causal_off,
+                             int dk_col0, void* dv, int64_t ld_dv, int dv_col0, float* dk_colsum, float* dv_colsum,
+                             const int* kv_lens, int B, int nh, int Tq, int Tk, int head_dim, int causal, int causal_off,
                              float dropout_p, uint64_t seed, uint64_t offset, void* stream) {
   if (!q || !k || !v || !out || !dout || !lse || !delta || !dq_accum || !dk || !dv) return ERGM_ERR_ARG;
   if (B <= 0 || nh <= 0 || Tq <= 0 || Tk <= 0) return ERGM_ERR_ARG;
@@ -379,6 +406,7 @@ extern "C" int ergm_attn_bwd(const void* q, int64_t ld_q, int q_col0, const void
   AttnBwdParams p;
   p.lse = lse; p.delta = delta; p.dq_accum = dq_accum;
   p.dk = reinterpret_cast<__nv_bfloat16*>(dk); p.dv = reinterpret_cast<__nv_bfloat16*>(dv);
+  p.dk_colsum = dk_colsum; p.dv_colsum = dv_colsum;
   p.kv_lens = kv_lens;
   p.ld_dq = ld_dq; p.ld_dk = ld_dk; p.ld_dv = ld_dv; p.dk_col0 = dk_col0; p.dv_col0 = dv_col0;
   p.Tq = Tq; p.Tk = Tk; p.nh = nh;

@@ -544,11 +544,12 @@ class Engine:
                 self._wgrad_gemm(r["ctx2"], dxb, self.pg(pfx + "crossattention.c_proj.weight"), H, H, M)
                 self._dgrad_gemm(dxb, self.pb(pfx + "crossattention.c_proj.weight"), dH, M, H, H)
                 dq_acc.zero_()
+                gbx = self.pg(pfx + "crossattention.c_attn.bias")  # K / V bias gradients come out of attn_bwd
                 ops.attn_bwd(r["q2"], r["kv2"], r["kv2"], r["ctx2"], dH, r["lse2"], delta, dq_acc, dkv2, dkv2,
                              B=B, nh=nh, Tq=T, Tk=Tc, q_col0=0, k_col0=0, v_col0=H, dk_col0=0, dv_col0=H,
-                             causal=False, dropout_p=pd_attn, seed=seed, offset=s_xattn, out_f32=r["ctx2_32"])
+                             causal=False, dropout_p=pd_attn, seed=seed, offset=s_xattn, out_f32=r["ctx2_32"],
+                             dk_colsum=gbx[:H], dv_colsum=gbx[H:])
                 ops.cast_f32_bf16_2d(dq_acc, dq2, self.pg(pfx + "crossattention.q_attn.bias"))
-                ops.colsum_bf16(dkv2, self.pg(pfx + "crossattention.c_attn.bias"))
                 self._wgrad_gemm(r["a2"], dq2, self.pg(pfx + "crossattention.q_attn.weight"), H, H, M)
                 self._wgrad_gemm(sv["enc"], dkv2, self.pg(pfx + "crossattention.c_attn.weight"), H, 2 * H, Mc)
                 self._dgrad_gemm(dq2, self.pb(pfx + "crossattention.q_attn.weight"), dH, M, H, H)
@@ -563,12 +564,12 @@ class Engine:
             self._dgrad_gemm(dxb, self.pb(pfx + "attn.c_proj.weight"), dH, M, H, H)
             dq_acc.zero_()
             qkv = r["qkv"]
+            gb = self.pg(pfx + "attn.c_attn.bias")
             ops.attn_bwd(qkv, qkv, qkv, r["ctx"], dH, r["lse1"], delta, dq_acc, dqkv, dqkv, B=B, nh=nh, Tq=T, Tk=T,
                          q_col0=0, k_col0=H, v_col0=2 * H, dk_col0=H, dv_col0=2 * H, causal=True,
-                         kv_lens=sv["kv_lens"], dropout_p=pd_attn, seed=seed, offset=s_attn, out_f32=r["ctx32"])
-            gb = self.pg(pfx + "attn.c_attn.bias")
+                         kv_lens=sv["kv_lens"], dropout_p=pd_attn, seed=seed, offset=s_attn, out_f32=r["ctx32"],
+                         dk_colsum=gb[H:2 * H], dv_colsum=gb[2 * H:])
             ops.cast_f32_bf16_2d(dq_acc, dqkv[:, :H], gb[:H])
-            ops.colsum_bf16(dqkv[:, H:], gb[H:], rows=M, N=2 * H, ld=3 * H)
             self._wgrad_gemm(r["a1"], dqkv, self.pg(pfx + "attn.c_attn.weight"), H, 3 * H, M)
             self._dgrad_gemm(dqkv, self.pb(pfx + "attn.c_attn.weight"), dH, M, H, 3 * H)
             if l > 0:

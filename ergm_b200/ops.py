@@ -201,13 +201,14 @@ def attn_fwd(q, k, v, out, lse, *, B, nh, Tq, Tk, q_col0=0, k_col0=0, v_col0=0, 
 
 def attn_bwd(q, k, v, out, dout, lse, delta, dq_accum, dk, dv, *, B, nh, Tq, Tk, q_col0=0, k_col0=0, v_col0=0,
              dk_col0=0, dv_col0=0, causal=True, causal_off=None, kv_lens=None, dropout_p=0.0, seed=0, offset=0,
-             out_f32=None):
+             out_f32=None, dk_colsum=None, dv_colsum=None):
     if causal_off is None:
         causal_off = Tk - Tq
     _call("ergm_attn_bwd", q.data_ptr(), q.stride(0), q_col0, k.data_ptr(), k.stride(0), k_col0, v.data_ptr(),
           v.stride(0), v_col0, out.data_ptr(), out.stride(0), _p(out_f32), dout.data_ptr(), dout.stride(0), lse.data_ptr(),
           delta.data_ptr(), dq_accum.data_ptr(), dq_accum.stride(0), dk.data_ptr(), dk.stride(0), dk_col0,
-          dv.data_ptr(), dv.stride(0), dv_col0, _p(kv_lens), B, nh, Tq, Tk, 64, int(causal), causal_off,
+          dv.data_ptr(), dv.stride(0), dv_col0, _p(dk_colsum), _p(dv_colsum), _p(kv_lens), B, nh, Tq, Tk, 64, int(causal),
+          causal_off,
           dropout_p, seed, offset)
 
 

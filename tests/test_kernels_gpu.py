@@ -306,8 +306,12 @@ def test_attn_bwd(cuda_device, B, nh, Tq, Tk, causal):
     dout = torch.randn(B * Tq, H, device="cuda", generator=g).bfloat16()
     delta = torch.empty(B, nh, Tq, device="cuda")
     dq = torch.zeros(B * Tq, H, device="cuda")
+    cs = torch.full((2, H), 0.5, device="cuda")  # fused K / V bias gradients accumulate onto existing values
     ops.attn_bwd(qm, km, vm, out, dout, lse, delta, dq, dkm, dvm, B=B, nh=nh, Tq=Tq, Tk=Tk, q_col0=qc, k_col0=kc,
-                 v_col0=vc, dk_col0=dkc, dv_col0=dvc, causal=causal)
+                 v_col0=vc, dk_col0=dkc, dv_col0=dvc, causal=causal, dk_colsum=cs[0], dv_colsum=cs[1])
+    for i, (mat, c0) in enumerate(((dkm, dkc), (dvm, dvc))):
+        want = 0.5 + mat[:, c0:c0 + H].float().sum(0)  # column sums of the values AS STORED (bf16)
+        assert (cs[i] - want).abs().max().item() < 2e-3 * (1 + want.abs().max().item()), (cs[i] - want).abs().max().item()
     q = qm[:, qc:qc + H].float().view(B, Tq, nh, 64).permute(0, 2, 1, 3).clone().requires_grad_(True)
     k = km[:, kc:kc + H].float().view(B, Tk, nh, 64).permute(0, 2, 1, 3).clone().requires_grad_(True)
     v = vm[:, vc:vc + H].float().view(B, Tk, nh, 64).permute(0, 2, 1, 3).clone().requires_grad_(True)
