@@ -22,6 +22,7 @@ class GemmArgs(ctypes.Structure):
     _fields_ = [
         ("a", ctypes.c_void_p), ("b", ctypes.c_void_p), ("d", ctypes.c_void_p),
         ("bias", ctypes.c_void_p), ("residual", ctypes.c_void_p), ("preact", ctypes.c_void_p),
+        ("colsum", ctypes.c_void_p),
         ("lda", ctypes.c_int64), ("ldb", ctypes.c_int64), ("ldd", ctypes.c_int64), ("ldr", ctypes.c_int64),
         ("M", ctypes.c_int32), ("N", ctypes.c_int32), ("K", ctypes.c_int32),
         ("a_major", ctypes.c_int32), ("b_major", ctypes.c_int32),

@@ -44,6 +44,7 @@ struct GemmParams {
   const float* bias;
   const float* residual;
   void* preact;
+  float* colsum;
   int64_t ldd, ldr;
   int M, N, K;
   int a_mn, b_mn;
@@ -238,7 +239,7 @@ ERGM_DEVINL void epilogue_chunk(const GemmParams& p, const EpiFlags& ep, int row
 // (no bounds tests; edge tiles take the generic path), strength-reduces the addressing and prefetches
 // the residual operand of chunk c+1 (and of the next tile's first chunk) while chunk c is processed.
 // ------------------------------------------------------------------------------------------
-enum { FM_NONE = 0, FM_BF16 = 1, FM_BF16_BIAS = 2, FM_F32 = 3, FM_F32_RES = 4, FM_GELU = 5, FM_ATOMIC = 6 };
+enum { FM_NONE = 0, FM_BF16 = 1, FM_BF16_BIAS = 2, FM_F32 = 3, FM_F32_RES = 4, FM_GELU = 5, FM_ATOMIC = 6, FM_GELU_GRAD = 7 };
 
 template <int FM>
 ERGM_DEVINL void fast_res_prefetch(const GemmParams& p, int row0, int col0, int lane, float4 (&res)[8]) {
@@ -247,6 +248,16 @@ ERGM_DEVINL void fast_res_prefetch(const GemmParams& p, int row0, int col0, int 
     const int64_t step = 4 * p.ldr;
 #pragma unroll
     for (int it = 0; it < 8; ++it) res[it] = *reinterpret_cast<const float4*>(rp + it * step);
+  }
+  if constexpr (FM == FM_GELU_GRAD) {  // saved pre-activation u (bf16, same layout as D): 4 values = 8 bytes per lane
+    const __nv_bfloat16* up = reinterpret_cast<const __nv_bfloat16*>(p.preact) + (int64_t)(row0 + (lane >> 3)) * p.ldd +
+                              col0 + 4 * (lane & 7);
+    const int64_t step = 4 * p.ldd;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const uint2 u = *reinterpret_cast<const uint2*>(up + it * step);
+      res[it] = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), 0.f, 0.f);
+    }
   }
 }
 
@@ -271,6 +282,7 @@ ERGM_DEVINL void epilogue_chunk_fast(const GemmParams& p, const EpiFlags& ep, in
   __syncwarp();
   const int64_t off0 = (int64_t)(row0 + rsub) * p.ldd + col;
   const int64_t dstep = 4 * p.ldd;
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);  // FM_GELU_GRAD: column sums of the stored values (bias gradient)
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int r = 4 * it + rsub;
@@ -298,6 +310,16 @@ ERGM_DEVINL void epilogue_chunk_fast(const GemmParams& p, const EpiFlags& ep, in
       }
       x.x += res[it].x; x.y += res[it].y; x.z += res[it].z; x.w += res[it].w;
     }
+    if constexpr (FM == FM_GELU_GRAD) {  // x *= gelu_new'(u)  (model.py:264 backward), then the bias-gradient column sum
+      const float2 f0 = unpack_bf16x2(__float_as_uint(res[it].x)), f1 = unpack_bf16x2(__float_as_uint(res[it].y));
+      x.x *= gelu_new_grad<false>(f0.x); x.y *= gelu_new_grad<false>(f0.y);
+      x.z *= gelu_new_grad<false>(f1.x); x.w *= gelu_new_grad<false>(f1.y);
+      const uint2 pk = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.d) + off) = pk;
+      const float2 r0 = unpack_bf16x2(pk.x), r1 = unpack_bf16x2(pk.y);
+      cs.x += r0.x; cs.y += r0.y; cs.z += r1.x; cs.w += r1.y;
+      continue;
+    }
     if constexpr (FM == FM_F32 || FM == FM_F32_RES) {
       *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.d) + off) = x;
     } else if constexpr (FM == FM_ATOMIC) {
@@ -307,6 +329,19 @@ ERGM_DEVINL void epilogue_chunk_fast(const GemmParams& p, const EpiFlags& ep, in
     } else {
       *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.d) + off) =
           make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+    }
+  }
+  if constexpr (FM == FM_GELU_GRAD) {
+    if (p.colsum) {  // lanes c4, c4+8, c4+16, c4+24 hold the same 4 columns of different rows
+#pragma unroll
+      for (int o = 8; o <= 16; o <<= 1) {
+        cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+        cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+      }
+      if (lane < 8)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.colsum + col), "f"(cs.x), "f"(cs.y), "f"(cs.z),
+                     "f"(cs.w)
+                     : "memory");
     }
   }
 }
@@ -323,7 +358,7 @@ ERGM_DEVINL void epilogue_tile(const GemmParams& p, const EpiFlags& ep, uint32_t
       uint32_t r[32];
       tmem_ld_32x32b_x32(tmem_tile + c, r);
       float4 res_cur[8];
-      if constexpr (FM == FM_F32_RES) {
+      if constexpr (FM == FM_F32_RES || FM == FM_GELU_GRAD) {
 #pragma unroll
         for (int it = 0; it < 8; ++it) res_cur[it] = res_pre[it];
         if (c + 32 < c_hi) fast_res_prefetch<FM>(p, row0, n0 + c + 32, lane, res_pre);
@@ -696,7 +731,7 @@ static int launch_gemm2(const ergm_gemm_args* a, cudaStream_t stream) {
     rc = encode_tmap_2d(&tb, a->b, 2, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb * 2, 64, BK);
   if (rc) return rc;
   GemmParams p;
-  p.d = a->d; p.bias = a->bias; p.residual = a->residual; p.preact = a->preact;
+  p.d = a->d; p.bias = a->bias; p.residual = a->residual; p.preact = a->preact; p.colsum = a->colsum;
   p.ldd = a->ldd; p.ldr = a->ldr;
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.a_mn = a->a_major == ERGM_MAJOR_MN; p.b_mn = a->b_major == ERGM_MAJOR_MN;
@@ -753,7 +788,7 @@ static int launch_gemm(const ergm_gemm_args* a, cudaStream_t stream) {
   if (rc) return rc;
 
   GemmParams p;
-  p.d = a->d; p.bias = a->bias; p.residual = a->residual; p.preact = a->preact;
+  p.d = a->d; p.bias = a->bias; p.residual = a->residual; p.preact = a->preact; p.colsum = a->colsum;
   p.ldd = a->ldd; p.ldr = a->ldr;
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.a_mn = a->a_major == ERGM_MAJOR_MN; p.b_mn = a->b_major == ERGM_MAJOR_MN;
@@ -855,7 +890,13 @@ extern "C" int ergm_gemm_bf16(const ergm_gemm_args* a, void* stream) {
       else if (f32 && (e & ERGM_EPI_RESIDUAL) &&
                (e & ~(ERGM_EPI_BIAS | ERGM_EPI_RESIDUAL | ERGM_EPI_DROPOUT)) == 0) fm = FM_F32_RES;
       else if (f32 && e == ERGM_EPI_ATOMIC) fm = FM_ATOMIC;
+      else if (!f32 && e == ERGM_EPI_GELU_GRAD && a->preact) fm = FM_GELU_GRAD;
     }
+  }
+  if (a->colsum) {
+    // fused bias-gradient column sums exist only in the lean GELU' epilogue, which runs on interior tiles
+    const int tm = bn > 2000 ? 256 : 128, tn = bn % 1000;
+    if (fm != FM_GELU_GRAD || a->M % tm || a->N % tn) return ERGM_ERR_UNSUPPORTED;
   }
 #define ERGM_DISPATCH_EC(FN, BNV)                                   \
   switch (fm) {                                                     \
@@ -865,6 +906,7 @@ extern "C" int ergm_gemm_bf16(const ergm_gemm_args* a, void* stream) {
     case FM_F32_RES: return FN<BNV, EC_LINEAR, FM_F32_RES>(a, s);   \
     case FM_GELU: return FN<BNV, EC_GELU, FM_GELU>(a, s);           \
     case FM_ATOMIC: return FN<BNV, EC_LINEAR, FM_ATOMIC>(a, s);     \
+    case FM_GELU_GRAD: return FN<BNV, EC_GELU_GRAD, FM_GELU_GRAD>(a, s); \
     default: break;                                                 \
   }                                                                 \
   switch (ec) {                                                     \

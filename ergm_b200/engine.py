@@ -530,8 +530,13 @@ class Engine:
             has_x = "a2" in r
             # ---- MLP backward ----
             self._wgrad_gemm(r["g"], dxb, self.pg(pfx + "mlp.c_proj.weight"), I, H, M)
-            self._dgrad_gemm(dxb, self.pb(pfx + "mlp.c_proj.weight"), dI, M, I, H)
-            ops.gelu_bwd_colsum(dI, r["u"], self.pg(pfx + "mlp.c_fc.bias"))
+            if M % 256 == 0 and I % 256 == 0:
+                # GELU' and the c_fc bias gradient ride in the dgrad epilogue (lean FM_GELU_GRAD mode)
+                self._dgrad_gemm(dxb, self.pb(pfx + "mlp.c_proj.weight"), dI, M, I, H, gelu_grad_of=r["u"],
+                                 colsum=self.pg(pfx + "mlp.c_fc.bias"), block_n=2256)
+            else:
+                self._dgrad_gemm(dxb, self.pb(pfx + "mlp.c_proj.weight"), dI, M, I, H)
+                ops.gelu_bwd_colsum(dI, r["u"], self.pg(pfx + "mlp.c_fc.bias"))
             self._wgrad_gemm(r["a3"], dI, self.pg(pfx + "mlp.c_fc.weight"), H, I, M)
             self._dgrad_gemm(dI, self.pb(pfx + "mlp.c_fc.weight"), dH, M, H, I)
             x_in = r["x2"] if has_x else r["x1"]

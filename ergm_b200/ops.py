@@ -20,7 +20,7 @@ def _ptr(t):
 
 def gemm(a, b, d, *, M, N, K, a_major=L.ERGM_MAJOR_K, b_major=L.ERGM_MAJOR_MN, lda=None, ldb=None,
          ldd=None, bias=None, residual=None, ldr=None, preact=None, gelu_grad_of=None, epilogue=0, split_k=1,
-         block_n=0, dropout_p=0.0, seed=0, offset=0):
+         block_n=0, dropout_p=0.0, seed=0, offset=0, colsum=None):
     """D[M,N] = epilogue(A * B).  a/b bf16, d bf16 or fp32.  See include/ergm_b200.h."""
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     args = L.GemmArgs()
@@ -28,6 +28,7 @@ def gemm(a, b, d, *, M, N, K, a_major=L.ERGM_MAJOR_K, b_major=L.ERGM_MAJOR_MN, l
     args.bias = bias.data_ptr() if bias is not None else None
     args.residual = residual.data_ptr() if residual is not None else None
     args.preact = preact.data_ptr() if preact is not None else None
+    args.colsum = colsum.data_ptr() if colsum is not None else None
     args.lda = a.stride(0) if lda is None else lda
     args.ldb = b.stride(0) if ldb is None else ldb
     args.ldd = d.stride(0) if ldd is None else ldd

@@ -66,6 +66,8 @@ typedef struct ergm_gemm_args {
   const float* bias;   /* [N] or NULL */
   const float* residual; /* fp32 [M, ldr] or NULL */
   void* preact;        /* bf16 [M, ldd] or NULL */
+  float* colsum;       /* NULL, or fp32 [N] += column sums of D as stored: bias gradient fused into the
+                          ERGM_EPI_GELU_GRAD dgrad (bf16 D, M and N multiples of the tile) */
   int64_t lda, ldb, ldd, ldr;
   int32_t M, N, K;
   int32_t a_major, b_major;

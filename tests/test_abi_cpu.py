@@ -42,8 +42,8 @@ def test_header_is_plain_c():
 
 def test_gemm_args_struct_matches_header():
     from ergm_b200 import _lib
-    # 6 pointers + 4 int64 + 9 int32 + float + 2 uint64, natural alignment
-    assert ctypes.sizeof(_lib.GemmArgs) == 6 * 8 + 4 * 8 + 9 * 4 + 4 + 2 * 8
+    # 7 pointers + 4 int64 + 9 int32 + float + 2 uint64, natural alignment
+    assert ctypes.sizeof(_lib.GemmArgs) == 7 * 8 + 4 * 8 + 9 * 4 + 4 + 2 * 8
 
 
 def test_argument_errors_without_gpu(lib):

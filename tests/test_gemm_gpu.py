@@ -135,3 +135,30 @@ def test_gemm_dropout_epilogue(cuda_device):
     assert torch.equal(d, d2)
     ops.gemm(a, w, d2, M=M, N=N, K=K, dropout_p=0.25, seed=1234, offset=8)
     assert not torch.equal(d, d2)
+
+
+@pytest.mark.parametrize("block_n", [0, 128, 192, 256, 2256])
+def test_gemm_gelu_grad_with_fused_bias_colsum(cuda_device, block_n):
+    """dgrad of the MLP output projection with gelu_new' and the c_fc bias gradient fused in the epilogue
+    (model.py:263-266 backward): D = (A @ B^T) * gelu_new'(u) as bf16, colsum += column sums of D as stored."""
+    from ergm_b200 import ops
+    M, N, K = 512, 768, 256
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    b = (0.1 * torch.randn(N, K, device="cuda", generator=g)).bfloat16()
+    u = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    d = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    cs = torch.full((N,), 0.25, device="cuda")
+    ops.gemm(a, b, d, M=M, N=N, K=K, a_major=0, b_major=0, gelu_grad_of=u, colsum=cs, block_n=block_n)
+    uf = u.float().requires_grad_(True)
+    torch.nn.functional.gelu(uf, approximate="tanh").sum().backward()
+    ref = (a.float() @ b.float().t()) * uf.grad
+    assert ((d.float() - ref).norm() / ref.norm()).item() < 1e-2
+    want = 0.25 + d.float().sum(0)
+    assert (cs - want).abs().max().item() < 2e-3 * (1 + want.abs().max().item())
+    # without the column sum the same mode still works, and non-tile-multiple shapes refuse the fused sum
+    d2 = torch.zeros_like(d)
+    ops.gemm(a, b, d2, M=M, N=N, K=K, a_major=0, b_major=0, gelu_grad_of=u, block_n=block_n)
+    assert torch.equal(d, d2)
+    with pytest.raises(Exception):
+        ops.gemm(a[:500], b, d[:500], M=500, N=N, K=K, a_major=0, b_major=0, gelu_grad_of=u[:500], colsum=cs, block_n=block_n)
