@@ -316,7 +316,8 @@ class Engine:
         """6x split-expanded bf16 copy of an fp32 weight (cached per parameter version)."""
         cache = self.__dict__.setdefault("_w6_cache", {})
         w = self.p(name)
-        ver = self.store.params[name]._version
+        self.store.refresh_shadow()
+        ver = self.store.weights_epoch
         hit = cache.get(name)
         if hit is not None and hit[0] == ver:
             return hit[1]

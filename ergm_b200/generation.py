@@ -60,7 +60,8 @@ def packed_weights(eng):
     """Decode-layout copies of the weights (bf16 16-column slabs in mma fragment order with the
     preceding LayerNorm folded in, ergm_dec_pack_weight), cached per parameter version: generation
     never re-packs unless the weights changed.  Values: (packed, bias)."""
-    ver = sum(p._version for p in eng.store._plist)
+    eng.store.refresh_shadow()  # notices in-place edits of the parameters (bumps weights_epoch)
+    ver = eng.store.weights_epoch
     hit = eng.__dict__.get("_dec_pack")
     if hit is not None and hit[0] == ver and hit[1] is eng.store.flat:
         return hit[2]

@@ -21,6 +21,10 @@ class ParamStore:
         self._ptrs = None
         self._versions = None
         self.shadow_fresh = False
+        # bumped whenever the parameter VALUES may have changed (fused optimiser step, detected in-place edits,
+        # rebuild): derived weight formats (decode slabs, fp32-mode split operands) key their caches on it,
+        # because the fused AdamW writes the flat buffer directly and never touches torch's version counters
+        self.weights_epoch = 0
         self.build()
 
     # ------------------------------------------------------------------
@@ -67,6 +71,7 @@ class ParamStore:
         self._plist = [p for _, p in params]
         self._versions = None
         self.shadow_fresh = False
+        self.weights_epoch = getattr(self, "weights_epoch", 0) + 1
         self.device = device
         self.had_grad = had_grad
 
@@ -106,10 +111,13 @@ class ParamStore:
             ops.cast_f32_bf16(self.flat, self.shadow)
             self._versions = versions
             self.shadow_fresh = True
+            self.weights_epoch += 1
 
     def mark_shadow_fresh(self):
+        """Called by the fused optimiser: it rewrote the fp32 weights AND their bf16 shadow."""
         self._versions = sum(p._version for p in self._plist)
         self.shadow_fresh = True
+        self.weights_epoch += 1
 
     def grads_live(self):
         """True when the caller kept gradients (no zero_grad since the last backward): the next

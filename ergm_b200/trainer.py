@@ -120,6 +120,9 @@ class GraphedTrainStep:
             self.graphs[key] = g
             return
         g.replay()
+        # the replayed AdamW rewrote the weights and their bf16 shadow; the Python-side bookkeeping of the
+        # captured call did not run again, so tell the parameter store explicitly
+        self.eng.store.mark_shadow_fresh()
 
     def close(self):
         """Drops the captured graphs (needed before tearing down the process group)."""

@@ -304,3 +304,52 @@ def test_persistent_decode_kernel_matches_launch_chain(cuda_device, caption, mon
     mega = m.generate(b["input_ids"].cuda(), b["token_type_ids"].cuda(), **kw).cpu()
     assert mega.shape == chain.shape
     assert (mega == chain).float().mean().item() >= 0.9, (mega.tolist(), chain.tolist())
+
+
+def test_generation_after_fused_optimizer_step_uses_new_weights(cuda_device):
+    """The fused AdamW rewrites the flat parameter buffer without touching torch's version counters: the
+    decode-layout weight cache (and the fp32-mode operand cache) must still notice.  Train a few large-lr
+    steps, generate, and compare with a FRESH model built from the updated state dict."""
+    from ergm_b200.optim import FusedAdamW
+    cfg = tiny_cfg()
+    sd = O.init_state_dict(cfg, seed=5, perturb=True)
+    m = build_model(cfg, sd)
+    b = synthetic.make_batch(4, 24, seed=21, vocab=cfg.vocab_size, feat_dim=cfg.n_embd, ragged=False)
+    ids, tt = b["input_ids"].cuda(), b["token_type_ids"].cuda()
+    before = m.generate(ids, tt, max_new_tokens=8, sp2_id=cfg.vocab_size - 1).cpu()  # fills the caches
+    m.train()
+    opt = FusedAdamW(m, lr=5e-2)
+    for _ in range(3):
+        out = m(input_ids=ids, token_type_ids=tt, labels=ids.clone())
+        out.loss.backward()
+        opt.step()
+        opt.zero_grad()
+    m.eval()
+    after = m.generate(ids, tt, max_new_tokens=8, sp2_id=cfg.vocab_size - 1).cpu()
+    fresh = build_model(cfg, {k: v.detach().cpu().clone() for k, v in m.state_dict().items()})
+    want = fresh.generate(ids, tt, max_new_tokens=8, sp2_id=cfg.vocab_size - 1).cpu()
+    assert torch.equal(after, want), (after.tolist(), want.tolist())
+    assert not torch.equal(after, before)  # lr = 5e-2 for three steps changes the greedy continuation
+
+
+def test_generation_after_graph_replayed_training_uses_new_weights(cuda_device):
+    """Same as above through GraphedTrainStep: replays run no Python-side optimiser bookkeeping."""
+    from ergm_b200.optim import FusedAdamW
+    from ergm_b200.trainer import GraphedTrainStep
+    cfg = tiny_cfg()
+    sd = O.init_state_dict(cfg, seed=5, perturb=True)
+    m = build_model(cfg, sd)
+    b = synthetic.make_batch(4, 24, seed=21, vocab=cfg.vocab_size, feat_dim=cfg.n_embd, ragged=False)
+    ids, tt = b["input_ids"].cuda(), b["token_type_ids"].cuda()
+    m.generate(ids, tt, max_new_tokens=4, sp2_id=cfg.vocab_size - 1)  # fills the caches
+    m.train()
+    step = GraphedTrainStep(m, FusedAdamW(m, lr=5e-2))
+    host = {k: b[k].pin_memory() for k in ("input_ids", "token_type_ids", "labels", "emotion_labels", "caption_ids", "auds")}
+    host["imgs"] = b["imgs"][:, 0].contiguous().pin_memory()
+    for _ in range(4):  # eager warm-up + capture + replays
+        step(host)
+    m.eval()
+    after = m.generate(ids, tt, max_new_tokens=8, sp2_id=cfg.vocab_size - 1).cpu()
+    fresh = build_model(cfg, {k: v.detach().cpu().clone() for k, v in m.state_dict().items()})
+    want = fresh.generate(ids, tt, max_new_tokens=8, sp2_id=cfg.vocab_size - 1).cpu()
+    assert torch.equal(after, want), (after.tolist(), want.tolist())
