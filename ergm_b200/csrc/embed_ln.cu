@@ -246,7 +246,7 @@ struct LnBwdParams {
 // consumer warps are doing; a consumer warp owns one row of the tile (warp-shuffle statistics, no block
 // barrier in the loop) and keeps its share of the three column sums in registers.
 constexpr int LNB_ROWS = 8;            // rows per tile = consumer warps
-constexpr int LNB_THREADS = (LNB_ROWS + 1) * 32;
+constexpr int LNB_THREADS = LNB_ROWS * 32;  // 256: registers are allocated per 4 warps, a 9th (producer) warp capped us at 168
 
 ERGM_DEVINL void lnb_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -264,47 +264,54 @@ __global__ void __launch_bounds__(LNB_THREADS, 1) ln_bwd_kernel(const LnBwdParam
   const uint32_t dy_bytes = LNB_ROWS * dy_row, f_bytes = LNB_ROWS * f_row;
   const uint32_t stage_bytes = dy_bytes + f_bytes + (p.dres_in ? f_bytes : 0u);
   const uint32_t bars = smem_u32(lnb_smem);            // full[s] at 8s, empty[s] at 64 + 8s
-  unsigned char* ring = lnb_smem + 128;
+  float4* s_gamma = reinterpret_cast<float4*>(lnb_smem + 128);  // gamma lives in smem, not in 24 registers
+  unsigned char* ring = lnb_smem + 128 + H * 4;
   const int n_tiles = (p.rows + LNB_ROWS - 1) / LNB_ROWS;
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(bars + 8 * s, 1); mbar_init(bars + 64 + 8 * s, LNB_ROWS); }
     fence_mbar_init();
   }
+  for (int i = threadIdx.x; i < H / 4; i += blockDim.x) s_gamma[i] = __ldg(reinterpret_cast<const float4*>(p.gamma) + i);
   __syncthreads();
   float4 ag[NV], ab[NV], an[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) ag[i] = ab[i] = an[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (warp == LNB_ROWS) {
-    // ===================== producer =====================
-    if (lane == 0) {
-      int it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int s = it % stages;
-        if (it >= stages) mbar_wait(bars + 64 + 8 * s, (uint32_t)((it / stages - 1) & 1));
-        const int row0 = tile * LNB_ROWS;
-        const uint32_t nr = (uint32_t)min(LNB_ROWS, p.rows - row0);
-        const uint32_t dst = smem_u32(ring + (size_t)s * stage_bytes);
-        mbar_expect_tx(bars + 8 * s, nr * (dy_row + f_row + (p.dres_in ? f_row : 0u)));
-        lnb_bulk_g2s(dst, reinterpret_cast<const unsigned char*>(p.dy) + (size_t)row0 * dy_row, nr * dy_row, bars + 8 * s);
-        lnb_bulk_g2s(dst + dy_bytes, p.x + (size_t)row0 * H, nr * f_row, bars + 8 * s);
-        if (p.dres_in) lnb_bulk_g2s(dst + dy_bytes + f_bytes, p.dres_in + (size_t)row0 * H, nr * f_row, bars + 8 * s);
-      }
-    }
-  } else {
+  // lane 0 of warp 0 doubles as the producer: it keeps `stages` tiles in flight, refilling the slot of tile
+  // it-1 at the top of iteration it (by then the other warps have normally released it)
+  auto issue_tile = [&](int tile, int s) {
+    const int row0 = tile * LNB_ROWS;
+    const uint32_t nr = (uint32_t)min(LNB_ROWS, p.rows - row0);
+    const uint32_t dst = smem_u32(ring + (size_t)s * stage_bytes);
+    mbar_expect_tx(bars + 8 * s, nr * (dy_row + f_row + (p.dres_in ? f_row : 0u)));
+    lnb_bulk_g2s(dst, reinterpret_cast<const unsigned char*>(p.dy) + (size_t)row0 * dy_row, nr * dy_row, bars + 8 * s);
+    lnb_bulk_g2s(dst + dy_bytes, p.x + (size_t)row0 * H, nr * f_row, bars + 8 * s);
+    if (p.dres_in) lnb_bulk_g2s(dst + dy_bytes + f_bytes, p.dres_in + (size_t)row0 * H, nr * f_row, bars + 8 * s);
+  };
+  const bool producer = threadIdx.x == 0;
+  if (producer) {
+    int tile = blockIdx.x;
+    for (int s = 0; s < stages && tile < n_tiles; ++s, tile += gridDim.x) issue_tile(tile, s);
+  }
+  {
     // ===================== consumers: warp w owns row w of every tile =====================
     const float keep_scale = p.do_drop ? p.drop.keep_scale() : 1.f;
-    float4 gm[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) gm[i] = __ldg(reinterpret_cast<const float4*>(p.gamma) + lane + 32 * i);
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int s = it % stages;
+      if (producer && it >= 1) {
+        const int prev = it - 1;
+        const int nxt_tile = tile + (stages - 1) * (int)gridDim.x;  // tile index of iteration prev + stages
+        if (nxt_tile < n_tiles) {
+          mbar_wait(bars + 64 + 8 * (prev % stages), (uint32_t)((prev / stages) & 1));
+          issue_tile(nxt_tile, prev % stages);
+        }
+      }
       const int row = tile * LNB_ROWS + warp;
       const bool row_ok = row < p.rows;
       const float mean = row_ok ? __ldg(p.mean + row) : 0.f, rstd = row_ok ? __ldg(p.rstd + row) : 0.f;
       mbar_wait(bars + 8 * s, (uint32_t)((it / stages) & 1));
       const unsigned char* st = ring + (size_t)s * stage_bytes;
-      float4 dy[NV], xh[NV], rs[NV];
+      float4 dy[NV], xh[NV];
       if (row_ok) {
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
@@ -316,19 +323,19 @@ __global__ void __launch_bounds__(LNB_THREADS, 1) ln_bwd_kernel(const LnBwdParam
             dy[i] = make_float4(a.x, a.y, b.x, b.y);
           }
           xh[i] = reinterpret_cast<const float4*>(st + dy_bytes + (size_t)warp * f_row)[lane + 32 * i];
-          rs[i] = p.dres_in ? reinterpret_cast<const float4*>(st + dy_bytes + f_bytes + (size_t)warp * f_row)[lane + 32 * i]
-                            : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+      } else {  // row past the end (last tile): nothing to do, hand the slot back
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + 64 + 8 * s);
+        continue;
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bars + 64 + 8 * s);  // this warp's row is in registers: slot may be refilled
-      if (!row_ok) continue;
       float c1 = 0.f, c2 = 0.f;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         xh[i].x = (xh[i].x - mean) * rstd; xh[i].y = (xh[i].y - mean) * rstd;
         xh[i].z = (xh[i].z - mean) * rstd; xh[i].w = (xh[i].w - mean) * rstd;
-        const float gx = dy[i].x * gm[i].x, gy = dy[i].y * gm[i].y, gz = dy[i].z * gm[i].z, gw = dy[i].w * gm[i].w;
+        const float4 gm = s_gamma[lane + 32 * i];
+        const float gx = dy[i].x * gm.x, gy = dy[i].y * gm.y, gz = dy[i].z * gm.z, gw = dy[i].w * gm.w;
         c1 += (gx + gy) + (gz + gw);
         c2 += (gx * xh[i].x + gy * xh[i].y) + (gz * xh[i].z + gw * xh[i].w);
       }
@@ -338,11 +345,16 @@ __global__ void __launch_bounds__(LNB_THREADS, 1) ln_bwd_kernel(const LnBwdParam
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int c = lane + 32 * i;
+        const float4 gm = s_gamma[c];
+        // residual-stream gradient: read from the stage right before use (keeps 24 registers free)
+        const float4 rs = p.dres_in
+                              ? reinterpret_cast<const float4*>(st + dy_bytes + f_bytes + (size_t)warp * f_row)[c]
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
         float4 dx;
-        dx.x = rstd * (dy[i].x * gm[i].x - c1 - xh[i].x * c2) + rs[i].x;
-        dx.y = rstd * (dy[i].y * gm[i].y - c1 - xh[i].y * c2) + rs[i].y;
-        dx.z = rstd * (dy[i].z * gm[i].z - c1 - xh[i].z * c2) + rs[i].z;
-        dx.w = rstd * (dy[i].w * gm[i].w - c1 - xh[i].w * c2) + rs[i].w;
+        dx.x = rstd * (dy[i].x * gm.x - c1 - xh[i].x * c2) + rs.x;
+        dx.y = rstd * (dy[i].y * gm.y - c1 - xh[i].y * c2) + rs.y;
+        dx.z = rstd * (dy[i].z * gm.z - c1 - xh[i].z * c2) + rs.z;
+        dx.w = rstd * (dy[i].w * gm.w - c1 - xh[i].w * c2) + rs.w;
         ag[i].x += dy[i].x * xh[i].x; ag[i].y += dy[i].y * xh[i].y; ag[i].z += dy[i].z * xh[i].z; ag[i].w += dy[i].w * xh[i].w;
         ab[i].x += dy[i].x; ab[i].y += dy[i].y; ab[i].z += dy[i].z; ab[i].w += dy[i].w;
         if (p.dx_out) reinterpret_cast<float4*>(p.dx_out + off)[c] = dx;
@@ -360,12 +372,14 @@ __global__ void __launch_bounds__(LNB_THREADS, 1) ln_bwd_kernel(const LnBwdParam
           }
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + 64 + 8 * s);  // every read of this stage is done: slot may be refilled
     }
   }
   // ---- column sums: 8 warps -> smem (the ring is drained) -> one atomic per column per CTA ----
   __syncthreads();
   float* red = reinterpret_cast<float*>(ring);  // [3][LNB_ROWS][H]
-  if (warp < LNB_ROWS) {
+  {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       reinterpret_cast<float4*>(red + ((size_t)0 * LNB_ROWS + warp) * H)[lane + 32 * i] = ag[i];
@@ -640,15 +654,15 @@ extern "C" int ergm_ln_bwd(const void* dy, int dy_is_f32, const float* x, const 
       (dres_in && (reinterpret_cast<uintptr_t>(dres_in) & 15)))
     return ERGM_ERR_ARG;
   const int stage_bytes = LNB_ROWS * H * ((dy_is_f32 ? 4 : 2) + 4 + (dres_in ? 4 : 0));
-  int stages = (232448 - 128) / stage_bytes;
+  int stages = (232448 - 128 - H * 4) / stage_bytes;
   if (stages > 4) stages = 4;
   const int n_tiles = (rows + LNB_ROWS - 1) / LNB_ROWS;
   int grid = n_tiles < num_sms() ? n_tiles : num_sms();
   const int per_cta = (n_tiles + grid - 1) / grid;
   if (stages > per_cta) stages = per_cta;
   if (stages < 1) return ERGM_ERR_UNSUPPORTED;
-  int smem = 128 + stages * stage_bytes;
-  const int red_bytes = 128 + 3 * LNB_ROWS * H * 4;  // column-sum reduction reuses the ring
+  int smem = 128 + H * 4 + stages * stage_bytes;
+  const int red_bytes = 128 + H * 4 + 3 * LNB_ROWS * H * 4;  // column-sum reduction reuses the ring
   if (smem < red_bytes) smem = red_bytes;
   if (smem > 232448) return ERGM_ERR_UNSUPPORTED;
   auto launch = [&](auto kern) -> int {
