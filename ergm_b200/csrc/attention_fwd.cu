@@ -108,6 +108,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const uint32_t tS = tmem, tP = tmem + 128, tO = tmem + 192;
   TRACE(1);
 
+  // Register reallocation between the warpgroups (setmaxnreg): the kernel is compiled for 80 registers per thread
+  // (two CTAs per SM); the helper warpgroup (TMA / MMA issue / TMEM allocation) gives most of its share to the
+  // two softmax warpgroups, whose per-row state (o[32] + a 32-column S chunk + its exponentials) spilled at 80.
+#ifdef ERGM_ATTN_SETMAXNREG
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+  }
+#endif
   if (warp == 0) {
     if (lane == 0) {
       for (int j = 1; j < n_kv; ++j) {
@@ -181,18 +191,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       TRACE(3 + 8 * j);
       float mx = -INFINITY;
 #pragma unroll
-      for (int cc = 0; cc < 64; cc += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tS_mine + cc, v);
+      for (int cc = 0; cc < 64; cc += 16) {  // 16-column chunks: half the live registers of a 32-column one
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(tS_mine + cc, v);
         tmem_ld_wait();
         float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         if (need_mask) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
+          for (int i = 0; i < 16; ++i)
             if (k0 + cc + i <= vis) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[i]));
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[i]));
+          for (int i = 0; i < 16; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[i]));
         }
         mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
       }
@@ -208,37 +218,37 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       float s4[4] = {0.f, 0.f, 0.f, 0.f};
       TRACE(5 + 8 * j);
 #pragma unroll
-      for (int cc = 0; cc < 64; cc += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tS_mine + cc, v);
+      for (int cc = 0; cc < 64; cc += 16) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(tS_mine + cc, v);
         tmem_ld_wait();
-        float pr[32];
+        float pr[16];
         if (need_mask) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
+          for (int i = 0; i < 16; ++i) {
             const float e = ex2_fast(fmaf(__uint_as_float(v[i]), c, -mc));
             pr[i] = (k0 + cc + i <= vis) ? e : 0.f;
             s4[i & 3] += pr[i];
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
+          for (int i = 0; i < 16; ++i) {
             pr[i] = ex2_fast(fmaf(__uint_as_float(v[i]), c, -mc));
             s4[i & 3] += pr[i];
           }
         }
         if (p.do_drop) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
+          for (int i = 0; i < 16; i += 2) {
             const uint32_t hsh = p.drop.hash2(drop_row, (uint32_t)(k0 + cc + i) >> 1);
             pr[i] = ((hsh & 0xffffu) >= thr16) ? pr[i] * keep_scale : 0.f;
             pr[i + 1] = ((hsh >> 16) >= thr16) ? pr[i + 1] * keep_scale : 0.f;
           }
         }
-        uint32_t pk[16];
+        uint32_t pk[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(pr[2 * i], pr[2 * i + 1]);
-        tmem_st_32x32b_x16(tP_mine + (cc >> 1), pk);   // 32 keys -> 16 packed columns
+        for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(pr[2 * i], pr[2 * i + 1]);
+        tmem_st_32x32b_x8(tP_mine + (cc >> 1), pk);   // 16 keys -> 8 packed columns
       }
       l = l * alpha + ((s4[0] + s4[1]) + (s4[2] + s4[3]));
       m = m_new;
