@@ -57,6 +57,8 @@ class Engine:
         self.seed = 0x5EED
         self.site_counter = 0
         self.rng_step = None
+        self._wgrad_side = None   # set per backward: side stream for the weight-gradient GEMMs
+        self._side_ev = None
         self._index()
 
     # ------------------------------------------------------------------
@@ -125,8 +127,7 @@ class Engine:
         # out[M, N_out] = dy[M, K_red] @ W[N_out, K_red]^T   (W is Conv1D [in=N_out, out=K_red])
         ops.gemm(dy, w_b, out, M=M, N=N_out, K=K_red, a_major=K_MAJOR, b_major=K_MAJOR, **kw)
 
-    @staticmethod
-    def _wgrad_gemm(x, dy, dw, K_in, N_out, M_red):
+    def _wgrad_gemm(self, x, dy, dw, K_in, N_out, M_red):
         # dw[K_in, N_out] += x[M_red, K_in]^T @ dy[M_red, N_out]
         # 128x256 tiles, K (= tokens) split so that tiles * splits fills the 148 SMs once
         # (measured, profiles/r1_gemm_epilogue.md: 768x3072 44.1 -> 32.4 us, 768x768 15.1 -> 12.9 us
@@ -134,8 +135,33 @@ class Engine:
         bn = 256 if N_out >= 256 else 128
         tiles = ((K_in + 127) // 128) * ((N_out + bn - 1) // bn)
         split = max(1, min(16, 148 // tiles))
-        ops.gemm(x, dy, dw, M=K_in, N=N_out, K=M_red, a_major=MN_MAJOR, b_major=MN_MAJOR,
-                 epilogue=L.EPI_ATOMIC, split_k=split, block_n=bn)
+
+        def launch():
+            ops.gemm(x, dy, dw, M=K_in, N=N_out, K=M_red, a_major=MN_MAJOR, b_major=MN_MAJOR,
+                     epilogue=L.EPI_ATOMIC, split_k=split, block_n=bn)
+
+        side = self._wgrad_side
+        if side is None:
+            launch()
+            return
+        # Weight gradients are off the critical path (nothing in this backward reads them): they go to a side
+        # stream, where their CTAs fill the SMs that the 1.3-2.6-wave GEMMs / attention kernels of the main
+        # chain leave idle in their last wave.  dy is ready on the main stream now; the main stream waits for
+        # the side stream (_side_join) before it overwrites any dy buffer.
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        side.wait_event(ev)
+        with torch.cuda.stream(side):
+            launch()
+            self._side_ev = torch.cuda.Event()
+            self._side_ev.record(side)
+
+    def _side_join(self):
+        """Main stream waits for every weight-gradient GEMM issued so far."""
+        if self._wgrad_side is not None and self._side_ev is not None:
+            torch.cuda.current_stream().wait_event(self._side_ev)
+            self._side_ev = None
 
     # ------------------------------------------------------------------
     def forward(self, input_ids, token_type_ids=None, labels=None, emotion_labels=None, imgs=None, auds=None,
@@ -484,6 +510,14 @@ class Engine:
         pd_embd, pd_attn, pd_res = sv["pd"]
         if not accumulate:
             self.store.grad.zero_()
+        import os
+        if os.environ.get("ERGM_WGRAD_STREAM", "1") != "0":
+            if self.__dict__.get("_side_stream_obj") is None:
+                self._side_stream_obj = torch.cuda.Stream(device=self.device)
+            self._wgrad_side = self._side_stream_obj
+        else:
+            self._wgrad_side = None
+        self._side_ev = None
         losses = sv["losses"]
         scales = ws.get("bwd_scales", (2,), f32)
         ops.scalar_mul(grad_loss, losses[3:4], scales[0:1])  # dL/d(row loss) = g / n_valid
@@ -542,6 +576,7 @@ class Engine:
             self._dgrad_gemm(dI, self.pb(pfx + "mlp.c_fc.weight"), dH, M, H, I)
             x_in = r["x2"] if has_x else r["x1"]
             nb = pfx + ("crossattention.c_proj.bias" if has_x else "attn.c_proj.bias")
+            self._side_join()  # dxb is about to be overwritten
             ops.ln_bwd(dH, x_in, r["mean3"], r["rstd3"], self.p(pfx + "ln_2.weight"), dx, dx, dxb,
                        self.pg(pfx + "ln_2.weight"), self.pg(pfx + "ln_2.bias"), self.pg(nb), dropout_p=pd_res,
                        seed=seed, offset=s_res2 if has_x else s_res1)
@@ -550,6 +585,7 @@ class Engine:
                 self._wgrad_gemm(r["ctx2"], dxb, self.pg(pfx + "crossattention.c_proj.weight"), H, H, M)
                 self._dgrad_gemm(dxb, self.pb(pfx + "crossattention.c_proj.weight"), dH, M, H, H)
                 dq_acc.zero_()
+                self._side_join()  # dkv2 is about to be overwritten
                 gbx = self.pg(pfx + "crossattention.c_attn.bias")  # K / V bias gradients come out of attn_bwd
                 ops.attn_bwd(r["q2"], r["kv2"], r["kv2"], r["ctx2"], dH, r["lse2"], delta, dq_acc, dkv2, dkv2,
                              B=B, nh=nh, Tq=T, Tk=Tc, q_col0=0, k_col0=0, v_col0=H, dk_col0=0, dv_col0=H,
@@ -562,6 +598,7 @@ class Engine:
                 # d enc accumulates over layers (the caption embeddings feed every block, model.py:521)
                 self._dgrad_gemm(dkv2, self.pb(pfx + "crossattention.c_attn.weight"), denc, Mc, H, 2 * H,
                                  residual=denc)
+                self._side_join()
                 ops.ln_bwd(dH, r["x1"], r["mean2"], r["rstd2"], self.p(pfx + "ln_cross_attn.weight"), dx, dx, dxb,
                            self.pg(pfx + "ln_cross_attn.weight"), self.pg(pfx + "ln_cross_attn.bias"),
                            self.pg(pfx + "attn.c_proj.bias"), dropout_p=pd_res, seed=seed, offset=s_res1)
@@ -569,6 +606,7 @@ class Engine:
             self._wgrad_gemm(r["ctx"], dxb, self.pg(pfx + "attn.c_proj.weight"), H, H, M)
             self._dgrad_gemm(dxb, self.pb(pfx + "attn.c_proj.weight"), dH, M, H, H)
             dq_acc.zero_()
+            self._side_join()  # dqkv is about to be overwritten
             qkv = r["qkv"]
             gb = self.pg(pfx + "attn.c_attn.bias")
             ops.attn_bwd(qkv, qkv, qkv, r["ctx"], dH, r["lse1"], delta, dq_acc, dqkv, dqkv, B=B, nh=nh, Tq=T, Tk=T,
@@ -578,6 +616,7 @@ class Engine:
             ops.cast_f32_bf16_2d(dq_acc, dqkv[:, :H], gb[:H])
             self._wgrad_gemm(r["a1"], dqkv, self.pg(pfx + "attn.c_attn.weight"), H, 3 * H, M)
             self._dgrad_gemm(dqkv, self.pb(pfx + "attn.c_attn.weight"), dH, M, H, 3 * H)
+            self._side_join()
             if l > 0:
                 prev = "transformer.h.%d." % (l - 1)
                 ops.ln_bwd(dH, r["x"], r["mean1"], r["rstd1"], self.p(pfx + "ln_1.weight"), dx, dx, dxb,
@@ -608,6 +647,8 @@ class Engine:
                      epilogue=L.EPI_ATOMIC, block_n=128)
         if denc is not None:
             ops.embed_bwd(denc, sv["cap"], None, None, self.pg("transformer.wte.weight"), None, T=Tc)
+        self._side_join()
+        self._wgrad_side = None
         if on_layer_done is not None:
             on_layer_done(-1)
         skip = () if sv["enc"] is not None else ("crossattention.", "ln_cross_attn.")
