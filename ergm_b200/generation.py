@@ -8,6 +8,8 @@ step: embed -> L x [LN, QKV GEMM, paged one-query attention (+append), proj GEMM
 -> ln_f -> LM head on B rows -> on-device arg-max / top-k sampling.  No host synchronisation
 happens until the generated ids are read back.
 """
+import os
+
 import torch
 
 from . import _lib as L
@@ -101,7 +103,6 @@ def mega_table(eng, st):
 
 
 def mega_supported(eng, B):
-    import os
     # opt-in: measured 576-660 us / step against 533 us for the launch chain (profiles/r1_decode.md) - the
     # in-kernel attention phase (4 groups per CTA, two rounds) and the 60 grid barriers still cost more than
     # they save

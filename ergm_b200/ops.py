@@ -1,7 +1,9 @@
-"""Thin Python wrappers (raw pointers in, nothing returned) around the C ABI.
+"""Thin Python wrappers (raw pointers in, nothing returned) around the C ABI of include/ergm_b200.h.
 
-These are *not* autograd aware; `ergm_b200.functional` builds the
-torch.autograd.Functions on top of them.
+One function per entry point; they are not autograd aware - ergm_b200.engine composes them into the
+forward and the hand-written backward, and ergm_b200.model hooks that backward into loss.backward().
+Every call counts its kernel launches (bench.py's gpu_launches) and, when ops.PROFILE is a list, brackets
+itself with CUDA events on the current stream.
 """
 import ctypes
 

@@ -52,6 +52,16 @@ def test_argument_errors_without_gpu(lib):
     assert lib.ergm_gemm_bf16(ctypes.byref(a), None) == -1  # null operands -> ERGM_ERR_ARG, nothing launched
     assert lib.ergm_ln_fwd(None, None, None, None, None, None, None, 4, 128, 1e-5, None, None) == -1
     assert lib.ergm_attn_fwd(1, 8, 0, 1, 8, 0, 1, 8, 0, 1, 8, None, None, None, 1, 1, 8, 8, 32, 1, 0, 0.0, 0, 0, None) == -2
+    # decode-side entry points: argument errors are detected before anything touches a device
+    assert lib.ergm_dec_pack_weight(None, 768, 768, 768, 0, None, None, None, None, None, None) == -1
+    assert lib.ergm_dec_gemm(None, None, 768, 1e-5, None, 768, 768, None, None, 768, 0, 0, 64, None) == -1
+    assert lib.ergm_dec_gemm(8, None, 768, 1e-5, 16, 768, 768, None, 16, 768, 0, 0, 65, None) == -2   # M > 64
+    assert lib.ergm_dec_gemm(8, None, 768, 1e-5, 16, 768, 768, None, 16, 768, 2, 1, 64, None) == -1   # gelu with "+="
+    assert lib.ergm_mm_pool_fwd(None, 0, 0, None, 4, 113, 768, None, 0, None, 0, None) == -1
+    assert lib.ergm_mm_pool_fwd(16, 768 * 113, 768, None, 4, 113, 770, 16, 768, None, 0, None) == -1  # D % 4
+    assert lib.ergm_sample(16, 50304, 4, 50260, 5, 0.8, 1.0, 0, None, 0, None, 0, None, None, None, -1, None) == -1  # top-k AND top-p
+    assert lib.ergm_sample(16, 50304, 4, 50260, 0, 0.0, 1.0, 0, None, 0, None, 0, None, None, None, -1, None) == -1  # top_p <= 0
+    assert lib.ergm_decode_layers(None, 12, 768, 3072, 12, 64, None, None, None, None, None, None, None, 12, 0, 1e-5, None, None) == -1
 
 
 def test_model_tree_matches_reference_keys():

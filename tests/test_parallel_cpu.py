@@ -114,3 +114,30 @@ def test_world2_gloo_global_mean_and_gather():
         assert exact, "global mean from all-reduced sums must equal the concatenated-batch mean"
         assert ok_gather and ok_bucket
     assert any(r[2] for r in res)
+
+
+def test_last_bucket_is_the_embedding_bucket():
+    """DataParallel defers the LAST bucket (wte + wpe, final only after the embedding backward) and runs
+    AdamW on everything behind split_point() meanwhile: the plan must put exactly the embedding range last."""
+    from ergm_b200.parallel import plan_buckets
+    entries, off = {}, 0
+
+    def add(name, n):
+        nonlocal off
+        entries[name] = (off, n, (n,))
+        off += (n + 63) // 64 * 64
+
+    add("transformer.wte.weight", 1000 * 64)
+    add("transformer.wpe.weight", 100 * 64)
+    for l in range(4):
+        add("transformer.h.%d.ln_1.weight" % l, 64)
+        add("transformer.h.%d.mlp.c_fc.weight" % l, 64 * 256)
+    add("transformer.ln_f.weight", 64)
+    add("emotion_head.weight", 7 * 64)
+    for mb in (0.001, 0.05, 128):
+        b = plan_buckets(entries, 4, int(mb * (1 << 20)))
+        trig, lo, hi = b[-1]
+        assert trig == -1 and lo == 0 and hi == entries["transformer.h.0.ln_1.weight"][0]
+        covered = sorted((lo, hi) for _, lo, hi in b)
+        assert covered[0][0] == 0 and covered[-1][1] == off
+        assert all(covered[i][1] == covered[i + 1][0] for i in range(len(covered) - 1))
