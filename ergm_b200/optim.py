@@ -71,16 +71,66 @@ class FusedAdamW:
         self.load_hyper()
         self.apply()
 
+    # -- checkpoint surface: the layout of torch.optim.AdamW.state_dict(), which is what the reference stores in
+    #    ckpt["optim_state_dict"] (main.py:103-110, 184-196), so its checkpoints resume here and vice versa --------
+    def _param_slices(self):
+        eng, st = self._ensure()
+        out = []
+        for name, p in st.params.items():  # same order as model.parameters() (tied lm_head counted once)
+            o, n, shape = st.entries[name]
+            out.append((o, n, shape))
+        return out
+
     def state_dict(self):
-        return dict(step=self.step_count, m=None if self.state is None else self.state["m"].clone(),
-                    v=None if self.state is None else self.state["v"].clone(), lr=self.lr)
+        slices = self._param_slices()
+        state = {}
+        if self.step_count > 0:
+            for i, (o, n, shape) in enumerate(slices):
+                state[i] = {"step": torch.tensor(float(self.step_count)),
+                            "exp_avg": self.state["m"][o:o + n].view(shape).clone(),
+                            "exp_avg_sq": self.state["v"][o:o + n].view(shape).clone()}
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.weight_decay,
+                 "amsgrad": False, "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
+                 "fused": None, "params": list(range(len(slices)))}
+        if "initial_lr" in self.param_groups[0]:
+            group["initial_lr"] = self.param_groups[0]["initial_lr"]
+        return {"state": state, "param_groups": [group]}
 
     def load_state_dict(self, sd):
-        self._ensure()
-        self.step_count = sd["step"]
-        if sd["m"] is not None:
-            self.state["m"].copy_(sd["m"])
-            self.state["v"].copy_(sd["v"])
+        slices = self._param_slices()
+        if "state" not in sd:  # legacy flat layout written by earlier versions of this class
+            self.step_count = sd["step"]
+            if sd["m"] is not None:
+                self.state["m"].copy_(sd["m"])
+                self.state["v"].copy_(sd["v"])
+            return
+        groups = sd["param_groups"]
+        ids = [i for g in groups for i in g["params"]]
+        if len(ids) != len(slices):
+            raise ValueError("optimizer state has %d parameters, the model has %d" % (len(ids), len(slices)))
+        g0 = groups[0]
+        self.lr, self.betas, self.eps = g0["lr"], tuple(g0["betas"]), g0["eps"]
+        self.weight_decay = g0["weight_decay"]
+        self.param_groups[0]["lr"] = self.lr
+        if "initial_lr" in g0:
+            self.param_groups[0]["initial_lr"] = g0["initial_lr"]
+        self.state["m"].zero_()
+        self.state["v"].zero_()
+        steps = set()
+        for pos, pid in enumerate(ids):
+            ent = sd["state"].get(pid)
+            if ent is None:
+                continue
+            o, n, shape = slices[pos]
+            if tuple(ent["exp_avg"].shape) != tuple(shape):
+                raise ValueError("optimizer state of parameter %d has shape %s, expected %s"
+                                 % (pid, tuple(ent["exp_avg"].shape), tuple(shape)))
+            self.state["m"][o:o + n].copy_(ent["exp_avg"].reshape(-1))
+            self.state["v"][o:o + n].copy_(ent["exp_avg_sq"].reshape(-1))
+            steps.add(int(float(ent["step"])))
+        if len(steps) > 1:
+            raise ValueError("per-parameter step counts differ (%s): the flat optimiser keeps one" % sorted(steps))
+        self.step_count = steps.pop() if steps else 0
 
 
 class PolynomialDecaySchedule:

@@ -347,3 +347,57 @@ def test_odd_shapes_forward_backward(cuda_device, B, T, Tc):
                      "transformer.wpe.weight", "transformer.h.1.ln_2.bias"):
             p = dict(m.named_parameters())[name]
             assert rel(p.grad, sdo[name].grad) < 6e-2, (name, rel(p.grad, sdo[name].grad))
+
+
+def test_optimizer_checkpoint_is_torch_adamw_compatible(cuda_device):
+    """N4: the reference checkpoints torch.optim.AdamW.state_dict() (main.py:103-110,184-196).
+    (a) a torch AdamW state dict loads into FusedAdamW with identical moments / step / hyper-parameters;
+    (b) save -> fresh model + fresh FusedAdamW -> load resumes on the same trajectory as the uninterrupted run;
+    (c) FusedAdamW.state_dict() loads back into torch's AdamW.
+    (A torch step and a fused step agree to 1e-7 in fp32, which is enough to flip single bf16 roundings of the
+    weight shadow, so trajectories are compared fused-vs-fused; the moments are compared exactly.)"""
+    from ergm_b200.optim import FusedAdamW
+    cfg = O.OracleConfig(vocab_size=512, n_positions=64, n_embd=128, n_layer=2, n_head=2)
+    sd = O.init_state_dict(cfg, seed=9, perturb=True)
+    b = synthetic.make_batch(3, 32, seed=10, vocab=cfg.vocab_size, feat_dim=cfg.n_embd)
+    kw = cuda_batch(b)
+
+    def grad_step(m):
+        for p in m.parameters():
+            p.grad = None
+        m(**kw).loss.backward()
+
+    # (a) torch -> fused
+    ref = build_model(cfg, sd).train()
+    opt_ref = FusedAdamW(ref, lr=1e-3)
+    m = build_model(cfg, sd).train()
+    topt = torch.optim.AdamW(m.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+    grad_step(ref)
+    grad_step(m)
+    opt_ref.step()
+    topt.step()
+    fopt = FusedAdamW(m, lr=123.0)           # wrong on purpose: everything must come from the checkpoint
+    fopt.load_state_dict(topt.state_dict())
+    assert fopt.step_count == 1 and abs(fopt.lr - 1e-3) < 1e-12 and fopt.weight_decay == 0.01
+    assert (fopt.state["m"] - opt_ref.state["m"]).abs().max().item() < 1e-6
+    assert (fopt.state["v"] - opt_ref.state["v"]).abs().max().item() < 1e-6
+    assert max((p.detach() - q.detach()).abs().max().item() for p, q in zip(m.parameters(), ref.parameters())) < 1e-6
+    # (b) fused -> checkpoint -> fresh model / optimiser -> same trajectory
+    ckpt = {"model_state_dict": {k: v.detach().cpu().clone() for k, v in ref.state_dict().items()},
+            "optim_state_dict": opt_ref.state_dict()}
+    resumed = build_model(cfg, ckpt["model_state_dict"]).train()
+    ropt = FusedAdamW(resumed, lr=7.0)
+    ropt.load_state_dict(ckpt["optim_state_dict"])
+    for _ in range(2):
+        grad_step(ref)
+        opt_ref.step()
+        grad_step(resumed)
+        ropt.step()
+    worst = max((p.detach() - q.detach()).abs().max().item() for p, q in zip(resumed.parameters(), ref.parameters()))
+    assert worst < 1e-5, worst
+    # (c) fused -> torch
+    t2 = torch.optim.AdamW(ref.parameters(), lr=5.0)
+    t2.load_state_dict(opt_ref.state_dict())
+    assert abs(t2.param_groups[0]["lr"] - 1e-3) < 1e-12
+    st0 = t2.state[t2.param_groups[0]["params"][0]]
+    assert int(st0["step"]) == 3 and st0["exp_avg"].shape == next(ref.parameters()).shape
