@@ -25,6 +25,7 @@ constexpr int MG_THREADS = 512;
 constexpr int MG_M = 64;
 constexpr int MG_MAX_STAGES = 4;
 constexpr int MG_PAGE = 16;
+constexpr int MG_UNR = 4;   // tokens per 8-lane group per pass (8 spilled at the 128-register cap of 512 threads)
 
 struct MegaLayer {  // one per transformer block, device resident (built once per generation batch)
   const __nv_bfloat16* w_qkv; const float* b_qkv;  // ln_1 folded in
@@ -361,19 +362,19 @@ ERGM_DEVINL void mg_attention(const MegaParams& p, unsigned char* smem, const __
     }
     float m_run = -INFINITY, l_run = 0.f;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int tb = 0; tb < n_old; tb += 16 * 8) {
-      uint4 kk[8], vv[8];
+    for (int tb = 0; tb < n_old; tb += 16 * MG_UNR) {
+      uint4 kk[MG_UNR], vv[MG_UNR];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < MG_UNR; ++u) {
         const int tok = tb + u * 16 + grp;
         const bool ok = tok < n_old;
         kk[u] = ok ? *kv_row(tok, 0) : make_uint4(0u, 0u, 0u, 0u);
         vv[u] = ok ? *kv_row(tok, 1) : make_uint4(0u, 0u, 0u, 0u);
       }
-      float sc[8];
+      float sc[MG_UNR];
       float m_new = m_run;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < MG_UNR; ++u) {
         float s = mg_dot8(qv, kk[u]);
         s += __shfl_xor_sync(0xffffffffu, s, 4);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
@@ -387,7 +388,7 @@ ERGM_DEVINL void mg_attention(const MegaParams& p, unsigned char* smem, const __
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] *= corr;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < MG_UNR; ++u) {
           const float w = __expf(sc[u] - m_new);
           l_run += w;
           const float2 v0 = unpack_bf16x2(vv[u].x), v1 = unpack_bf16x2(vv[u].y), v2 = unpack_bf16x2(vv[u].z),
