@@ -117,7 +117,7 @@ def build(device, n_layer=12, n_embd=768, n_head=12, dropout=0.1, seed=0, feat_d
 
 
 def host_batch(B, T, seed, pin=True, sequences=False, kf=1):
-    from oracle import synthetic
+    from ergm_b200 import synthetic
     b = synthetic.make_batch(B, T, seed=seed, kf=kf)
     out = {k: b[k] for k in ("input_ids", "token_type_ids", "labels", "emotion_labels", "caption_ids", "imgs", "auds")}
     if sequences:  # [B, 197*kf, 768] key-frame features, [B, 113, 768] audio features (text_feature.py:44,49)
@@ -133,7 +133,7 @@ def cpu_reference_run(steps, warmup, B=2, T=SEQ, threads=None):
     """fwd + bwd + AdamW of the oracle port on the host cores (fp32, dropout omitted: the oracle is the
     p=0 / eval restatement; dropout is <1% of CPU time).  Returns (tokens/s, ms/step, threads)."""
     from oracle import ergm_oracle as O
-    from oracle import synthetic
+    from ergm_b200 import synthetic
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
     cfg = O.OracleConfig()
@@ -176,7 +176,7 @@ def run_reference_arm(args, rank):
 
 def bench_generation(model, device, B=64, prompt=128, new=64, reps=3):
     """BASELINE config 4: greedy decode, ragged prompts 64..128, 64 new tokens, paged KV."""
-    from oracle import synthetic
+    from ergm_b200 import synthetic
     from ergm_b200 import generation
     g = torch.Generator().manual_seed(7)
     b = synthetic.make_batch(B, prompt, seed=99, ragged=False)

@@ -18,5 +18,12 @@ extern "C" int ergm_rng_step_advance(uint64_t* dev_ptr, uint64_t inc, void* stre
   return (int)cudaGetLastError();
 }
 
-extern "C" int ergm_abi_version(void) { return 1; }
+namespace ergm { void tmap_cache_stats(uint64_t* hits, uint64_t* misses); }
+extern "C" int ergm_tmap_cache_stats(uint64_t* hits, uint64_t* misses) {
+  if (!hits || !misses) return ERGM_ERR_ARG;
+  ergm::tmap_cache_stats(hits, misses);
+  return ERGM_OK;
+}
+
+extern "C" int ergm_abi_version(void) { return 2; }
 extern "C" int ergm_device_sm_count(void) { return ergm::num_sms(); }

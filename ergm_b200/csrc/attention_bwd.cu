@@ -415,12 +415,8 @@ extern "C" int ergm_attn_bwd(const void* q, int64_t ld_q, int q_col0, const void
   p.scale = 1.0f / sqrtf((float)head_dim);
   p.drop = make_site(seed, offset, dropout_p, (uint32_t)Tk);
   p.do_drop = dropout_p > 0.f;
-  static bool attr = false;
-  if (!attr) {
-    ERGM_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
-    ERGM_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
-    attr = true;
-  }
+  ERGM_SET_SMEM_ATTR(attn_bwd_kernel<true>, AB_SMEM);
+  ERGM_SET_SMEM_ATTR(attn_bwd_kernel<false>, AB_SMEM);
   dim3 grid(B, nh, (Tk + 127) / 128);
   if (causal)
     attn_bwd_kernel<true><<<grid, AB_THREADS, AB_SMEM, s>>>(tq, tk, tv, tdo, p);

@@ -23,12 +23,6 @@
 
 namespace ergm {
 
-#ifdef ERGM_TRACE
-__device__ long long g_attn_trace[64];
-#define TRACE(slot) do { if (blockIdx.z == 0 && blockIdx.y == 0 && blockIdx.x == 0 && trace_thread) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_attn_trace[slot] = t_; } } while (0)
-#else
-#define TRACE(slot) do { } while (0)
-#endif
 
 constexpr int AT_D = 64;
 constexpr int AT_THREADS = 384;
@@ -71,10 +65,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   // first (blockIdx.z is the slowest-varying index of the block scheduler) and the light ones fill the tail
   const int qb = (int)gridDim.z - 1 - (int)blockIdx.z, h = blockIdx.y, b = blockIdx.x;
   const int q0 = qb * 128;
-#ifdef ERGM_TRACE
-  const bool trace_thread = (threadIdx.x == 4 * 32);
-#endif
-  TRACE(0);
   int kv_len = p.Tk;
   if (p.kv_lens) kv_len = min(kv_len, p.kv_lens[b]);
   int n_kv = max(1, (kv_len + 127) / 128);
@@ -106,7 +96,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
   const uint32_t tS = tmem, tP = tmem + 128, tO = tmem + 192;
-  TRACE(1);
 
   // Register reallocation between the warpgroups (setmaxnreg): the kernel is compiled for 80 registers per thread
   // (two CTAs per SM); the helper warpgroup (TMA / MMA issue / TMEM allocation) gives most of its share to the
@@ -185,10 +174,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       // warp-uniform: does any row of this warp need masking in this block?
       const bool need_mask = (j * 128 + 127 > kv_len - 1) ||
                              (CAUSAL && (j * 128 + 127 > q0 + (warp & 3) * 32 + p.causal_off));
-      TRACE(2 + 8 * j);
       mbar_wait(bar_s, j & 1);
       tc_fence_after();
-      TRACE(3 + 8 * j);
       float mx = -INFINITY;
 #pragma unroll
       for (int cc = 0; cc < 64; cc += 16) {  // 16-column chunks: half the live registers of a 32-column one
@@ -206,7 +193,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
       }
-      TRACE(4 + 8 * j);
       asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch_mine), "f"(mx) : "memory");
       asm volatile("bar.sync 1, 256;" ::: "memory");
       float mo;
@@ -216,7 +202,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const float alpha = ex2_fast((m - m_use) * c);  // m = -inf -> 0
       const float mc = m_use * c;
       float s4[4] = {0.f, 0.f, 0.f, 0.f};
-      TRACE(5 + 8 * j);
 #pragma unroll
       for (int cc = 0; cc < 64; cc += 16) {
         uint32_t v[16];
@@ -253,13 +238,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       l = l * alpha + ((s4[0] + s4[1]) + (s4[2] + s4[3]));
       m = m_new;
       tmem_st_wait();
-      TRACE(6 + 8 * j);
       tc_fence_before();
       mbar_arrive(bar_p);
-      TRACE(7 + 8 * j);
       mbar_wait(bar_o, j & 1);
       tc_fence_after();
-      TRACE(8 + 8 * j);
       {
         uint32_t v[32];
         tmem_ld_32x32b_x32(tO_mine, v);
@@ -268,7 +250,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], alpha, __uint_as_float(v[i]));
       }
       tc_fence_before();
-      TRACE(9 + 8 * j);
     }
     // combine the two half-row sums
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch_mine), "f"(l) : "memory");
@@ -295,20 +276,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         p.lse[((int64_t)b * p.nh + h) * p.Tq + qi] = (m == -INFINITY ? 0.f : m) * p.scale + logf(l);
     }
   }
-  TRACE(40);
   tc_fence_before();
   __syncthreads();
-  TRACE(41);
   if (warp == 2) tmem_dealloc(tmem, 256);
 }
 
 }  // namespace ergm
 
-#ifdef ERGM_TRACE
-extern "C" int ergm_debug_attn_trace(long long* host_out) {
-  return (int)cudaMemcpyFromSymbol(host_out, ergm::g_attn_trace, sizeof(long long) * 64);
-}
-#endif
 
 using namespace ergm;
 
@@ -341,16 +315,21 @@ extern "C" int ergm_attn_fwd(const void* q, int64_t ld_q, int q_col0, const void
   p.scale = 1.0f / sqrtf((float)head_dim);
   p.drop = make_site(seed, offset, dropout_p, (uint32_t)Tk);
   p.do_drop = dropout_p > 0.f;
-  static bool attr = false;
-  if (!attr) {
-    ERGM_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-    ERGM_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-    // two CTAs per SM need 2 x 83 KB of shared memory: ask for the maximum shared-memory carve-out
-    ERGM_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                       cudaSharedmemCarveoutMaxShared));
-    ERGM_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                       cudaSharedmemCarveoutMaxShared));
-    attr = true;
+  {
+    static std::atomic<uint64_t> done_mask{0};
+    int dev = 0;
+    ERGM_CUDA_TRY(cudaGetDevice(&dev));
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(done_mask.load(std::memory_order_acquire) & bit)) {
+      ERGM_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+      ERGM_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+      // two CTAs per SM need 2 x 83 KB of shared memory: ask for the maximum shared-memory carve-out
+      ERGM_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         cudaSharedmemCarveoutMaxShared));
+      ERGM_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         cudaSharedmemCarveoutMaxShared));
+      done_mask.fetch_or(bit, std::memory_order_release);
+    }
   }
   dim3 grid(B, nh, (Tq + 127) / 128);
   if (causal)

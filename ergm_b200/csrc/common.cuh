@@ -7,6 +7,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 
 #define ERGM_DEVINL __device__ __forceinline__
 
@@ -371,6 +372,20 @@ ERGM_DEVINL float warp_max(float v) {
   do {                                        \
     cudaError_t _e = (expr);                  \
     if (_e != cudaSuccess) return (int)_e;    \
+  } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per function AND per device: remember which devices
+// have it in an atomic bit mask (two host threads racing here both set the same value: harmless).
+#define ERGM_SET_SMEM_ATTR(kernel, bytes)                                                              \
+  do {                                                                                                 \
+    static std::atomic<uint64_t> _done_mask{0};                                                        \
+    int _dev = 0;                                                                                      \
+    ERGM_CUDA_TRY(cudaGetDevice(&_dev));                                                               \
+    const uint64_t _bit = 1ull << (_dev & 63);                                                         \
+    if (!(_done_mask.load(std::memory_order_acquire) & _bit)) {                                        \
+      ERGM_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); \
+      _done_mask.fetch_or(_bit, std::memory_order_release);                                            \
+    }                                                                                                  \
   } while (0)
 
 namespace ergm {

@@ -620,8 +620,11 @@ extern "C" int ergm_sample(const float* logits, int64_t ld, int B, int V, int to
                            float temperature, uint64_t seed, int* step_ptr, int advance_step, int64_t* out_ids,
                            int64_t out_ld, int64_t* next_ids, int* finished, int* seq_lens,
                            int64_t eos_id, void* stream) {
-  if (!logits || B <= 0 || V <= 0 || top_k < 0 || top_k > SMP_MAX_K) return ERGM_ERR_ARG;
-  const bool nucleus = top_p < 1.0f;
+  if (!logits || B <= 0 || V <= 0 || top_k < -1 || top_k > SMP_MAX_K) return ERGM_ERR_ARG;
+  // top_k == -1 (ERGM_SAMPLE_ALL): multinomial over the whole distribution = the nucleus kernel at top_p = 1
+  const bool all = top_k == -1;
+  if (all) { top_k = 0; if (top_p > 1.0f) top_p = 1.0f; }
+  const bool nucleus = top_p < 1.0f || all;
   if (nucleus && (!(top_p > 0.f) || top_k > 1)) return ERGM_ERR_ARG;  // top-k and top-p are alternatives
   if ((top_k > 1 || nucleus) && !(temperature > 0.f)) return ERGM_ERR_ARG;
   if (advance_step && !step_ptr) return ERGM_ERR_ARG;
@@ -633,11 +636,7 @@ extern "C" int ergm_sample(const float* logits, int64_t ld, int B, int V, int to
   if (nucleus) {
     const size_t smem = (size_t)V * 4;
     if (smem > 220 * 1024) return ERGM_ERR_UNSUPPORTED;
-    static bool attr_set = false;
-    if (!attr_set) {
-      ERGM_CUDA_TRY(cudaFuncSetAttribute(nucleus_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-      attr_set = true;
-    }
+    ERGM_SET_SMEM_ATTR(nucleus_kernel, 220 * 1024);
     return (int)launch_pdl(nucleus_kernel, dim3((unsigned)B), dim3(NUC_THREADS), smem, st, 1, p);
   }
   if (top_k <= 1) return (int)launch_pdl(argmax_kernel, dim3((unsigned)B), dim3(AMX_THREADS), 0, st, 1, p);

@@ -377,11 +377,7 @@ static int ln_cluster_and_ctas(int smem, int want_ctas, int* cluster_out) {
 
 template <int NV, int KS>
 static int launch_dec_gemm(DecGemmParams& p, dim3 grid, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    ERGM_CUDA_TRY(cudaFuncSetAttribute(dec_gemm_kernel<NV, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_set = true;
-  }
+  ERGM_SET_SMEM_ATTR((dec_gemm_kernel<NV, KS>), 232448);
   const int threads = NV > 0 ? 512 : 256;
   const int a_bytes = DG_M * (p.KBc * 32 + 16);
   const int red_bytes = (threads / 32) * 2048;

@@ -557,11 +557,7 @@ extern "C" int ergm_decode_layers(const void* layer_table, int L, int H, int I, 
   ERGM_CUDA_TRY(cudaMemsetAsync(sync_ctr, 0, sizeof(unsigned int), st));
   void* args[] = {(void*)&p};
   auto launch = [&](auto kern) -> int {
-    static bool attr_set = false;
-    if (!attr_set) {
-      ERGM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-      attr_set = true;
-    }
+    ERGM_SET_SMEM_ATTR(kern, 232448);
     return (int)cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)grid), dim3(MG_THREADS), args, smem, st);
   };
   switch (H / 128) {

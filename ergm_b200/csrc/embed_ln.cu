@@ -44,7 +44,11 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) embed_fuse_fwd_kernel(const Em
     const int64_t pos = p.pos_ids ? p.pos_ids[b * p.pos_stride_b + t]
                                   : (int64_t)((p.past_lens ? p.past_lens[b] : p.past_len) + t);
     if (id < 0 || id >= p.vocab || pos < 0 || pos >= p.n_pos || (p.tts && (tt < 0 || tt >= p.vocab))) {
+      // the reference raises IndexError / a device assert here; we flag (checked by the host after the step)
+      // and leave a defined (zero) row behind instead of stale workspace contents
       if (lane == 0) *p.err_flag = 1;
+      float4* oz = reinterpret_cast<float4*>(p.out + (int64_t)row * p.H);
+      for (int c = lane; c < p.H / 4; c += 32) oz[c] = make_float4(0.f, 0.f, 0.f, 0.f);
       continue;
     }
     const float4* we = reinterpret_cast<const float4*>(p.wte + id * p.H);
@@ -77,9 +81,13 @@ gather_rows_bf16_kernel(const int64_t* ids, const float* table, __nv_bfloat16* o
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int row = blockIdx.x * ROW_WARPS + warp; row < rows; row += gridDim.x * ROW_WARPS) {
     const int64_t id = ids[row];
-    if (id < 0 || id >= vocab) { if (lane == 0) *err_flag = 1; continue; }
-    const float4* src = reinterpret_cast<const float4*>(table + id * H);
     uint2* dst = reinterpret_cast<uint2*>(out + (int64_t)row * H);
+    if (id < 0 || id >= vocab) {
+      if (lane == 0) *err_flag = 1;
+      for (int c = lane; c < H / 4; c += 32) dst[c] = make_uint2(0u, 0u);
+      continue;
+    }
+    const float4* src = reinterpret_cast<const float4*>(table + id * H);
     for (int c = lane; c < H / 4; c += 32) {
       const float4 e = __ldg(src + c);
       dst[c] = make_uint2(pack_bf16x2(e.x, e.y), pack_bf16x2(e.z, e.w));
@@ -106,6 +114,8 @@ struct EmbedBwdParams {
   int rows, T, H, past_len, rows_per_cta;
   DropoutSite drop;
   int do_drop;
+  int vocab, n_pos;         // table heights: an index outside [0, height) is skipped and flagged
+  int* err_flag;            // nullable
 };
 
 ERGM_DEVINL void red_add4(float* addr, const float4 v) {
@@ -139,6 +149,15 @@ __global__ void embed_bwd_kernel(const EmbedBwdParams p_in) {
     idx[0] = p.ids ? p.ids[row] : -1;
     idx[1] = p.tts ? p.tts[row] : -1;
     idx[2] = p.dwpe ? (p.pos_ids ? p.pos_ids[(row / p.T) * p.pos_stride_b + t] : (int64_t)(p.past_len + t)) : -1;
+    // never scatter outside the gradient tables (the forward flagged the same row): skip + flag
+    const bool bad0 = p.ids && (idx[0] < 0 || idx[0] >= p.vocab), bad1 = p.tts && (idx[1] < 0 || idx[1] >= p.vocab),
+               bad2 = p.dwpe && (idx[2] < 0 || idx[2] >= p.n_pos);
+    if (bad0 || bad1 || bad2) {
+      if (c == 0 && p.err_flag) *p.err_flag = 1;
+      if (bad0) idx[0] = -1;
+      if (bad1) idx[1] = -1;
+      if (bad2) idx[2] = -1;
+    }
 #pragma unroll
     for (int s = 0; s < 3; ++s) {
       if (!tables[s]) continue;
@@ -617,13 +636,14 @@ extern "C" int ergm_gather_rows_bf16(const int64_t* ids, const float* table, voi
 
 extern "C" int ergm_embed_bwd(const float* dh, const int64_t* ids, const int64_t* token_type_ids,
                               const int64_t* position_ids, int64_t pos_stride_b, float* dwte, float* dwpe, float* dimgs,
-                              float* dauds, int rows, int T, int H, int past_len, float dropout_p,
-                              uint64_t seed, uint64_t offset, void* stream) {
+                              float* dauds, int rows, int T, int H, int past_len, int vocab, int n_pos,
+                              float dropout_p, uint64_t seed, uint64_t offset, int* err_flag, void* stream) {
   if (!dh || rows <= 0 || T <= 0 || H % 128 || H / 4 > 1024) return ERGM_ERR_ARG;
-  if ((ids || token_type_ids) && !dwte) return ERGM_ERR_ARG;
+  if ((ids || token_type_ids) && (!dwte || vocab <= 0)) return ERGM_ERR_ARG;
+  if (dwpe && n_pos <= 0) return ERGM_ERR_ARG;
   EmbedBwdParams p{dh, ids, token_type_ids, position_ids, pos_stride_b, dwte, dwpe, dimgs, dauds, rows, T, H,
                    past_len, 32, make_site(seed, offset, dropout_p, (uint32_t)H),
-                   dropout_p > 0.f};
+                   dropout_p > 0.f, vocab, n_pos, err_flag};
   const int threads = ((H / 4 + 31) / 32) * 32;
   embed_bwd_kernel<<<(rows + 31) / 32, threads, 0, (cudaStream_t)stream>>>(p);
   return (int)cudaGetLastError();

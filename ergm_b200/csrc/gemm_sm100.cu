@@ -17,7 +17,6 @@
 #include "../../include/ergm_b200.h"
 #include "common.cuh"
 #include "dropout.cuh"
-#include <cstdlib>
 
 namespace ergm {
 
@@ -120,13 +119,6 @@ enum { EC_LINEAR = 0, EC_GELU = 1, EC_GELU_GRAD = 2, EC_EXACT = 3 };
 template <int EC>
 ERGM_DEVINL void epilogue_chunk(const GemmParams& p, const EpiFlags& ep, int row0, int col0, bool first_split,
                                 const float (&v)[32], uint32_t stage_smem, int lane) {
-  if (p.epi & (1 << 30)) {  // timing experiment: no global traffic at all
-    float acc = 0.f;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) acc += v[i];
-    if (acc == 123.456f) reinterpret_cast<float*>(p.d)[0] = acc;
-    return;
-  }
   const int c4 = lane & 7;             // float4 column index inside the chunk
   const int rsub = lane >> 3;          // row inside each group of 4
   const int col = col0 + 4 * c4;       // first of this lane's 4 columns
@@ -186,10 +178,6 @@ ERGM_DEVINL void epilogue_chunk(const GemmParams& p, const EpiFlags& ep, int row
       const uint32_t keep = ep.do_drop ? ep.site.keep4((uint32_t)row, (uint32_t)col >> 2) : 0xfu;
       epilogue_tail(p.d, p.preact, p.residual, p.ldd, p.ldr, p.N, p.d_f32, p.epi, keep, ep.keep_scale, row, col,
                     make_float4(x.x + b4.x, x.y + b4.y, x.z + b4.z, x.w + b4.w));
-      continue;
-    }
-    if (p.epi & (1 << 29)) {  // timing experiment: transposition only, no global traffic
-      if (x.x == 123.456f) reinterpret_cast<float*>(p.d)[0] = x.y;
       continue;
     }
     x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
@@ -746,12 +734,7 @@ static int launch_gemm2(const ergm_gemm_args* a, cudaStream_t stream) {
   p.split_k = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   p.dropout_p = a->dropout_p;
   p.site = make_site(a->seed, a->offset, a->dropout_p, (uint32_t)a->N);
-  static bool attr_set = false;
-  if (!attr_set) {
-    ERGM_CUDA_TRY(cudaFuncSetAttribute(gemm2_bf16_kernel<BN, EC, FM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  ERGM_SET_SMEM_ATTR((gemm2_bf16_kernel<BN, EC, FM>), Cfg::SMEM_BYTES);
   const int total = p.m_tiles * p.n_tiles * p.split_k;
   const int max_clusters = num_sms() / 2;
   const int clusters = total < max_clusters ? total : max_clusters;
@@ -804,12 +787,7 @@ static int launch_gemm(const ergm_gemm_args* a, cudaStream_t stream) {
   p.dropout_p = a->dropout_p;
   p.site = make_site(a->seed, a->offset, a->dropout_p, (uint32_t)a->N);
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    ERGM_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_kernel<BN, EC, FM>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  ERGM_SET_SMEM_ATTR((gemm_bf16_kernel<BN, EC, FM>), Cfg::SMEM_BYTES);
   const int total = p.m_tiles * p.n_tiles * p.split_k;
   const int grid = total < num_sms() ? total : num_sms();
   gemm_bf16_kernel<BN, EC, FM><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
@@ -822,6 +800,7 @@ extern "C" int ergm_gemm_bf16(const ergm_gemm_args* a, void* stream) {
   using namespace ergm;
   if (!a || !a->a || !a->b || !a->d) return ERGM_ERR_ARG;
   if (a->M <= 0 || a->N <= 0 || a->K <= 0) return ERGM_ERR_ARG;
+  if (a->epilogue & ~0xff) return ERGM_ERR_ARG;  // only the ERGM_EPI_* bits of the header exist
   if ((a->epilogue & ERGM_EPI_BIAS) && !a->bias) return ERGM_ERR_ARG;
   if ((a->epilogue & ERGM_EPI_RESIDUAL) && !a->residual) return ERGM_ERR_ARG;
   if ((a->epilogue & (ERGM_EPI_PREACT | ERGM_EPI_GELU_GRAD)) && !a->preact) return ERGM_ERR_ARG;
@@ -880,9 +859,8 @@ extern "C" int ergm_gemm_bf16(const ergm_gemm_args* a, void* stream) {
   {
     const int e = a->epilogue;
     const bool f32 = a->d_dtype == ERGM_DT_F32;
-    const char* off = getenv("ERGM_GEMM_FAST_EPI");
     const bool aligned = (reinterpret_cast<uintptr_t>(a->d) & 15) == 0 && a->ldd % (f32 ? 4 : 8) == 0;
-    if (!(off && off[0] == '0') && aligned && bn != 64 && !(bn == 192 && a->N % 192)) {
+    if (aligned && bn != 64 && !(bn == 192 && a->N % 192)) {
       if (!f32 && e == 0) fm = FM_BF16;
       else if (!f32 && e == ERGM_EPI_BIAS) fm = FM_BF16_BIAS;
       else if (!f32 && e == (ERGM_EPI_BIAS | ERGM_EPI_GELU | ERGM_EPI_PREACT) && a->preact) fm = FM_GELU;

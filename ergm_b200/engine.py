@@ -48,10 +48,10 @@ class LayerParams:
 
 
 class Engine:
-    def __init__(self, model):
+    def __init__(self, model, prefix=""):
         self.model = model
         self.cfg = model.config
-        self.store = ParamStore(model)
+        self.store = ParamStore(model, prefix)
         self.device = self.store.device
         self.ws_train = Workspace(self.device)
         self.ws_eval = Workspace(self.device)
@@ -337,6 +337,12 @@ class Engine:
         if save:
             sv.update(xf=x, hn=hn, meanf=meanf, rstdf=rstdf, logits=logits, ce_lse=lse, hlast=hlast,
                       emo_dlog=emo_dlog, losses=losses, ldl=ldl)
+            # One set of saved activations exists (named, reused workspaces): tag it so that a backward through
+            # an OLDER forward - loss = model(a).loss + model(b).loss - fails loudly instead of differentiating
+            # through the wrong activations.
+            self.forward_id = getattr(self, "forward_id", 0) + 1
+            sv["id"] = self.forward_id
+            out["forward_id"] = self.forward_id
             self.saved = sv
         return out
 
@@ -498,13 +504,20 @@ class Engine:
         return feat
 
     # ------------------------------------------------------------------
-    def backward(self, grad_loss, accumulate=False, on_layer_done=None):
+    def backward(self, grad_loss, accumulate=False, on_layer_done=None, forward_id=None):
         """Hand-written backward of the whole path.  grad_loss: device fp32 scalar tensor (dLoss).
         Gradients are accumulated into the flat gradient buffer (zeroed first unless
-        `accumulate`)."""
+        `accumulate`).  forward_id: the tag of the forward this backward belongs to (checked)."""
         sv = self.saved
         if sv is None:
-            raise RuntimeError("backward() without a saved training forward")
+            raise RuntimeError("backward() without a saved training forward (ergm_b200 keeps the activations of "
+                               "ONE training forward per model: each loss must be back-propagated before the "
+                               "next training forward, and only once)")
+        if forward_id is not None and sv["id"] != forward_id:
+            raise RuntimeError("backward() through training forward #%d, but the saved activations belong to the "
+                               "later forward #%d: ergm_b200 keeps one set of saved activations per model - call "
+                               "loss.backward() before the next training forward (accumulate gradients across "
+                               "backward calls instead of summing losses)" % (forward_id, sv["id"]))
         self.saved = None
         cfg, H, nh, Lyr, I, V = self.cfg, self.H, self.nh, self.L, self.I, self.V
         B, T, Tc = sv["B"], sv["T"], sv["Tc"]

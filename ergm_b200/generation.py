@@ -206,6 +206,8 @@ def generate(model, input_ids, token_type_ids=None, max_new_tokens=64, do_sample
         if sp2_id is not None:
             st.tt = torch.full((B, 1), int(sp2_id), dtype=torch.int64, device=dev)
         k = int(top_k) if do_sample else 0
+        if do_sample and k == 0 and top_p >= 1.0:
+            k = -1  # plain multinomial sampling over the whole distribution (ERGM_SAMPLE_ALL), never silently greedy
         sample_kw = dict(top_k=k, top_p=float(top_p) if do_sample else 1.0, temperature=float(temperature), seed=int(seed),
                          eos_id=int(eos_token_id) if eos_token_id is not None else -1)
         # ---- prefill: fused attention over the padded prompts, K/V -> pages, cross K/V cached ----
@@ -273,6 +275,17 @@ def _generate_fp32(model, input_ids, token_type_ids, max_new_tokens, eos_token_i
     return out_ids
 
 
+def legacy_past_to_rows(past_key_values, B, H, dev):
+    """Legacy tuple cache L x (k, v) [B, nh, ctx, 64] (model.py:228-236) -> per layer bf16 [B, ctx, 2H] K|V rows."""
+    past = []
+    for k, v in past_key_values:
+        ctx = k.shape[-2]
+        k2 = k.to(dev).permute(0, 2, 1, 3).reshape(B, ctx, H)
+        v2 = v.to(dev).permute(0, 2, 1, 3).reshape(B, ctx, H)
+        past.append(torch.cat([k2, v2], dim=-1).to(torch.bfloat16).contiguous())
+    return past
+
+
 def legacy_cached_forward(model, input_ids, token_type_ids, pos, past_key_values, attention_mask, caption_ids,
                           use_cache, return_dict):
     """forward(..., past_key_values=tuple) — the reference's own cache surface (model.py:228-236,
@@ -282,12 +295,7 @@ def legacy_cached_forward(model, input_ids, token_type_ids, pos, past_key_values
     dev = eng.device
     B, T = input_ids.shape
     H, nh = eng.H, eng.nh
-    past = []
-    for k, v in past_key_values:
-        ctx = k.shape[-2]
-        k2 = k.to(dev).permute(0, 2, 1, 3).reshape(B, ctx, H)
-        v2 = v.to(dev).permute(0, 2, 1, 3).reshape(B, ctx, H)
-        past.append(torch.cat([k2, v2], dim=-1).to(torch.bfloat16).contiguous())
+    past = legacy_past_to_rows(past_key_values, B, H, dev)
     ctx = past[0].shape[1]
     kv_lens = None
     if attention_mask is not None:

@@ -29,6 +29,7 @@ from transformers.models.gpt2.configuration_gpt2 import GPT2Config
 from transformers.pytorch_utils import Conv1D
 
 from . import _lib as L
+from . import blocks
 from .engine import Engine
 
 NUM_EMOTIONS = 7  # model.py:607
@@ -127,12 +128,16 @@ class GPT2Attention(nn.Module):
             self.c_attn = Conv1D(3 * self.embed_dim, self.embed_dim)
         self.c_proj = Conv1D(self.embed_dim, self.embed_dim)
 
+    forward = blocks.attention_forward  # model.py:200-251 (inference surface; see ergm_b200/blocks.py)
+
 
 class GPT2MLP(nn.Module):
     def __init__(self, intermediate_size, config):
         super().__init__()
         self.c_fc = Conv1D(intermediate_size, config.hidden_size)
         self.c_proj = Conv1D(config.hidden_size, intermediate_size)
+
+    forward = blocks.mlp_forward  # model.py:262-267
 
 
 class GPT2Block(nn.Module):
@@ -147,6 +152,8 @@ class GPT2Block(nn.Module):
         self.crossattention = GPT2Attention(config, is_cross_attention=True, layer_idx=layer_idx)
         self.ln_cross_attn = nn.LayerNorm(hidden_size, eps=config.layer_norm_epsilon)
         self.mlp = GPT2MLP(inner_dim, config)
+
+    forward = blocks.block_forward  # model.py:286-341
 
 
 class GPT2PreTrainedModel(PreTrainedModel):
@@ -181,11 +188,113 @@ class GPT2Model(GPT2PreTrainedModel):
         self.ln_f = nn.LayerNorm(self.embed_dim, eps=config.layer_norm_epsilon)
         self.post_init()
 
+        self._owner = None    # weakref to the GPT2LMHeadModel this backbone belongs to (shares its engine)
+        self._engine = None   # stand-alone backbone: its own engine (parameter names get the "transformer." prefix)
+
     def get_input_embeddings(self):
         return self.wte
 
     def set_input_embeddings(self, new_embeddings):
         self.wte = new_embeddings
+
+    @property
+    def engine(self):
+        owner = self._owner() if self._owner is not None else None
+        if owner is not None:
+            return owner.engine
+        if self._engine is None:
+            dev = self.wte.weight.device
+            if dev.type != "cuda":
+                raise L.ErgmError("ergm_b200 has no CPU path: call .to('cuda') on the model first")
+            with torch.cuda.device(dev):
+                self._engine = Engine(self, prefix="transformer.")
+        return self._engine
+
+    @torch.no_grad()
+    def forward(self, input_ids=None, past_key_values=None, attention_mask=None, token_type_ids=None,
+                position_ids=None, head_mask=None, inputs_embeds=None, encoder_hidden_states=None,
+                encoder_attention_mask=None, use_cache=None, output_attentions=None, output_hidden_states=None,
+                return_dict=None, imgs=None, auds=None, caption_ids=None):
+        """GPT2Model.forward, model.py:420-596: embeddings + fusion, L blocks, ln_f.  Returns
+        BaseModelOutputWithPastAndCrossAttentions(last_hidden_state [B, T, H] fp32, past_key_values) or the tuple
+        form.  Inference surface (no autograd graph): the training path is GPT2LMHeadModel.forward."""
+        if input_ids is not None and inputs_embeds is not None:
+            raise ValueError("You cannot specify both input_ids and inputs_embeds at the same time")
+        if input_ids is None:
+            if inputs_embeds is not None:
+                raise L.ErgmError("inputs_embeds is not supported: the embedding stage is fused (ergm_embed_fuse_fwd)")
+            raise ValueError("You have to specify either input_ids or inputs_embeds")
+        _get_head_mask_check(head_mask)
+        if output_attentions or output_hidden_states:
+            raise L.ErgmError("output_attentions / output_hidden_states are not available: attention probabilities "
+                              "are never materialised by the fused kernels")
+        if encoder_hidden_states is not None:
+            raise L.ErgmError("pass caption_ids (model.py:460-463 embeds them with wte), not encoder_hidden_states")
+        return_dict = return_dict if return_dict is not None else getattr(self.config, "return_dict", True)
+        use_cache = use_cache if use_cache is not None else self.config.use_cache
+        eng = self.engine
+        dev = eng.device
+        input_ids = input_ids.reshape(-1, input_ids.shape[-1]).to(dev, torch.int64).contiguous()
+        B, T = input_ids.shape
+        tt = token_type_ids.reshape(B, T).to(dev, torch.int64).contiguous() if token_type_ids is not None else None
+        cap = caption_ids.reshape(B, -1).to(dev, torch.int64).contiguous() if caption_ids is not None else None
+        pos = None
+        if position_ids is not None:
+            position_ids = position_ids.reshape(-1, T)
+            if position_ids.shape[0] != 1 and not bool((position_ids == position_ids[:1]).all().item()):
+                raise L.ErgmError("per-sample position_ids are not supported (model.py:474-476 uses a shared arange)")
+            pos = position_ids[0].to(dev, torch.int64).contiguous()
+        with torch.cuda.device(dev):
+            legacy, past_len = None, 0
+            if past_key_values is not None:
+                from .generation import legacy_past_to_rows
+                legacy = legacy_past_to_rows(past_key_values, B, eng.H, dev)
+                past_len = legacy[0].shape[1]
+            kv_lens = None
+            if attention_mask is not None:
+                kv_lens = _kv_lens_from_mask(attention_mask.to(dev), B, past_len + T)
+            out = eng.forward(input_ids, tt, None, None, imgs if legacy is None else None,
+                              auds if legacy is None else None, cap, pos, kv_lens=kv_lens, training=False, save=False,
+                              heads=False, legacy_past=legacy)
+            from . import ops
+            hidden = torch.empty(B * T, eng.H, dtype=torch.float32, device=dev)
+            ops.ln_fwd(out["x_final"], eng.p("transformer.ln_f.weight"), eng.p("transformer.ln_f.bias"), None, hidden,
+                       None, None, self.config.layer_norm_epsilon)  # model.py:578
+            hidden = hidden.view(B, T, eng.H)
+            past_fn = _past_fn(out["kv_present"], B, eng.H, eng.nh, legacy is not None) if use_cache else None
+        ret = BaseModelOutputWithPastAndCrossAttentions(hidden, past_fn)
+        if not return_dict:
+            return (hidden,) + ((ret.past_key_values,) if use_cache else ())
+        return ret
+
+
+def _kv_lens_from_mask(attention_mask, B, total):
+    """Right-padded 0/1 attention mask [B, past + T] (model.py:478-482) -> per-sequence key counts."""
+    am = attention_mask.reshape(B, -1)
+    if am.shape[1] != total:
+        raise ValueError("attention_mask must cover past + current tokens (model.py:478-482)")
+    ok = bool(((am[:, 1:] <= am[:, :-1]).all() & (am[:, 0] > 0).all()).item())
+    if not ok:
+        raise L.ErgmError("only right-padded attention masks (ones then zeros) are supported")
+    return am.to(torch.int64).sum(1).to(torch.int32)
+
+
+def _past_fn(kv_bufs, B, H, nh, legacy):
+    """Lazy legacy-tuple view of the K/V the forward produced: L x (k, v), each [B, nh, ctx, 64] fp32
+    (model.py:228-236).  kv_bufs: per layer the [B*T, 3H] qkv matrix, or (legacy) the [B, ctx, 2H] K|V rows."""
+    def fn():
+        res = []
+        for buf in kv_bufs:
+            if legacy:
+                tk = buf.shape[1]
+                k = buf[:, :, :H].view(B, tk, nh, 64).permute(0, 2, 1, 3).float()
+                v = buf[:, :, H:].view(B, tk, nh, 64).permute(0, 2, 1, 3).float()
+            else:
+                v5 = buf.view(B, -1, 3, nh, 64)
+                k, v = v5[:, :, 1].permute(0, 2, 1, 3).float(), v5[:, :, 2].permute(0, 2, 1, 3).float()
+            res.append((k, v))
+        return tuple(res)
+    return fn
 
 
 def _get_head_mask_check(head_mask):
@@ -199,9 +308,10 @@ class _LossFn(torch.autograd.Function):
     written straight into the flat gradient buffer and bound to p.grad by the engine."""
 
     @staticmethod
-    def forward(ctx, anchor, engine, losses, on_backward):
+    def forward(ctx, anchor, engine, losses, on_backward, forward_id):
         ctx.engine = engine
         ctx.on_backward = on_backward
+        ctx.forward_id = forward_id
         return losses[0].clone()
 
     @staticmethod
@@ -209,11 +319,14 @@ class _LossFn(torch.autograd.Function):
         eng = ctx.engine
         g = g.detach().reshape(1).to(torch.float32).contiguous()
         accumulate = eng.store.grads_live()
+        sv = eng.saved
+        if sv is None or sv.get("id") != ctx.forward_id:
+            eng.backward(g, forward_id=ctx.forward_id)  # raises the explanatory error
         if ctx.on_backward is not None:
             ctx.on_backward(g, accumulate)
         else:
-            eng.backward(g, accumulate=accumulate)
-        return None, None, None, None
+            eng.backward(g, accumulate=accumulate, forward_id=ctx.forward_id)
+        return None, None, None, None, None
 
 
 class GPT2LMHeadModel(GPT2PreTrainedModel):
@@ -224,6 +337,8 @@ class GPT2LMHeadModel(GPT2PreTrainedModel):
         if not hasattr(config, "n_ctx"):
             config.n_ctx = config.n_positions  # main.py:64 reads config.n_ctx
         self.transformer = GPT2Model(config)
+        import weakref
+        self.transformer._owner = weakref.ref(self)
         self.lm_head = nn.Linear(config.n_embd, config.vocab_size, bias=False)
         self.num_emotions = NUM_EMOTIONS
         self.emotion_head = nn.Linear(config.n_embd, self.num_emotions, bias=False)
@@ -304,13 +419,7 @@ class GPT2LMHeadModel(GPT2PreTrainedModel):
         return self._engine
 
     def _kv_lens_from_mask(self, attention_mask, B, total):
-        am = attention_mask.reshape(B, -1)
-        if am.shape[1] != total:
-            raise ValueError("attention_mask must cover past + current tokens (model.py:478-482)")
-        ok = bool(((am[:, 1:] <= am[:, :-1]).all() & (am[:, 0] > 0).all()).item())
-        if not ok:
-            raise L.ErgmError("only right-padded attention masks (ones then zeros) are supported")
-        return am.to(torch.int64).sum(1).to(torch.int32)
+        return _kv_lens_from_mask(attention_mask, B, total)
 
     def forward(self, input_ids: Optional[torch.LongTensor] = None,
                 past_key_values: Optional[Tuple[Tuple[torch.Tensor]]] = None,
@@ -391,7 +500,7 @@ class GPT2LMHeadModel(GPT2PreTrainedModel):
                 losses = eng.finalize_loss(out)
                 if save:
                     on_bwd = self._dp.backward if self._dp is not None else None
-                    loss = _LossFn.apply(self.transformer.wte.weight, eng, losses, on_bwd)
+                    loss = _LossFn.apply(self.transformer.wte.weight, eng, losses, on_bwd, out["forward_id"])
                 else:
                     loss = losses[0].clone()
                 lm_loss = losses[1].clone() if labels is not None else None
@@ -402,25 +511,16 @@ class GPT2LMHeadModel(GPT2PreTrainedModel):
             def logits_fn():
                 return logits_buf[:, :V].to(torch.float32).view(B, T, V)
 
-            H, nh = eng.H, eng.nh
-            kv_bufs = out["kv_present"] if use_cache else None
-
-            def past_fn():
-                if kv_bufs is None:
-                    return None
-                res = []
-                for qkv in kv_bufs:
-                    v5 = qkv.view(B, T, 3, nh, 64)
-                    res.append((v5[:, :, 1].permute(0, 2, 1, 3).float(), v5[:, :, 2].permute(0, 2, 1, 3).float()))
-                return tuple(res)
+            past_fn = _past_fn(out["kv_present"], B, eng.H, eng.nh, False) if use_cache else None
 
             emo_logits = out["emotion_logits"].clone()
-        ops_check = os.environ.get("ERGM_CHECK_INDICES", "0") == "1"
-        if ops_check:
-            from . import ops
-            ops.check_err_flag(dev)
+        from . import ops
+        if os.environ.get("ERGM_CHECK_INDICES", "0") == "1":
+            ops.check_err_flag(dev)   # synchronous (debugging)
+        else:
+            ops.poll_err_flag(dev)    # asynchronous: raises at the next forward
         ret = CausalLMOutputWithEmotionClassification(loss=loss, logits_fn=logits_fn, emotion_logits=emo_logits,
-                                                      past_fn=past_fn if use_cache else None, lm_loss=lm_loss,
+                                                      past_fn=past_fn, lm_loss=lm_loss,
                                                       emotion_loss=emo_loss)
         if not return_dict:
             outp = (ret.logits, ret.emotion_logits) + ((ret.past_key_values,) if use_cache else ())

@@ -119,6 +119,35 @@ def check_err_flag(device):
         raise IndexError("ergm_b200: index out of range in input_ids / token_type_ids / labels")
 
 
+_err_pending = {}
+
+
+def poll_err_flag(device):
+    """Default (cheap) index check: every forward enqueues a 4-byte async D2H read of the flag; the NEXT forward
+    (or an explicit check) raises if an earlier one saw an out-of-range index.  No host synchronisation is added:
+    a read that has not completed yet is simply looked at later.  ERGM_CHECK_INDICES=1 checks synchronously."""
+    if torch.cuda.is_current_stream_capturing():
+        return
+    key = (device.type, device.index)
+    pend = _err_pending.get(key)
+    if pend is not None:
+        host, ev = pend
+        if not ev.query():
+            return  # still in flight: look at it later, do not stack another read
+        if int(host[0]) != 0:
+            _err_pending.pop(key)
+            err_flag(device).zero_()
+            raise IndexError("ergm_b200: index out of range in input_ids / token_type_ids / position_ids / caption_ids "
+                             "/ labels of an earlier forward (the reference raises IndexError there); did you call "
+                             "resize_token_embeddings for the special tokens?")
+    else:
+        host = torch.zeros(1, dtype=torch.int32).pin_memory()
+    host.copy_(err_flag(device), non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    _err_pending[key] = (host, ev)
+
+
 def _pos_stride(pos_ids, T):
     return 0 if (pos_ids is None or pos_ids.numel() == T) else T
 
@@ -150,9 +179,11 @@ def mm_pool_fwd(seq, pooled_f32, pooled_bf16, lens=None):
 
 
 def embed_bwd(dh, ids, tts, pos_ids, dwte, dwpe, *, T, past_len=0, dimgs=None, dauds=None, dropout_p=0.0, seed=0, offset=0):
+    """dwte [vocab, H] / dwpe [n_pos, H] gradient tables: out-of-range indices are skipped and flagged."""
     rows, H = dh.shape
     _call("ergm_embed_bwd", dh.data_ptr(), _p(ids), _p(tts), _p(pos_ids), _pos_stride(pos_ids, T), _p(dwte), _p(dwpe), _p(dimgs), _p(dauds),
-          rows, T, H, past_len, dropout_p, seed, offset)
+          rows, T, H, past_len, dwte.shape[0] if dwte is not None else 0, dwpe.shape[0] if dwpe is not None else 0,
+          dropout_p, seed, offset, err_flag(dh.device).data_ptr())
 
 
 def ln_fwd(x, gamma, beta, y_bf16, y_f32, mean, rstd, eps, row_idx=None):

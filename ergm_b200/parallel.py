@@ -24,14 +24,27 @@ def plan_buckets(entries, n_layer, bucket_bytes):
     embedding stage) the fp32 range [lo, hi) is final."""
     total_hi = max(o + ((n + 63) // 64) * 64 for o, n, _ in entries.values())
     layer_lo = [entries["transformer.h.%d.ln_1.weight" % l][0] for l in range(n_layer)]
+    # Parameters whose gradients are only written by the EMBEDDING stage, at the very end of the backward
+    # (engine.backward: embed_bwd, then the A3 projection wgrads): wte / wpe at the front of the buffer and,
+    # when the model has them, visual_proj / audio_proj, registered after emotion_head at its tail.  They must
+    # never ride in a bucket that a layer triggers - that bucket would be reduced before they exist.
+    late = [entries[n][0] for n in entries if n.startswith(("visual_proj.", "audio_proj."))]
+    head_hi = min(late) if late else total_hi
+    if late and any(o >= head_hi and not n.startswith(("visual_proj.", "audio_proj.")) for n, (o, _, _) in entries.items()):
+        raise RuntimeError("plan_buckets: a non-projection parameter is registered after the A3 projections")
     buckets = []
-    hi = total_hi  # the head parameters (ln_f, emotion_head) sit after the last layer
+    hi = head_hi  # the head parameters (ln_f, emotion_head) sit after the last layer
     for l in reversed(range(n_layer)):
         lo = layer_lo[l]
         if (hi - lo) * 4 >= bucket_bytes or l == 0:
             buckets.append((l, lo, hi))
             hi = lo
-    buckets.append((-1, 0, layer_lo[0] if n_layer else total_hi))  # wte / wpe: complete last
+    if not n_layer:
+        buckets.append((-1, 0, total_hi))
+        return buckets
+    buckets.append((-1, 0, layer_lo[0]))  # wte / wpe: complete last
+    if late:
+        buckets.append((-1, head_hi, total_hi))
     return buckets
 
 
@@ -87,14 +100,27 @@ class DataParallel:
         if self.world > 1 and accumulate:
             raise RuntimeError("gradient accumulation across backward calls is not supported under DataParallel")
         eng.backward(grad_loss, accumulate=accumulate, on_layer_done=self._launch if self.world > 1 else None)
-        keep = 1 if (defer_last and self.world > 1 and self._pending) else 0
+        keep = min(len(self.deferred_ranges()), len(self._pending)) if (defer_last and self.world > 1) else 0
         for w in self._pending[:len(self._pending) - keep]:
             w.wait()
         self._pending = self._pending[len(self._pending) - keep:]
 
-    def split_point(self):
-        """First element of the flat buffers that does NOT belong to the last bucket (wte / wpe)."""
-        return self.buckets[-1][2]
+    def deferred_ranges(self):
+        """Element ranges of the flat buffers that become final only after the embedding stage (trigger -1):
+        with defer_last their all-reduces are still in flight when backward() returns."""
+        return [(lo, hi) for trig, lo, hi in self.buckets if trig == -1 and hi > lo]
+
+    def early_ranges(self):
+        """Complement of deferred_ranges(): reduced and final when backward(defer_last=True) returns."""
+        total = self.model.engine.store.total
+        out, cur = [], 0
+        for lo, hi in sorted(self.deferred_ranges()):
+            if lo > cur:
+                out.append((cur, lo))
+            cur = max(cur, hi)
+        if cur < total:
+            out.append((cur, total))
+        return out
 
     def finish(self):
         for w in self._pending:

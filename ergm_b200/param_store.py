@@ -14,8 +14,9 @@ ALIGN = 64  # elements; keeps every tensor 16-byte aligned in both the fp32 and 
 
 
 class ParamStore:
-    def __init__(self, module):
+    def __init__(self, module, prefix=""):
         self.module = module
+        self.prefix = prefix  # a stand-alone GPT2Model is stored under the names it has inside GPT2LMHeadModel
         self.entries = {}   # name -> (offset, numel, shape)
         self.flat = self.grad = self.shadow = None
         self._ptrs = None
@@ -34,7 +35,7 @@ class ParamStore:
             if id(p) in seen:
                 continue
             seen.add(id(p))
-            yield name, p
+            yield self.prefix + name, p
 
     def build(self):
         params = list(self._unique_named_params())

@@ -34,6 +34,7 @@ class GraphedTrainStep:
         # A3 extension: imgs / auds are raw feature sequences [B, T, D] (pooled + projected on the device)
         self.seq_features = hasattr(model, "visual_proj")
         self.graphs = {}
+        self.graph_plans = {}
         self.static = {}
         eng = model.engine
         self.eng = eng
@@ -41,6 +42,7 @@ class GraphedTrainStep:
         eng.set_rng_step_tensor(self.rng_step)
         self.one = torch.ones(1, dtype=torch.float32, device=eng.device)
         self.loss_host = torch.zeros(5, dtype=torch.float32).pin_memory()
+        self.err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.h2d_bytes = 0
         self.launches_per_step = 0
 
@@ -57,11 +59,14 @@ class GraphedTrainStep:
         if self.dp is not None and getattr(self.dp, "world", 1) > 1:
             # AdamW on the layer / head parameters runs while the embedding bucket (wte + wpe, 25 % of the
             # bytes, final only after the embedding backward) is still being all-reduced
+            # (wte + wpe, 25 % of the bytes, and the A3 projections: final only after the embedding backward)
             self.dp.backward(self.one, False, defer_last=True)
-            cut = self.dp.split_point()
-            self.opt.apply(lo=cut, last=False)
+            for lo, hi in self.dp.early_ranges():
+                self.opt.apply(lo=lo, hi=hi, last=False)
             self.dp.finish()
-            self.opt.apply(lo=0, hi=cut)
+            late = self.dp.deferred_ranges()
+            for i, (lo, hi) in enumerate(late):
+                self.opt.apply(lo=lo, hi=hi, last=(i == len(late) - 1))
         else:
             if self.dp is not None:
                 self.dp.backward(self.one, False)
@@ -104,11 +109,15 @@ class GraphedTrainStep:
 
     def run_device(self, key, st):
         """Forward + backward + optimizer on the static buffers (graph replay after capture)."""
-        self.opt.load_hyper()
+        # the optimiser needs to know BEFORE the backward which parameters it will touch (torch's "grad is None
+        # -> skip" rule): without captions the cross-attention tensors take no part (model.py:311-329)
+        self.opt.load_hyper(skip=() if "caption_ids" in st else ("crossattention.", "ln_cross_attn."))
         if not self.use_graph:
             self.losses = self._device_step(st)
             return
         g = self.graphs.get(key)
+        if g is not None and self.graph_plans.get(key) != self.opt._plan:
+            g = None  # the per-parameter step counts regrouped (mode switch mid-training): capture again
         if g is None:
             # warm-up eagerly once (allocates workspaces, NCCL channels), then capture
             self.losses = self._device_step(st)
@@ -118,6 +127,7 @@ class GraphedTrainStep:
             with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 self.losses = self._device_step(st)
             self.graphs[key] = g
+            self.graph_plans[key] = [list(r) for r in self.opt._plan]
             return
         g.replay()
         # the replayed AdamW rewrote the weights and their bf16 shadow; the Python-side bookkeeping of the
@@ -134,5 +144,11 @@ class GraphedTrainStep:
         key, st = self.copy_in(batch)
         self.run_device(key, st)
         self.loss_host.copy_(self.losses, non_blocking=True)
+        flag = ops.err_flag(self.eng.device)
+        self.err_host.copy_(flag, non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        if int(self.err_host[0]) != 0:
+            flag.zero_()
+            raise IndexError("ergm_b200: index out of range in input_ids / token_type_ids / caption_ids / labels "
+                             "(the reference raises IndexError there)")
         return float(self.loss_host[0])

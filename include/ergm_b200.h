@@ -30,6 +30,9 @@ extern "C" {
 /* library / device probes (no compute) */
 int ergm_abi_version(void);
 int ergm_device_sm_count(void);
+/* TMA descriptors are encoded once per distinct (pointer, shape, stride, box) */
+/* and then served from a mutex-guarded table: hit / miss counters of it.      */
+int ergm_tmap_cache_stats(uint64_t* hits, uint64_t* misses);
 /* Dropout masks are Philox functions of (seed + *step, offset, element); the
  * step counter lives in device memory so that CUDA-graph replays draw fresh
  * masks.  NULL (default) disables the indirection.                          */
@@ -112,11 +115,13 @@ int ergm_mm_pool_fwd(const float* seq, int64_t ld_b, int64_t ld_t, const int* le
 int ergm_gather_rows_bf16(const int64_t* ids, const float* table, void* out_bf16, int rows,
                           int H, int vocab, int* err_flag, void* stream);
 /* backward of the embedding stage: scatter-add dh rows into dwte (by id and  */
-/* by token type), dwpe, and optionally the fused-feature gradients.          */
+/* by token type), dwpe, and optionally the fused-feature gradients.  Indices */
+/* outside [0, vocab) / [0, n_pos) are skipped (never scattered) and flagged  */
+/* in err_flag (nullable), like the forward does.                             */
 int ergm_embed_bwd(const float* dh, const int64_t* ids, const int64_t* token_type_ids,
                    const int64_t* position_ids, int64_t pos_stride_b, float* dwte, float* dwpe, float* dimgs,
-                   float* dauds, int rows, int T, int H, int past_len, float dropout_p,
-                   uint64_t seed, uint64_t offset, void* stream);
+                   float* dauds, int rows, int T, int H, int past_len, int vocab, int n_pos, float dropout_p,
+                   uint64_t seed, uint64_t offset, int* err_flag, void* stream);
 
 /* ------------------------------------------------------------------------ */
 /* LayerNorm (model.py:298,318,332,578; eps inside the sqrt, biased variance) */
@@ -260,10 +265,13 @@ int ergm_attn_decode_contig(const void* q, int64_t ld_q, int q_col0, const void*
 int ergm_kv_to_pages(const void* kv, int64_t ld, int k_col0, int v_col0, void* pool,
                      const int* block_table, const int* lens, int max_pages, int B, int T, int nh,
                      void* stream);
-/* next token per row of fp32 logits: top_k <= 1 greedy arg-max (lowest index
- * on ties), else top-k / temperature sampling (Philox(seed, *step_ptr)).
+/* next token per row of fp32 logits: top_k 0 or 1 = greedy arg-max (lowest index
+ * on ties); top_k >= 2 = top-k / temperature sampling (Philox(seed, *step_ptr));
+ * top_k == -1 (ERGM_SAMPLE_ALL) = multinomial over the whole distribution
+ * (the nucleus kernel at top_p = 1), with temperature.
  * Writes out_ids[b, *step_ptr], next_ids[b]; finished rows emit eos_id;
  * seq_lens[b] += 1.                                                          */
+#define ERGM_SAMPLE_ALL (-1)
 int ergm_sample(const float* logits, int64_t ld, int B, int V, int top_k,
                 float top_p /* < 1: nucleus sampling with main.py:263-265's shifted mask; 1 = off */,
                 float temperature, uint64_t seed, int* step_ptr,

@@ -24,7 +24,7 @@ def test_header_symbols_exported(lib):
     assert len(protos) >= 27
     for name in protos:
         assert hasattr(lib, name), name
-    assert lib.ergm_abi_version() == 1
+    assert lib.ergm_abi_version() == 2
 
 
 def test_header_is_plain_c():

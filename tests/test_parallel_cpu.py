@@ -118,7 +118,7 @@ def test_world2_gloo_global_mean_and_gather():
 
 def test_last_bucket_is_the_embedding_bucket():
     """DataParallel defers the LAST bucket (wte + wpe, final only after the embedding backward) and runs
-    AdamW on everything behind split_point() meanwhile: the plan must put exactly the embedding range last."""
+    AdamW on early_ranges() meanwhile: the plan must put exactly the embedding range last."""
     from ergm_b200.parallel import plan_buckets
     entries, off = {}, 0
 
@@ -140,4 +140,24 @@ def test_last_bucket_is_the_embedding_bucket():
         assert trig == -1 and lo == 0 and hi == entries["transformer.h.0.ln_1.weight"][0]
         covered = sorted((lo, hi) for _, lo, hi in b)
         assert covered[0][0] == 0 and covered[-1][1] == off
+        assert all(covered[i][1] == covered[i + 1][0] for i in range(len(covered) - 1))
+
+
+def test_projection_parameters_ride_in_the_embedding_stage_buckets():
+    """A3 extension (config.ergm_visual_dim): visual_proj / audio_proj are registered after emotion_head, but
+    their gradients are written at the very END of the backward (after embed_bwd).  They must be in a
+    trigger -1 bucket, never in the bucket the last layers trigger (which is reduced long before)."""
+    cfg = O.OracleConfig(vocab_size=1024, n_positions=64, n_embd=128, n_layer=4, n_head=2, visual_dim=96, audio_dim=96)
+    ent, total = _entries(cfg)
+    for mb in (0.001, 0.05, 128):
+        b = parallel.plan_buckets(ent, cfg.n_layer, int(mb * (1 << 20)))
+        late = [(lo, hi) for t, lo, hi in b if t == -1]
+        proj_lo = ent["visual_proj.weight"][0]
+        assert (0, ent["transformer.h.0.ln_1.weight"][0]) in late and (proj_lo, total) in late
+        for t, lo, hi in b:
+            if t >= 0:  # layer-triggered buckets stop before the projections
+                assert hi <= proj_lo
+        assert ent["emotion_head.weight"][0] < proj_lo  # the head still rides with the last layers
+        covered = sorted((lo, hi) for _, lo, hi in b)
+        assert covered[0][0] == 0 and covered[-1][1] == total
         assert all(covered[i][1] == covered[i + 1][0] for i in range(len(covered) - 1))
