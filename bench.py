@@ -129,53 +129,68 @@ def host_batch(B, T, seed, pin=True, sequences=False, kf=1):
     return out
 
 
-def cpu_reference_run(steps, warmup, B=2, T=SEQ, threads=None):
-    """fwd + bwd + AdamW of the oracle port on the host cores (fp32, dropout omitted: the oracle is the
-    p=0 / eval restatement; dropout is <1% of CPU time).  Returns (tokens/s, ms/step, threads)."""
-    from oracle import ergm_oracle as O
-    from ergm_b200 import synthetic
-    threads = threads or os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    cfg = O.OracleConfig()
-    sd = {k: v.clone().requires_grad_(True) for k, v in O.init_state_dict(cfg, seed=0).items() if k != "lm_head.weight"}
-    sd["lm_head.weight"] = sd["transformer.wte.weight"]
-    opt = torch.optim.AdamW([v for k, v in sd.items() if k != "lm_head.weight"], lr=2e-5)
-    b = synthetic.make_batch(B, T, seed=1234)
-    times = []
-    for it in range(warmup + steps):
-        t0 = time.perf_counter()
-        opt.zero_grad()
-        o = O.forward(sd, cfg, b["input_ids"], b["token_type_ids"], b["labels"], b["emotion_labels"],
-                      b["imgs"], b["auds"], b["caption_ids"])
-        o["loss"].backward()
-        opt.step()
-        dt = time.perf_counter() - t0
-        if it >= warmup:
-            times.append(dt)
-    ms = 1e3 * sum(times) / len(times)
-    return B * T / (ms / 1e3), ms, threads
-
-
-# ------------------------------------------------------------------------------------------
 def run_reference_arm(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path (the unmodified model.py through
+    oracle/ref_shim.py; the oracle port only if no copy of it is present) on all host threads.  Each step is a
+    bounded sample (B=4) of the B=32 training step; rank 0 alone runs it under torchrun."""
     if rank != 0:
         return
-    B = 2
-    tps, ms, threads = cpu_reference_run(args.steps, args.warmup, B=B)
-    sample = "oracle port fwd+bwd+AdamW, GPT-2 small caption mode, B=%d x T=%d per step (bounded sample of the B=32 step)" % (B, SEQ)
-    line = {"impl": "reference", "metric": METRIC, "value": tps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "ERGM GPT-2 small teacher-forced training step (fwd+bwd+AdamW), caption mode, "
-                                   "synthetic MELD-shaped, CPU sample B=%d T=%d" % (B, SEQ)},
-            "cpu_baseline": {"value": tps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
-            "e2e": {"value": tps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    from oracle import ref_runner
+    B = 4
+    r = ref_runner.cpu_train_step(args.steps, args.warmup, B=B, T=SEQ)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "ERGM GPT-2 small teacher-forced training step (fwd+bwd+AdamW), caption mode + "
+                                   "img/aud fusion, dropout 0.10, synthetic MELD-shaped, CPU sample B=%d x T=%d of the "
+                                   "B=%d x T=%d step" % (B, SEQ, B_PER_GPU, SEQ)},
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if not args.no_suite:
+        # BASELINE.md 3.4: config-1 forward+loss / forward+backward and generation both ways, same host cores
+        try:
+            line["cpu_reference_suite"] = ref_runner.cpu_suite()
+        except Exception as e:
+            line["cpu_reference_suite"] = {"error": "%s: %s" % (type(e).__name__, e)}
     print(json.dumps(line), flush=True)
 
 
+def run_reference_gpu_arm(args, rank, local):
+    """--impl reference-gpu: the same-box bar of BASELINE.md 3.5 - the unmodified reference model executed by stock
+    torch eager ON the B200 (fp32 and autocast bf16), configs 2 and 4.  Rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import ref_runner
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    medium = args.config == "medium"
+    res = ref_runner.gpu_eager_suite(device, B=B_PER_GPU, T=SEQ, steps=max(3, min(args.steps, 10)), medium=medium)
+    key = "train_caption_autocast_bf16"
+    best = res.get(key, {})
+    line = {"impl": "reference-gpu", "metric": METRIC, "value": best.get("train_tokens_per_s"), "unit": UNIT,
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": best.get("ms_per_step"),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 autocast (fp32 beside it)",
+            "data": "synthetic",
+            "config": {"workload": "reference ERGM GPT-2 %s in torch eager on the B200: training step B=%d x T=%d "
+                                   "(caption mode, dropout 0.10, torch.optim.AdamW) and KV-cached greedy decode"
+                                   % (args.config, B_PER_GPU, SEQ)},
+            "reference_on_b200": res}
+    print(json.dumps(line), flush=True)
+
+
+def decode_bytes(eng, B, ctx, Tc=0):
+    """Algorithmic HBM bytes of one decode step (SURVEY.md 8d): bf16 weights once + the K/V each sequence reads;
+    caption mode adds the q_attn / c_proj weights and the cached cross-attention K/V (Tc keys per sequence)."""
+    H, L, V = eng.H, eng.L, eng.V
+    w = 2 * (12 * L * H * H + V * H) + (2 * L * 2 * H * H if Tc else 0)
+    kv = B * (2 * L * ctx * H * 2) + (B * 2 * L * Tc * H * 2 if Tc else 0)
+    return w + kv
+
+
 def bench_generation(model, device, B=64, prompt=128, new=64, reps=3):
-    """BASELINE config 4: greedy decode, ragged prompts 64..128, 64 new tokens, paged KV."""
+    """BASELINE config 4: ragged prompts 64..128, 64 new tokens, paged KV; greedy (caption / no caption) and
+    top-k = 50 sampling; per-token latency = graph replays of the decode step alone."""
     from ergm_b200 import synthetic
     from ergm_b200 import generation
     g = torch.Generator().manual_seed(7)
@@ -184,14 +199,15 @@ def bench_generation(model, device, B=64, prompt=128, new=64, reps=3):
     ids, tt, cap = b["input_ids"].to(device), b["token_type_ids"].to(device), b["caption_ids"].to(device)
     model.eval()
     res = {}
-    for mode, capt in (("nocaption", None), ("caption", cap)):
+    for mode, capt, kw in (("nocaption", None, {}), ("caption", cap, {}),
+                           ("nocaption_topk50", None, dict(do_sample=True, top_k=50, seed=1))):
         times = []
         for r in range(reps + 1):
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             out = generation.generate(model, ids, tt, max_new_tokens=new, eos_token_id=None, sp2_id=50259,
-                                      caption_ids=capt, prompt_lens=lens)
+                                      caption_ids=capt, prompt_lens=lens, **kw)
             e1.record()
             torch.cuda.synchronize()
             if r > 0:
@@ -199,8 +215,12 @@ def bench_generation(model, device, B=64, prompt=128, new=64, reps=3):
         ms = statistics.median(times)
         res[mode] = {"gen_tokens_per_s": B * new / (ms / 1e3), "ms_total": ms, "batch": B, "new_tokens": new}
     # per-token latency: time graph replays of the decode step alone
-    out, st = generation.generate(model, ids, tt, max_new_tokens=new, sp2_id=50259, prompt_lens=lens, return_state=True)
-    if st.graph is not None:
+    ctx = float(lens.float().mean()) + new / 2
+    for key, capt in (("decode_step", None), ("decode_step_caption", cap)):
+        out, st = generation.generate(model, ids, tt, max_new_tokens=new, sp2_id=50259, prompt_lens=lens,
+                                      caption_ids=capt, return_state=True)
+        if st.graph is None:
+            continue
         st.step.zero_()
         st.seq_lens.copy_(lens.to(device).int())
         lat = []
@@ -210,16 +230,24 @@ def bench_generation(model, device, B=64, prompt=128, new=64, reps=3):
             torch.cuda.synchronize()
             lat.append(e0.elapsed_time(e1))
         p50 = statistics.median(lat)
-        eng = model.engine
-        H, L, V = eng.H, eng.L, eng.V
-        ctx = float(lens.float().mean()) + new / 2
-        bytes_step = 2 * (12 * L * H * H + V * H) + B * (2 * L * ctx * H * 2)
-        res["decode_step"] = {"p50_ms_per_token": p50, "tokens_per_s_steady": B / (p50 / 1e3),
-                              "algorithmic_bytes_per_step": bytes_step,
-                              "hbm_gbs_achieved": bytes_step / (p50 / 1e3) / 1e9,
-                              "hbm_frac_of_measured": bytes_step / (p50 / 1e3) / 1e9 / peaks()["hbm"]}
+        nbytes = decode_bytes(model.engine, B, ctx, cap.shape[1] if capt is not None else 0)
+        res[key] = {"p50_ms_per_token": p50, "tokens_per_s_steady": B / (p50 / 1e3),
+                    "algorithmic_bytes_per_step": nbytes, "mean_ctx": ctx,
+                    "hbm_gbs_achieved": nbytes / (p50 / 1e3) / 1e9,
+                    "hbm_frac_of_measured": nbytes / (p50 / 1e3) / 1e9 / peaks()["hbm"],
+                    "launches_per_step": getattr(st, "launches_per_step", None)}
     model.train()
     return res
+
+
+def measured_traffic():
+    """ncu DRAM traffic per launch / step (profiles/traffic.json, written by scripts/ncu_traffic.py from a
+    committed `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` pass of this same command)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
 
 
 def main():
@@ -230,6 +258,8 @@ def main():
     ap.add_argument("--impl", default="ergm_b200")
     ap.add_argument("--no-gen", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-suite", action="store_true", help="--impl reference: skip the config-1 / generation CPU suite")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-in-torch-eager-on-B200 leg of the main line")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--dropout", type=float, default=0.1)
     ap.add_argument("--config", default="small", choices=["small", "medium"],
@@ -245,6 +275,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference_arm(args, rank)
+        return
+    if args.impl == "reference-gpu":
+        run_reference_gpu_arm(args, rank, int(os.environ.get("LOCAL_RANK", "0")))
         return
     import torch.distributed as dist
     device = torch.device("cuda", local)
@@ -335,7 +368,11 @@ def main():
             achieved = g_fl / (g_ms / 1e3) / 1e12
             roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": achieved,
                     "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sust"],
-                    "peak_source": pk["src"] + " (sustained bf16)", "traffic": None,
+                    "peak_source": pk["src"] + " (sustained bf16)",
+                    "traffic": measured_traffic().get("gemm_bf16_kernel", {}).get("dram_bytes_per_launch"),
+                    "traffic_source": measured_traffic().get("gemm_bf16_kernel", {}).get("source"),
+                    "algorithmic_bytes_per_launch_note": "tensor-bound kernel: traffic is reported for completeness "
+                                                         "(operands + output of an average launch)",
                     "gemm_launches_per_step": n_gemm, "gemm_ms_per_step": g_ms, "gemm_flops_per_step": g_fl,
                     "avg_launch_us": 1e3 * g_ms / max(n_gemm, 1), "gemm_by_shape": by_shape,
                     "eager_ms_by_entry_point": {k: round(v, 3) for k, v in sorted(by.items(), key=lambda kv: -kv[1])}}
@@ -368,26 +405,49 @@ def main():
         try:
             gen = bench_generation(model, device)
             if world > 1:
-                tg = torch.tensor([gen["nocaption"]["ms_total"], gen["caption"]["ms_total"],
-                                   gen.get("decode_step", {}).get("p50_ms_per_token", 0.0)], device=device)
+                modes = ("nocaption", "caption", "nocaption_topk50")
+                steps_k = ("decode_step", "decode_step_caption")
+                tg = torch.tensor([gen[m]["ms_total"] for m in modes] +
+                                  [gen.get(k, {}).get("p50_ms_per_token", 0.0) for k in steps_k], device=device)
                 dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-                for i, mode in enumerate(("nocaption", "caption")):
+                for i, mode in enumerate(modes):
                     gen[mode]["ms_total"] = float(tg[i])
                     gen[mode]["gen_tokens_per_s"] = world * gen[mode]["batch"] * gen[mode]["new_tokens"] / (float(tg[i]) / 1e3)
                     gen[mode]["batch"] *= world
-                if "decode_step" in gen:
-                    gen["decode_step"]["p50_ms_per_token"] = float(tg[2])
-                    gen["decode_step"]["tokens_per_s_steady"] = world * 64 / (float(tg[2]) / 1e3)
+                for i, k in enumerate(steps_k):
+                    if k in gen:
+                        gen[k]["p50_ms_per_token"] = float(tg[len(modes) + i])
+                        gen[k]["tokens_per_s_steady"] = world * 64 / (float(tg[len(modes) + i]) / 1e3)
                 gen["sharding"] = "%d ranks x 64 requests, no communication" % world
         except Exception as e:  # generation is a secondary line; never lose the training number
             gen = {"error": "%s: %s" % (type(e).__name__, e)}
             if world > 1:
                 raise
     cpu = None
+    ref_gpu = None
     if rank == 0 and world == 1 and not args.no_cpu and not medium:
-        tps, ms_cpu, threads = cpu_reference_run(steps=2, warmup=1, B=2)
-        cpu = {"value": tps, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "oracle port fwd+bwd+AdamW, B=2 x T=256 caption mode, 2 timed steps (%.0f ms/step)" % ms_cpu}
+        from oracle import ref_runner
+        r = ref_runner.cpu_train_step(steps=2, warmup=1, B=2, T=SEQ)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+               "sample": r["sample"] + " (%.0f ms/step)" % r["ms_per_step"]}
+    if rank == 0 and world == 1 and not args.no_ref_gpu and not medium:
+        # the same-box bar: the reference model in torch eager on this B200, measured after
+        # every number of ours has been taken (it shares nothing with our path)
+        try:
+            from oracle import ref_runner
+            torch.cuda.empty_cache()
+            ref_gpu = ref_runner.gpu_eager_suite(device, B=B_PER_GPU, T=SEQ, steps=5)
+        except Exception as e:
+            ref_gpu = {"error": "%s: %s" % (type(e).__name__, e)}
+    roof_dec = None
+    if gen and "decode_step" in gen:
+        d = gen["decode_step"]
+        tr = measured_traffic().get("decode_step", {})
+        roof_dec = {"bound": "hbm", "kernel": "decode step = one CUDA-graph replay (%s launches): LN+QKV / paged attention "
+                                              "/ out-proj / MLP slab GEMMs, LM head, arg-max" % d.get("launches_per_step"),
+                    "achieved": d["hbm_gbs_achieved"], "peak": pk["hbm"], "unit": "GB/s", "frac": d["hbm_frac_of_measured"],
+                    "peak_source": pk["src"], "traffic": tr.get("dram_bytes_per_step"), "traffic_source": tr.get("source"),
+                    "algorithmic_bytes": d["algorithmic_bytes_per_step"], "p50_us": 1e3 * d["p50_ms_per_token"]}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
@@ -403,10 +463,11 @@ def main():
                                  "iteration, far above the 126 MB L2",
                            "cuda_graph": bool(step.use_graph)},
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
-                        "h2d_bytes_per_step": step.h2d_bytes * world, "d2h_bytes_per_step": 20 * world,
+                        "h2d_bytes_per_step": step.h2d_bytes * world, "d2h_bytes_per_step": 24 * world,
                         "api": "ergm_b200.trainer.GraphedTrainStep(model, FusedAdamW)(pinned_host_batch) -> loss"},
                 "gpu_launches": step.launches_per_step * args.steps,
-                "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+                "clocks": clk, "roofline": roof, "roofline_decode": roof_dec, "cpu_baseline": cpu,
+                "reference_on_b200": ref_gpu,
                 "model_tflops_per_gpu": model_tf, "model_flops_per_token": fl_tok,
                 "mfu_of_measured_sustained": model_tf / pk["tf_sust"], "last_loss": loss,
                 "tokens_per_step": {"all_positions_incl_padding": tokens, "non_pad_rank0": nonpad},

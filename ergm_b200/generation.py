@@ -228,7 +228,9 @@ def generate(model, input_ids, token_type_ids=None, max_new_tokens=64, do_sample
                 with torch.cuda.stream(s):
                     # warm-up run outside capture is not possible without consuming a step, so the
                     # first token is decoded eagerly and the graph replays the remaining ones
+                    n0 = ops.launch_count()
                     decode_step(eng, st, sample_kw)
+                    st.launches_per_step = ops.launch_count() - n0
                 torch.cuda.current_stream().wait_stream(s)
                 if n_steps > 1:
                     g = torch.cuda.CUDAGraph()

@@ -1,9 +1,10 @@
-"""Imports the UNMODIFIED reference model (/root/reference/src/model.py) under the installed
-transformers 5.5 / torch 2.11 — TEST INFRASTRUCTURE ONLY, build container only.
+"""Imports the UNMODIFIED reference model (/root/reference/src/model.py, or its byte-identical copy
+oracle/_ref/model.py made by oracle/build_ref.py where /root/reference does not exist: the GPU box)
+under the installed transformers 5.5 / torch 2.11 — TEST / BENCH INFRASTRUCTURE ONLY.
 
-/root/reference does not exist on the GPU box, so nothing that runs there may import this
-module; it is used by oracle/make_golden.py (fixture generation) and by CPU tests that are
-skipped when the reference tree is absent.  The shims follow SURVEY.md §8(c): they only
+Used by oracle/make_golden.py (fixture generation), by CPU tests that are skipped when no reference
+copy is present, and by bench.py's reference arms (oracle/ref_runner.py), which time the reference
+itself on the host cores and in torch eager on the B200.  The shims follow SURVEY.md §8(c): they only
 restore names transformers 4.26.1 had and 5.5 removed, and keep model.py:401-408's
 hard-coded .to("cuda") from failing on a CPU-only host.  No reference file is edited.
 """
@@ -13,11 +14,23 @@ import types
 
 import torch
 
-REF_SRC = "/root/reference/src"
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _ref_src():
+    if os.path.isfile("/root/reference/src/model.py"):
+        return "/root/reference/src"
+    from . import build_ref
+    if build_ref.verify():
+        return os.path.join(_HERE, "_ref")
+    return None
+
+
+REF_SRC = _ref_src()
 
 
 def available():
-    return os.path.isfile(os.path.join(REF_SRC, "model.py"))
+    return REF_SRC is not None
 
 
 _cached = {}
