@@ -113,7 +113,9 @@ def err_flag(device):
 
 
 def check_err_flag(device):
+    """Synchronous check (also drops any asynchronous read that is still pending for this device)."""
     f = err_flag(device)
+    _err_pending.pop((device.type, device.index), None)
     if int(f.item()) != 0:
         f.zero_()
         raise IndexError("ergm_b200: index out of range in input_ids / token_type_ids / labels")

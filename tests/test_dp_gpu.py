@@ -24,13 +24,19 @@ from oracle import ergm_oracle as O, synthetic
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(rank)
 dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
-cfg = O.OracleConfig(vocab_size=1024, n_positions=256, n_embd=128, n_layer=3, n_head=2)
+PROJ = %(proj)r   # A3 extension: visual_proj / audio_proj gradients are written at the very end of the backward
+cfg = O.OracleConfig(vocab_size=1024, n_positions=256, n_embd=128, n_layer=3, n_head=2,
+                     visual_dim=96 if PROJ else None, audio_dim=96 if PROJ else None)
 sd = O.init_state_dict(cfg, seed=3, perturb=True)
 def build():
     hf = GPT2Config(vocab_size=1024, n_positions=256, n_embd=128, n_layer=3, n_head=2, attn_pdrop=0.0, resid_pdrop=0.0, embd_pdrop=0.0)
+    if PROJ:
+        hf.ergm_visual_dim = hf.ergm_audio_dim = 96
     m = GPT2LMHeadModel(hf); m.load_state_dict(sd); return m.cuda().train()
 B = 4 * world
-b = synthetic.make_batch(B, 64, seed=31, vocab=1024, feat_dim=128)
+b = synthetic.make_batch(B, 64, seed=31, vocab=1024, feat_dim=96 if PROJ else 128)
+if PROJ:
+    b["imgs"], b["auds"] = b["vis_seq"], b["aud_seq"]
 keys = ("input_ids", "token_type_ids", "labels", "emotion_labels", "caption_ids", "imgs", "auds")
 full = {k: b[k].cuda() for k in keys}
 mine = {k: v[rank * 4:(rank + 1) * 4].contiguous() for k, v in full.items()}
@@ -40,15 +46,24 @@ out = ref(**full); out.loss.backward()
 ref_loss = out.loss.item()
 ref_grads = {n: p.grad.clone() for n, p in ref.named_parameters()}
 FusedAdamW(ref, lr=1e-3).step()
+# the ORACLE on the concatenated global batch (SURVEY 8e): fp32 on the CPU
+sdo = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k != "lm_head.weight"}
+sdo["lm_head.weight"] = sdo["transformer.wte.weight"]
+oo = O.forward(sdo, cfg, b["input_ids"], b["token_type_ids"], b["labels"], b["emotion_labels"], b["imgs"], b["auds"], b["caption_ids"])
+oo["loss"].backward()
 # data-parallel step through the public model API
 m = build()
 dp = DataParallel(m, bucket_mb=0.25)
 o = m(**mine); o.loss.backward()
 ok = abs(o.loss.item() - ref_loss) < 1e-5
+ok_oracle = abs(o.loss.item() - oo["loss"].item()) < 2.5e-3
 worst = 0.0
+worst_oracle = 0.0
 for n, p in m.named_parameters():
     r = ((p.grad - ref_grads[n]).norm() / (ref_grads[n].norm() + 1e-20)).item()
     worst = max(worst, r)
+    go = sdo[n].grad.cuda()
+    worst_oracle = max(worst_oracle, ((p.grad - go).norm() / (go.norm() + 1e-20)).item())
 FusedAdamW(m, lr=1e-3).step()
 wdiff = max((p.detach() - q.detach()).abs().max().item() for p, q in zip(m.parameters(), ref.parameters()))
 # graph-captured DP train step (the bench path) runs and agrees with itself across ranks
@@ -59,8 +74,11 @@ losses = [step(pinned) for _ in range(3)]
 t = torch.tensor(losses, device="cuda"); t2 = t.clone(); dist.broadcast(t2, 0)
 same = bool(torch.equal(t, t2))
 w0 = m2.transformer.h[1].mlp.c_fc.weight.detach().clone(); w1 = w0.clone(); dist.broadcast(w1, 0)
-print("RANK%%d loss_ok=%%s worst_grad_rel=%%.2e wdiff=%%.2e graph_losses=%%s same=%%s wsync=%%s" %% (rank, ok, worst, wdiff, ["%%.4f" %% x for x in losses], same, bool(torch.equal(w0, w1))), flush=True)
-assert ok and worst < 2e-3 and wdiff < 1e-5 and same and torch.equal(w0, w1) and losses[2] < losses[0]
+# replicas must stay bit-identical in EVERY parameter (incl. the late-gradient projections) after graphed steps
+flat = m2.engine.store.flat.detach().clone(); flat0 = flat.clone(); dist.broadcast(flat0, 0)
+allsync = bool(torch.equal(flat, flat0))
+print("RANK%%d loss_ok=%%s oracle_loss_ok=%%s worst_grad_rel=%%.2e worst_grad_rel_vs_oracle=%%.2e wdiff=%%.2e graph_losses=%%s same=%%s wsync=%%s allsync=%%s" %% (rank, ok, ok_oracle, worst, worst_oracle, wdiff, ["%%.4f" %% x for x in losses], same, bool(torch.equal(w0, w1)), allsync), flush=True)
+assert ok and ok_oracle and worst < 2e-3 and worst_oracle < 6e-2 and wdiff < 1e-5 and same and torch.equal(w0, w1) and allsync and losses[2] < losses[0]
 step.close()
 dist.barrier()
 dist.destroy_process_group()
@@ -75,12 +93,14 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world", [2])
-def test_dp_step_equals_single_gpu_step(world, tmp_path):
+@pytest.mark.parametrize("world,proj", [(2, False), (2, True)])
+def test_dp_step_equals_single_gpu_step(world, proj, tmp_path):
+    """N-rank step on the split batch == single-GPU step == the ORACLE on the concatenated batch; with proj the
+    model carries the A3 projection parameters, whose gradients only exist after the embedding backward."""
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     script = tmp_path / "dp_worker.py"
-    script.write_text(WORKER % {"root": ROOT})
+    script.write_text(WORKER % {"root": ROOT, "proj": proj})
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)

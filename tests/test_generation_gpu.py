@@ -353,3 +353,22 @@ def test_generation_after_graph_replayed_training_uses_new_weights(cuda_device):
     fresh = build_model(cfg, {k: v.detach().cpu().clone() for k, v in m.state_dict().items()})
     want = fresh.generate(ids, tt, max_new_tokens=8, sp2_id=cfg.vocab_size - 1).cpu()
     assert torch.equal(after, want), (after.tolist(), want.tolist())
+
+
+def test_plain_multinomial_sampling_is_not_greedy(cuda_device):
+    """generate(do_sample=True) with top_k = 0 and top_p = 1.0 is multinomial sampling over the whole distribution
+    (ERGM_SAMPLE_ALL), not arg-max; temperature applies; seeds reproduce."""
+    cfg = tiny_cfg(0.02)   # flat distribution: sampling must leave the arg-max path at once
+    sd = O.init_state_dict(cfg, seed=5, perturb=True)
+    m = build_model(cfg, sd)
+    b = synthetic.make_batch(8, 24, seed=21, vocab=cfg.vocab_size, feat_dim=cfg.n_embd, ragged=False)
+    ids, tt = b["input_ids"].cuda(), b["token_type_ids"].cuda()
+    greedy = m.generate(ids, tt, max_new_tokens=12, sp2_id=cfg.vocab_size - 1).cpu()
+    s1 = m.generate(ids, tt, max_new_tokens=12, sp2_id=cfg.vocab_size - 1, do_sample=True, top_k=0, top_p=1.0, seed=3).cpu()
+    s2 = m.generate(ids, tt, max_new_tokens=12, sp2_id=cfg.vocab_size - 1, do_sample=True, top_k=0, top_p=1.0, seed=3).cpu()
+    s3 = m.generate(ids, tt, max_new_tokens=12, sp2_id=cfg.vocab_size - 1, do_sample=True, top_k=0, top_p=1.0, seed=4).cpu()
+    assert torch.equal(s1, s2) and not torch.equal(s1, s3)
+    assert (s1 != greedy).float().mean().item() > 0.5
+    cold = m.generate(ids, tt, max_new_tokens=12, sp2_id=cfg.vocab_size - 1, do_sample=True, top_k=0, top_p=1.0,
+                      temperature=1e-3, seed=3).cpu()
+    assert (cold[:, 0] == greedy[:, 0]).all()   # T -> 0 concentrates the whole distribution on the arg-max
