@@ -53,7 +53,39 @@ struct GemmParams {
   int m_tiles, n_tiles, kb_total, kb_per_split;
   float dropout_p;
   DropoutSite site;
+  const int* dyn;  // nullable device int: the run-time extent of M (dyn_dim 1) or K (dyn_dim 2), <= the static one
+  int dyn_dim;
 };
+
+// Run-time problem extent (label-sparse LM head, packed batches): the host sizes the launch, the tensor maps and
+// the workspaces for the static capacity; the kernel re-derives its tile schedule from a device-side count, so a
+// CUDA graph captured once serves every batch.  dyn_dim 1: rows of A / D beyond the count are never stored (the
+// last tile may LOAD stale rows: they only feed accumulator rows that are discarded).  dyn_dim 2: the reduction
+// stops at the count rounded up to BK: the caller keeps the operand rows in [count, roundup(count, 128)) zero.
+// With ERGM_EPI_ATOMIC and dyn_dim 1 the K split is chosen here so that the (few) row tiles still fill the GPU.
+ERGM_DEVINL void apply_dyn(GemmParams& p, int tile_m, int slots) {
+  if (!p.dyn) return;
+  int v = *p.dyn;
+  v = v < 0 ? 0 : v;
+  if (p.dyn_dim == 1) {
+    p.M = v < p.M ? v : p.M;
+    p.m_tiles = (p.M + tile_m - 1) / tile_m;
+    if ((p.epi & ERGM_EPI_ATOMIC) && p.m_tiles > 0) {
+      int sk = slots / (p.m_tiles * p.n_tiles);
+      const int max_sk = p.kb_total / 8 > 0 ? p.kb_total / 8 : 1;  // at least 8 k-blocks per split
+      sk = sk < 1 ? 1 : (sk > max_sk ? max_sk : sk);
+      p.kb_per_split = (p.kb_total + sk - 1) / sk;
+      p.split_k = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+    }
+  } else if (p.dyn_dim == 2) {
+    p.K = v < p.K ? v : p.K;
+    p.kb_total = (p.K + BK - 1) / BK;
+    int sk = p.split_k < p.kb_total ? p.split_k : p.kb_total;
+    sk = sk < 1 ? 1 : sk;
+    p.kb_per_split = p.kb_total > 0 ? (p.kb_total + sk - 1) / sk : 1;
+    p.split_k = p.kb_total > 0 ? (p.kb_total + p.kb_per_split - 1) / p.kb_per_split : 0;
+  }
+}
 
 
 struct EpiFlags {
@@ -376,8 +408,10 @@ ERGM_DEVINL void epilogue_tile(const GemmParams& p, const EpiFlags& ep, uint32_t
 template <int BN, int EC, int FM>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                 const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmap_b, const GemmParams p_in) {
   using Cfg = GemmCfg<BN>;
+  GemmParams p = p_in;
+  apply_dyn(p, BM, (int)gridDim.x);
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle needs 1024-byte aligned tiles
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -553,8 +587,10 @@ struct Gemm2Cfg {
 template <int BN, int EC, int FM>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                  const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+                  const __grid_constant__ CUtensorMap tmap_b, const GemmParams p_in) {
   using Cfg = Gemm2Cfg<BN>;
+  GemmParams p = p_in;
+  apply_dyn(p, 256, (int)(gridDim.x >> 1));
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stage_all = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
@@ -734,6 +770,7 @@ static int launch_gemm2(const ergm_gemm_args* a, cudaStream_t stream) {
   p.split_k = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   p.dropout_p = a->dropout_p;
   p.site = make_site(a->seed, a->offset, a->dropout_p, (uint32_t)a->N);
+  p.dyn = a->dyn_count; p.dyn_dim = a->dyn_count ? a->dyn_dim : 0;
   ERGM_SET_SMEM_ATTR((gemm2_bf16_kernel<BN, EC, FM>), Cfg::SMEM_BYTES);
   const int total = p.m_tiles * p.n_tiles * p.split_k;
   const int max_clusters = num_sms() / 2;
@@ -786,6 +823,7 @@ static int launch_gemm(const ergm_gemm_args* a, cudaStream_t stream) {
   p.split_k = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
   p.dropout_p = a->dropout_p;
   p.site = make_site(a->seed, a->offset, a->dropout_p, (uint32_t)a->N);
+  p.dyn = a->dyn_count; p.dyn_dim = a->dyn_count ? a->dyn_dim : 0;
 
   ERGM_SET_SMEM_ATTR((gemm_bf16_kernel<BN, EC, FM>), Cfg::SMEM_BYTES);
   const int total = p.m_tiles * p.n_tiles * p.split_k;
@@ -819,6 +857,8 @@ extern "C" int ergm_gemm_bf16(const ergm_gemm_args* a, void* stream) {
   if ((a->epilogue & ERGM_EPI_BIAS) && (reinterpret_cast<uintptr_t>(a->bias) & 15))
     return ERGM_ERR_ARG;
   if (a->lda % 8 || a->ldb % 8) return ERGM_ERR_ARG;
+  if (a->dyn_count && a->dyn_dim != 1 && a->dyn_dim != 2) return ERGM_ERR_ARG;
+  if (a->dyn_count && a->dyn_dim == 2 && !(a->epilogue & ERGM_EPI_ATOMIC)) return ERGM_ERR_ARG;  // K = 0 must write nothing
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   int bn = a->block_n;
   if (bn == 0 && a->M >= 512 && a->N >= 256) {

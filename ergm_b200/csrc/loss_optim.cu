@@ -38,10 +38,16 @@ ERGM_DEVINL float load1(const void* row, int col) {
              : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(row)[col]);
 }
 
-// target of logits row (b, t) is labels[b, t+1]; the last position has none
+// target of logits row (b, t) is labels[b, t+1]; the last position has none.  T == 0: `labels` is already
+// aligned with the rows (compacted label-sparse LM head: row i scores labels[i]).
 ERGM_DEVINL int64_t shifted_target(const int64_t* labels, int row, int T) {
+  if (T == 0) return labels[row];
   const int t = row % T;
   return (t + 1 < T) ? labels[row + 1] : (int64_t)-100;
+}
+// rows at or beyond the 128-aligned run-time row count take no part at all (their buffers are never read)
+ERGM_DEVINL bool row_beyond_dyn(const int* rows_dyn, int row) {
+  return rows_dyn && row >= ((*rows_dyn + 127) & ~127);
 }
 
 // One CTA per row.  Rows whose target is ignore_index are skipped (lse = 0, loss = 0).
@@ -50,9 +56,11 @@ __global__ void __launch_bounds__(CE_THREADS)
 ce_fwd_kernel(const void* __restrict__ logits, int64_t ldl, const int64_t* __restrict__ labels,
               int T, int V, float* __restrict__ lse_out, float* __restrict__ row_loss,
               float* __restrict__ sums /* [0]=loss sum, [1]=valid count */, int* err_flag,
-              const __nv_bfloat16* __restrict__ hn, const __nv_bfloat16* __restrict__ w, int H) {
+              const __nv_bfloat16* __restrict__ hn, const __nv_bfloat16* __restrict__ w, int H,
+              const int* __restrict__ rows_dyn) {
   __shared__ float sm[CE_THREADS / 32], ss[CE_THREADS / 32], st[CE_THREADS / 32];
   const int row = blockIdx.x;
+  if (row_beyond_dyn(rows_dyn, row)) return;
   const int64_t tgt = shifted_target(labels, row, T);
   if (tgt == -100) {
     if (threadIdx.x == 0) { lse_out[row] = 0.f; row_loss[row] = 0.f; }
@@ -118,8 +126,9 @@ template <bool F32>
 __global__ void __launch_bounds__(CE_THREADS)
 ce_bwd_kernel(const void* __restrict__ logits, int64_t ldl, const int64_t* __restrict__ labels,
               int T, int V, const float* __restrict__ lse, const float* __restrict__ scale_ptr,
-              __nv_bfloat16* __restrict__ dlogits, int64_t ldd) {
+              __nv_bfloat16* __restrict__ dlogits, int64_t ldd, const int* __restrict__ rows_dyn) {
   const int row = blockIdx.x;
+  if (row_beyond_dyn(rows_dyn, row)) return;
   const int64_t tgt = shifted_target(labels, row, T);
   __nv_bfloat16* dp = dlogits + (int64_t)row * ldd;
   const int nvec = (int)(ldd / 8);  // whole padded row is written so the pad stays finite
@@ -284,38 +293,135 @@ adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __r
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Label-sparse LM head.  model.py:698-708 scores EVERY position with the [H, V] head and then ignores the
+// positions whose shifted label is -100 (the dialogue history: ~90 % of a MELD-shaped batch).  Loss and all
+// gradients only depend on the scored rows, so the head runs on the compacted rows: plan (ordered stream
+// compaction of the scored row indices + their targets, on the device: no host synchronisation, CUDA-graph
+// safe), gather of the ln_f output rows, GEMM / CE / dgrad / wgrad with a run-time row count, scatter of
+// d(ln_f output) back.  `.logits` of all positions are produced only if somebody reads them.
+// ------------------------------------------------------------------------------------------
+constexpr int PLAN_THREADS = 1024;
+__global__ void __launch_bounds__(PLAN_THREADS)
+lm_rows_plan_kernel(const int64_t* __restrict__ labels, int rows, int T, int* __restrict__ row_idx,
+                    int64_t* __restrict__ labels_c, int* __restrict__ count_out) {
+  __shared__ int s_warp[PLAN_THREADS / 32];
+  __shared__ int s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int r0 = 0; r0 < rows; r0 += PLAN_THREADS) {
+    const int row = r0 + tid;
+    const int64_t tgt = row < rows ? shifted_target(labels, row, T) : (int64_t)-100;
+    const bool keep = tgt != -100;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < PLAN_THREADS / 32; ++w) {
+      const int c = s_warp[w];
+      before += w < warp ? c : 0;
+      total += c;
+    }
+    if (keep) {
+      const int dst = s_base + before + __popc(m & ((1u << lane) - 1u));
+      row_idx[dst] = row;
+      labels_c[dst] = tgt;
+    }
+    __syncthreads();
+    if (tid == 0) s_base += total;
+    __syncthreads();
+  }
+  const int n = s_base;
+  // pad up to the next multiple of 128 rows: ignored targets, "no source row"
+  for (int i = n + tid; i < ((n + 127) & ~127) && i < rows; i += PLAN_THREADS) { row_idx[i] = -1; labels_c[i] = -100; }
+  if (tid == 0) *count_out = n;
+}
+
+// dst[i, :] = src[row_idx[i], :] for i < count; zero rows up to the next multiple of 128 (bf16, 16-byte vectors)
+__global__ void __launch_bounds__(256)
+gather_rows_dyn_kernel(const __nv_bfloat16* __restrict__ src, const int* __restrict__ row_idx,
+                       const int* __restrict__ count, __nv_bfloat16* __restrict__ dst, int H, int cap) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = *count, n_pad = min((n + 127) & ~127, cap);
+  for (int i = blockIdx.x * 8 + warp; i < n_pad; i += gridDim.x * 8) {
+    uint4* d = reinterpret_cast<uint4*>(dst + (int64_t)i * H);
+    if (i < n) {
+      const uint4* s = reinterpret_cast<const uint4*>(src + (int64_t)row_idx[i] * H);
+      for (int c = lane; c < H / 8; c += 32) d[c] = s[c];
+    } else {
+      for (int c = lane; c < H / 8; c += 32) d[c] = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+}
+
+// dst[row_idx[i], :] = src[i, :] for i < count (fp32; the scored rows are distinct, plain stores)
+__global__ void __launch_bounds__(256)
+scatter_rows_dyn_kernel(const float* __restrict__ src, const int* __restrict__ row_idx,
+                        const int* __restrict__ count, float* __restrict__ dst, int H) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = *count;
+  for (int i = blockIdx.x * 8 + warp; i < n; i += gridDim.x * 8) {
+    const float4* s = reinterpret_cast<const float4*>(src + (int64_t)i * H);
+    float4* d = reinterpret_cast<float4*>(dst + (int64_t)row_idx[i] * H);
+    for (int c = lane; c < H / 4; c += 32) d[c] = s[c];
+  }
+}
+
 }  // namespace ergm
 
 using namespace ergm;
 
+extern "C" int ergm_lm_rows_plan(const int64_t* labels, int rows, int T, int* row_idx, int64_t* labels_c,
+                                 int* count, void* stream) {
+  if (!labels || !row_idx || !labels_c || !count || rows <= 0 || T <= 0) return ERGM_ERR_ARG;
+  lm_rows_plan_kernel<<<1, PLAN_THREADS, 0, (cudaStream_t)stream>>>(labels, rows, T, row_idx, labels_c, count);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int ergm_gather_rows_dyn(const void* src_bf16, const int* row_idx, const int* count, void* dst_bf16,
+                                    int H, int cap, void* stream) {
+  if (!src_bf16 || !row_idx || !count || !dst_bf16 || H <= 0 || H % 8 || cap <= 0) return ERGM_ERR_ARG;
+  gather_rows_dyn_kernel<<<num_sms() * 2, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src_bf16), row_idx, count, reinterpret_cast<__nv_bfloat16*>(dst_bf16), H, cap);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int ergm_scatter_rows_dyn(const float* src, const int* row_idx, const int* count, float* dst, int H,
+                                     void* stream) {
+  if (!src || !row_idx || !count || !dst || H <= 0 || H % 4) return ERGM_ERR_ARG;
+  scatter_rows_dyn_kernel<<<num_sms() * 2, 256, 0, (cudaStream_t)stream>>>(src, row_idx, count, dst, H);
+  return (int)cudaGetLastError();
+}
+
 extern "C" int ergm_ce_fwd(const void* logits, int logits_is_f32, int64_t ldl, const int64_t* labels,
                            int rows, int T, int V, float* lse, float* row_loss, float* sums,
                            int* err_flag, const void* hn_bf16, const void* w_bf16, int H,
-                           void* stream) {
-  if (!logits || !labels || !lse || !row_loss || !sums || !err_flag || rows <= 0 || T <= 0 || V <= 0)
+                           const int* rows_dyn, void* stream) {
+  if (!logits || !labels || !lse || !row_loss || !sums || !err_flag || rows <= 0 || T < 0 || V <= 0)
     return ERGM_ERR_ARG;
   if (ldl % 8 || (reinterpret_cast<uintptr_t>(logits) & 15)) return ERGM_ERR_ARG;
   if ((hn_bf16 != nullptr) != (w_bf16 != nullptr) || (hn_bf16 && H % 8)) return ERGM_ERR_ARG;
   const __nv_bfloat16* hn = reinterpret_cast<const __nv_bfloat16*>(hn_bf16);
   const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(w_bf16);
   if (logits_is_f32)
-    ce_fwd_kernel<true><<<rows, CE_THREADS, 0, (cudaStream_t)stream>>>(logits, ldl, labels, T, V, lse, row_loss, sums, err_flag, hn, w, H);
+    ce_fwd_kernel<true><<<rows, CE_THREADS, 0, (cudaStream_t)stream>>>(logits, ldl, labels, T, V, lse, row_loss, sums, err_flag, hn, w, H, rows_dyn);
   else
-    ce_fwd_kernel<false><<<rows, CE_THREADS, 0, (cudaStream_t)stream>>>(logits, ldl, labels, T, V, lse, row_loss, sums, err_flag, hn, w, H);
+    ce_fwd_kernel<false><<<rows, CE_THREADS, 0, (cudaStream_t)stream>>>(logits, ldl, labels, T, V, lse, row_loss, sums, err_flag, hn, w, H, rows_dyn);
   return (int)cudaGetLastError();
 }
 
 extern "C" int ergm_ce_bwd(const void* logits, int logits_is_f32, int64_t ldl, const int64_t* labels,
                            int rows, int T, int V, const float* lse, const float* scale_ptr,
-                           void* dlogits_bf16, int64_t ldd, void* stream) {
-  if (!logits || !labels || !lse || !scale_ptr || !dlogits_bf16 || rows <= 0) return ERGM_ERR_ARG;
+                           void* dlogits_bf16, int64_t ldd, const int* rows_dyn, void* stream) {
+  if (!logits || !labels || !lse || !scale_ptr || !dlogits_bf16 || rows <= 0 || T < 0) return ERGM_ERR_ARG;
   if (ldl % 8 || ldd % 8 || ldd < V) return ERGM_ERR_ARG;
   if (logits_is_f32)
     ce_bwd_kernel<true><<<rows, CE_THREADS, 0, (cudaStream_t)stream>>>(
-        logits, ldl, labels, T, V, lse, scale_ptr, reinterpret_cast<__nv_bfloat16*>(dlogits_bf16), ldd);
+        logits, ldl, labels, T, V, lse, scale_ptr, reinterpret_cast<__nv_bfloat16*>(dlogits_bf16), ldd, rows_dyn);
   else
     ce_bwd_kernel<false><<<rows, CE_THREADS, 0, (cudaStream_t)stream>>>(
-        logits, ldl, labels, T, V, lse, scale_ptr, reinterpret_cast<__nv_bfloat16*>(dlogits_bf16), ldd);
+        logits, ldl, labels, T, V, lse, scale_ptr, reinterpret_cast<__nv_bfloat16*>(dlogits_bf16), ldd, rows_dyn);
   return (int)cudaGetLastError();
 }
 

@@ -56,6 +56,7 @@ class Engine:
         self.ws_train = Workspace(self.device)
         self.ws_eval = Workspace(self.device)
         self.saved = None
+        self.forward_serial = 0
         self.seed = 0x5EED
         self.site_counter = 0
         self.rng_step = None
@@ -193,6 +194,7 @@ class Engine:
         pd_res = cfg.resid_pdrop if (training and dropout is None) else (dropout or 0.0) if training else 0.0
         site0 = self._new_sites(training)
         seed = self.seed
+        self.forward_serial = getattr(self, "forward_serial", 0) + 1
 
         def lname(base, l):
             return "%s_%d" % (base, l) if save else base
@@ -310,11 +312,17 @@ class Engine:
         out = dict(hidden=hn, kv_present=kv_present, B=B, T=T)
         ldl = (V + 63) // 64 * 64  # padded leading dimension: 16-byte rows for TMA / vector access
         logits = None
-        need_lm = want_logits or labels is not None
+        # Label-sparse LM head: with labels, only the rows whose shifted label is not -100 enter the loss and the
+        # gradients (model.py:705-708), so the head / CE / their backward run on those rows alone (run-time row
+        # count on the device: no host sync, one captured graph serves every batch).  The logits of ALL positions
+        # (outputs.logits, main.py:160) are produced by full_logits() only when somebody reads them.
+        sparse = (labels is not None and not want_logits and not logits_fp32
+                  and getattr(self.model, "ergm_sparse_lm_head", True))
+        need_lm = (want_logits or labels is not None) and not sparse
         if need_lm:
-            logits = ws.get("logits32" if logits_fp32 else "logits", (M, ldl), f32 if logits_fp32 else bf16)
-            ops.gemm(hn, self.pb("transformer.wte.weight"), logits, M=M, N=V, K=H, a_major=K_MAJOR, b_major=K_MAJOR)
-            out["logits"] = logits
+            logits = self.full_logits(hn, ws, logits_fp32)
+        out["logits"] = logits
+        out["logits_src"] = (hn, ws, logits_fp32)
         sums = ws.get("loss_sums", (4,), f32)
         sums.zero_()
         losses = ws.get("losses", (5,), f32)
@@ -326,7 +334,22 @@ class Engine:
                              B=B, T=T)
         out["emotion_logits"] = emo_logits
         lse = row_loss = None
-        if labels is not None:
+        sp = None
+        if sparse:
+            i32 = torch.int32
+            sp = dict(row_idx=ws.get("lm_row_idx", (M,), i32), labels_c=ws.get("lm_labels_c", (M,), torch.int64),
+                      count=ws.get("lm_count", (1,), i32), hn_c=ws.get("lm_hn_c", (M, H), bf16),
+                      logits_c=ws.get("lm_logits_c", (M, ldl), bf16))
+            wte_b = self.pb("transformer.wte.weight")
+            ops.lm_rows_plan(labels, sp["row_idx"], sp["labels_c"], sp["count"], T=T)
+            ops.gather_rows_dyn(hn, sp["row_idx"], sp["count"], sp["hn_c"])
+            ops.gemm(sp["hn_c"], wte_b, sp["logits_c"], M=M, N=V, K=H, a_major=K_MAJOR, b_major=K_MAJOR,
+                     dyn_m=sp["count"])
+            lse = ws.get("ce_lse", (M,), f32)
+            row_loss = ws.get("ce_row_loss", (M,), f32)
+            ops.ce_fwd(sp["logits_c"], sp["labels_c"], lse, row_loss, sums, T=0, V=V, hn=sp["hn_c"], w=wte_b,
+                       rows_dyn=sp["count"])
+        elif labels is not None:
             lse = ws.get("ce_lse", (M,), f32)
             row_loss = ws.get("ce_row_loss", (M,), f32)
             ops.ce_fwd(logits, labels, lse, row_loss, sums, T=T, V=V, hn=hn, w=self.pb("transformer.wte.weight"))
@@ -336,7 +359,7 @@ class Engine:
         out["has_emo"] = emotion_labels is not None
         if save:
             sv.update(xf=x, hn=hn, meanf=meanf, rstdf=rstdf, logits=logits, ce_lse=lse, hlast=hlast,
-                      emo_dlog=emo_dlog, losses=losses, ldl=ldl)
+                      emo_dlog=emo_dlog, losses=losses, ldl=ldl, sparse=sp)
             # One set of saved activations exists (named, reused workspaces): tag it so that a backward through
             # an OLDER forward - loss = model(a).loss + model(b).loss - fails loudly instead of differentiating
             # through the wrong activations.
@@ -345,6 +368,15 @@ class Engine:
             out["forward_id"] = self.forward_id
             self.saved = sv
         return out
+
+    def full_logits(self, hn, ws, logits_fp32=False):
+        """LM head on every position: logits[M, ldl] = ln_f(x) @ wte^T (model.py:698)."""
+        M, H, V = hn.shape[0], self.H, self.V
+        ldl = (V + 63) // 64 * 64
+        f32, bf16 = torch.float32, torch.bfloat16
+        logits = ws.get("logits32" if logits_fp32 else "logits", (M, ldl), f32 if logits_fp32 else bf16)
+        ops.gemm(hn, self.pb("transformer.wte.weight"), logits, M=M, N=V, K=H, a_major=K_MAJOR, b_major=K_MAJOR)
+        return logits
 
     # ------------------------------------------------------------------
     # fp32 mode: forward-only verification path (north_star: logits within 1e-4, greedy ids exact)
@@ -543,7 +575,25 @@ class Engine:
         ops.scalar_mul(grad_loss, losses[4:5], scales[1:2])  # g / n_samples
         dhn = ws.get("dhn", (M, H), f32)
         hn = sv["hn"]
-        if sv["labels"] is not None:
+        sp = sv.get("sparse")
+        if sp is not None:
+            # label-sparse head backward on the compacted rows (run-time count sp["count"])
+            ldl = sv["ldl"]
+            cnt = sp["count"]
+            dlogits_c = ws.get("lm_dlogits_c", (M, ldl), bf16)
+            ops.ce_bwd(sp["logits_c"], sp["labels_c"], sv["ce_lse"], scales[0:1], dlogits_c, T=0, V=V, rows_dyn=cnt)
+            wte_b = self.pb("transformer.wte.weight")
+            dhn_c = ws.get("lm_dhn_c", (M, H), f32)
+            dhn_c.zero_()
+            # d hn_c = dlogits_c @ wte: few row tiles, very long K (= V): the kernel splits K itself to fill the GPU
+            ops.gemm(dlogits_c, wte_b, dhn_c, M=M, N=H, K=V, a_major=K_MAJOR, b_major=MN_MAJOR, epilogue=L.EPI_ATOMIC,
+                     block_n=2256, dyn_m=cnt)
+            dhn.zero_()
+            ops.scatter_rows_dyn(dhn_c, sp["row_idx"], cnt, dhn)
+            # d wte += dlogits_c^T @ hn_c (reduction over the run-time row count)
+            ops.gemm(dlogits_c, sp["hn_c"], self.pg("transformer.wte.weight"), M=V, N=H, K=M, a_major=MN_MAJOR,
+                     b_major=MN_MAJOR, epilogue=L.EPI_ATOMIC, block_n=2256, dyn_k=cnt)
+        elif sv["labels"] is not None:
             ldl = sv["ldl"]
             dlogits = ws.get("dlogits", (M, ldl), bf16)
             ops.ce_bwd(sv["logits"], sv["labels"], sv["ce_lse"], scales[0:1], dlogits, T=T, V=V)

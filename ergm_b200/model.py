@@ -360,6 +360,9 @@ class GPT2LMHeadModel(GPT2PreTrainedModel):
         self._engine = None
         self._dp = None  # set by ergm_b200.parallel.DataParallel
         self.fp32_logits = False
+        # label-sparse LM head (engine.forward): with labels, head + CE + their backward run only on the rows whose
+        # shifted label is not -100; identical loss and gradients, outputs.logits computed on first access
+        self.ergm_sparse_lm_head = True
         # "bf16" = bf16 tensor-core operands, fp32 accumulation / residual / statistics (throughput mode);
         # "fp32" = split-operand fp32-accurate products (forward only; logits within 1e-4 of the reference)
         self.ergm_precision = "bf16"
@@ -490,9 +493,10 @@ class GPT2LMHeadModel(GPT2PreTrainedModel):
                                        pos, kv_lens=kv_lens)
                 use_cache = False
             else:
+                # with labels the LM head runs label-sparse and .logits (all positions) is computed on first access
                 out = eng.forward(input_ids, token_type_ids, labels, emotion_labels, imgs, auds, caption_ids, pos,
                                   past_len=0, kv_lens=kv_lens, training=self.training, save=save,
-                                  want_logits=True, logits_fp32=self.fp32_logits)
+                                  want_logits=labels is None, logits_fp32=self.fp32_logits)
             loss = lm_loss = emo_loss = None
             if labels is not None or emotion_labels is not None:
                 if self._dp is not None:
@@ -507,9 +511,19 @@ class GPT2LMHeadModel(GPT2PreTrainedModel):
                 emo_loss = losses[2].clone() if emotion_labels is not None else None
             V = eng.V
             logits_buf = out["logits"]
+            logits_src = out.get("logits_src")
+            fwd_serial = eng.forward_serial
 
             def logits_fn():
-                return logits_buf[:, :V].to(torch.float32).view(B, T, V)
+                buf = logits_buf
+                if buf is None:
+                    # lazily: ln_f output of THIS forward is valid until the next forward of the model
+                    if eng.forward_serial != fwd_serial:
+                        raise L.ErgmError("outputs.logits must be read before the next forward of the same model "
+                                          "(the label-sparse LM head computes all-position logits on demand)")
+                    with torch.cuda.device(dev):
+                        buf = eng.full_logits(*logits_src)
+                return buf[:, :V].to(torch.float32).view(B, T, V)
 
             past_fn = _past_fn(out["kv_present"], B, eng.H, eng.nh, False) if use_cache else None
 

@@ -22,7 +22,7 @@ def _ptr(t):
 
 def gemm(a, b, d, *, M, N, K, a_major=L.ERGM_MAJOR_K, b_major=L.ERGM_MAJOR_MN, lda=None, ldb=None,
          ldd=None, bias=None, residual=None, ldr=None, preact=None, gelu_grad_of=None, epilogue=0, split_k=1,
-         block_n=0, dropout_p=0.0, seed=0, offset=0, colsum=None):
+         block_n=0, dropout_p=0.0, seed=0, offset=0, colsum=None, dyn_m=None, dyn_k=None):
     """D[M,N] = epilogue(A * B).  a/b bf16, d bf16 or fp32.  See include/ergm_b200.h."""
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     args = L.GemmArgs()
@@ -54,6 +54,10 @@ def gemm(a, b, d, *, M, N, K, a_major=L.ERGM_MAJOR_K, b_major=L.ERGM_MAJOR_MN, l
     args.block_n = block_n
     args.dropout_p = dropout_p
     args.seed, args.offset = seed, offset
+    if dyn_m is not None or dyn_k is not None:  # device int32 count bounding M or K at run time (see header)
+        dyn = dyn_m if dyn_m is not None else dyn_k
+        assert dyn.dtype == torch.int32
+        args.dyn_count, args.dyn_dim = dyn.data_ptr(), 1 if dyn_m is not None else 2
     global _launch_count
     _launch_count += 1
     if PROFILE is not None:
@@ -248,17 +252,32 @@ def attn_bwd(q, k, v, out, dout, lse, delta, dq_accum, dk, dv, *, B, nh, Tq, Tk,
           dropout_p, seed, offset)
 
 
-def ce_fwd(logits, labels, lse, row_loss, sums, *, T, V, hn=None, w=None):
+def ce_fwd(logits, labels, lse, row_loss, sums, *, T, V, hn=None, w=None, rows_dyn=None):
+    """T = 0: labels already aligned with the (compacted) rows; rows_dyn: device int32 run-time row count."""
     rows = logits.shape[0]
     _call("ergm_ce_fwd", logits.data_ptr(), int(logits.dtype == torch.float32), logits.stride(0), labels.data_ptr(),
           rows, T, V, lse.data_ptr(), row_loss.data_ptr(), sums.data_ptr(), err_flag(logits.device).data_ptr(),
-          _p(hn), _p(w), hn.shape[1] if hn is not None else 0)
+          _p(hn), _p(w), hn.shape[1] if hn is not None else 0, _p(rows_dyn))
 
 
-def ce_bwd(logits, labels, lse, scale, dlogits, *, T, V):
+def ce_bwd(logits, labels, lse, scale, dlogits, *, T, V, rows_dyn=None):
     rows = logits.shape[0]
     _call("ergm_ce_bwd", logits.data_ptr(), int(logits.dtype == torch.float32), logits.stride(0), labels.data_ptr(),
-          rows, T, V, lse.data_ptr(), scale.data_ptr(), dlogits.data_ptr(), dlogits.stride(0))
+          rows, T, V, lse.data_ptr(), scale.data_ptr(), dlogits.data_ptr(), dlogits.stride(0), _p(rows_dyn))
+
+
+def lm_rows_plan(labels, row_idx, labels_c, count, *, T):
+    _call("ergm_lm_rows_plan", labels.data_ptr(), labels.numel(), T, row_idx.data_ptr(), labels_c.data_ptr(),
+          count.data_ptr())
+
+
+def gather_rows_dyn(src, row_idx, count, dst):
+    _call("ergm_gather_rows_dyn", src.data_ptr(), row_idx.data_ptr(), count.data_ptr(), dst.data_ptr(), src.shape[1],
+          dst.shape[0])
+
+
+def scatter_rows_dyn(src, row_idx, count, dst):
+    _call("ergm_scatter_rows_dyn", src.data_ptr(), row_idx.data_ptr(), count.data_ptr(), dst.data_ptr(), src.shape[1])
 
 
 def emotion_head_fwd(x_final, mean, rstd, gamma, beta, w_emo, emo_labels, hlast, logits, dlogits, sums, *, B, T):

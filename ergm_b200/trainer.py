@@ -52,7 +52,7 @@ class GraphedTrainStep:
         ops.reset_launch_count()
         out = eng.forward(b["input_ids"], b.get("token_type_ids"), b.get("labels"), b.get("emotion_labels"),
                           b.get("imgs"), b.get("auds"), b.get("caption_ids"), None, training=model.training,
-                          save=True, want_logits=True, logits_fp32=model.fp32_logits)
+                          save=True, want_logits=False, logits_fp32=model.fp32_logits)
         if self.dp is not None:
             self.dp.reduce_loss_sums(out["loss_sums"])
         losses = eng.finalize_loss(out)

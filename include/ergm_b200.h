@@ -81,6 +81,11 @@ typedef struct ergm_gemm_args {
                           2128 / 2256 = CTA-pair (cta_group::2) kernel, 256 x {128,256} tiles */
   float dropout_p;
   uint64_t seed, offset; /* Philox key / subsequence of this dropout site */
+  const int32_t* dyn_count; /* NULL, or a DEVICE int32: run-time extent (<= the static M / K) read by the kernel, so
+                               that one captured launch serves every batch (label-sparse LM head, packed batches) */
+  int32_t dyn_dim;     /* 1: dyn_count bounds M (rows beyond it are not stored; with ERGM_EPI_ATOMIC the kernel picks
+                          the K split itself); 2: dyn_count bounds K (ERGM_EPI_ATOMIC only; operand rows in
+                          [count, roundup(count, 128)) must be zero) */
 } ergm_gemm_args;
 
 int ergm_gemm_bf16(const ergm_gemm_args* args, void* stream);
@@ -180,14 +185,28 @@ int ergm_attn_bwd(const void* q, int64_t ld_q, int q_col0, const void* k, int64_
 /* ignore_index=-100 (model.py:705-708): row (b,t) is scored against          */
 /* labels[b,t+1].  sums[0] += sum of row losses, sums[1] += valid rows.       */
 /* hn / w (nullable, bf16 [rows,H] / [V,H]): when given, the target logit is
- * recomputed as their fp32 dot product instead of read from rounded logits.  */
+ * recomputed as their fp32 dot product instead of read from rounded logits.
+ * T == 0: labels[row] is the target of row `row` (compacted rows of the label-sparse head).
+ * rows_dyn (nullable device int): rows >= roundup(*rows_dyn, 128) are not touched.            */
 int ergm_ce_fwd(const void* logits, int logits_is_f32, int64_t ldl, const int64_t* labels,
                 int rows, int T, int V, float* lse, float* row_loss, float* sums, int* err_flag,
-                const void* hn_bf16, const void* w_bf16, int H, void* stream);
+                const void* hn_bf16, const void* w_bf16, int H, const int* rows_dyn, void* stream);
 /* dlogits = (softmax - onehot) * (*scale_ptr), zero for ignored rows (bf16)   */
 int ergm_ce_bwd(const void* logits, int logits_is_f32, int64_t ldl, const int64_t* labels,
                 int rows, int T, int V, const float* lse, const float* scale_ptr,
-                void* dlogits_bf16, int64_t ldd, void* stream);
+                void* dlogits_bf16, int64_t ldd, const int* rows_dyn, void* stream);
+/* Label-sparse LM head (model.py:698-708 scores every position, then ignores the -100 ones): the head, its
+ * CE and their backward run on the compacted scored rows only.                                  */
+/* plan: ordered compaction of the rows whose shifted label is not -100 -> row_idx[i] (int32 source row),
+ * labels_c[i] (its target), *count; entries up to the next multiple of 128 are padded (-1 / -100).  */
+int ergm_lm_rows_plan(const int64_t* labels, int rows, int T, int* row_idx, int64_t* labels_c, int* count,
+                      void* stream);
+/* dst[i] = src[row_idx[i]] (bf16 [.., H]) for i < *count, zero rows up to the next multiple of 128 */
+int ergm_gather_rows_dyn(const void* src_bf16, const int* row_idx, const int* count, void* dst_bf16, int H,
+                         int cap, void* stream);
+/* dst[row_idx[i]] = src[i] (fp32 [.., H]) for i < *count */
+int ergm_scatter_rows_dyn(const float* src, const int* row_idx, const int* count, float* dst, int H,
+                          void* stream);
 /* Emotion head on the last position + 7-way CE (model.py:700-701,710-711).   */
 /* sums[2] += sum of sample losses, sums[3] += samples.                       */
 int ergm_emotion_head_fwd(const float* x_final, const float* mean, const float* rstd,

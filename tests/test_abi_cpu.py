@@ -3,6 +3,7 @@ exports every symbol include/ergm_b200.h declares; the Python model mirrors the 
 module tree; the product path refuses to run without CUDA (no CPU fallback)."""
 import ctypes
 import os
+import subprocess
 
 import pytest
 import torch
@@ -40,10 +41,21 @@ def test_header_is_plain_c():
         assert r.returncode == 0, r.stderr
 
 
-def test_gemm_args_struct_matches_header():
+def test_gemm_args_struct_matches_header(tmp_path):
+    """The ctypes mirror of ergm_gemm_args has the size and field offsets a C compiler gives the header's struct."""
     from ergm_b200 import _lib
-    # 7 pointers + 4 int64 + 9 int32 + float + 2 uint64, natural alignment
-    assert ctypes.sizeof(_lib.GemmArgs) == 7 * 8 + 4 * 8 + 9 * 4 + 4 + 2 * 8
+    src = tmp_path / "sz.c"
+    fields = [f[0] for f in _lib.GemmArgs._fields_]
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ergm_b200.h"\nint main(void) {\n'
+                   '  printf("%zu", sizeof(ergm_gemm_args));\n'
+                   + "".join('  printf(" %%zu", offsetof(ergm_gemm_args, %s));\n' % f for f in fields)
+                   + "  return 0;\n}\n")
+    exe = tmp_path / "sz"
+    r = subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    nums = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()]
+    assert ctypes.sizeof(_lib.GemmArgs) == nums[0]
+    assert [getattr(_lib.GemmArgs, f).offset for f in fields] == nums[1:]
 
 
 def test_argument_errors_without_gpu(lib):
