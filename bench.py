@@ -99,8 +99,15 @@ def train_flops_per_token(H, L, V, T, Tc, caption=True):
     return 3 * fwd, 3 * (L * per_layer + 2 * H * V)
 
 
-def gemm_flops(info):
+def gemm_flops(info, dyn_count=None):
+    """Algorithmic FLOPs of one launch; launches whose M / K extent is bounded at run time by a device-side count
+    (label-sparse LM head) are counted with that count, not with their static capacity."""
     M, N, K = info[0], info[1], info[2]
+    dyn = info[6] if len(info) > 6 else 0
+    if dyn == 1 and dyn_count is not None:
+        M = min(M, dyn_count)
+    if dyn == 2 and dyn_count is not None:
+        K = min(K, dyn_count)
     return 2.0 * M * N * K
 
 
@@ -352,7 +359,9 @@ def main():
             torch.cuda.synchronize()
             prof, ops.PROFILE = ops.PROFILE, None
             g_ms = sum(a.elapsed_time(b) for n, i, a, b in prof if n == "ergm_gemm_bf16") / 2
-            g_fl = sum(gemm_flops(i) for n, i, a, b in prof if n == "ergm_gemm_bf16") / 2
+            # rows the label-sparse LM head scores in this batch (shifted labels != -100)
+            n_scored = int((batch["labels"][:, 1:] != -100).sum())
+            g_fl = sum(gemm_flops(i, n_scored) for n, i, a, b in prof if n == "ergm_gemm_bf16") / 2
             n_gemm = sum(1 for n, i, a, b in prof if n == "ergm_gemm_bf16") // 2
             by = {}
             for n, i, a, b in prof:
@@ -360,10 +369,15 @@ def main():
             shapes = {}
             for n, i, a, b in prof:
                 if n == "ergm_gemm_bf16":
-                    k = "M%d N%d K%d a%d b%d sk%d" % i
+                    k = "M%d N%d K%d a%d b%d sk%d" % i[:6] + (" dyn%s=%d" % ("MK"[i[6] - 1], n_scored) if i[6] else "")
                     t, c = shapes.get(k, (0.0, 0))
                     shapes[k] = (t + a.elapsed_time(b) / 2, c + 0.5)
-            by_shape = {k: {"ms": round(t, 3), "launches": c, "tflops": round(gemm_flops([int(x[1:]) for x in k.split()[:3]]) * c / (t / 1e3) / 1e12, 1)}
+            def shape_flops(k):
+                f = k.split()
+                info = [int(x[1:]) for x in f[:3]] + [0, 0, 0, ({"M": 1, "K": 2}[f[6][3]] if len(f) > 6 else 0)]
+                return gemm_flops(info, n_scored)
+
+            by_shape = {k: {"ms": round(t, 3), "launches": c, "tflops": round(shape_flops(k) * c / (t / 1e3) / 1e12, 1)}
                         for k, (t, c) in sorted(shapes.items(), key=lambda kv: -kv[1][0])}
             achieved = g_fl / (g_ms / 1e3) / 1e12
             roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": achieved,

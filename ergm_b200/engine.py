@@ -17,6 +17,7 @@ from . import ops
 from .param_store import ParamStore
 
 K_MAJOR, MN_MAJOR = L.ERGM_MAJOR_K, L.ERGM_MAJOR_MN
+_RNG_KEEPALIVE = []  # device step counters ever handed to ergm_set_rng_step_ptr (see Engine.set_rng_step_tensor)
 
 
 def _pad8(n):
@@ -116,8 +117,18 @@ class Engine:
         return self.site_counter * 4096
 
     def set_rng_step_tensor(self, t):
-        """Registers a device uint64 step counter (see ergm_set_rng_step_ptr)."""
+        """Registers a device uint64 step counter (see ergm_set_rng_step_ptr).  The library keeps ONE raw pointer
+        for the whole process and every dropout kernel dereferences it, so (a) a registered tensor is kept alive
+        for the life of the process (8 bytes) - a freed counter would be a dangling device pointer - and (b) each
+        training forward / backward of an engine re-registers its own counter (or none), so that engines and raw
+        kernel calls never read another trainer's counter."""
         self.rng_step = t
+        if t is not None:
+            _RNG_KEEPALIVE.append(t)
+        self._apply_rng_step()
+
+    def _apply_rng_step(self):
+        t = self.rng_step
         L.check(L.lib().ergm_set_rng_step_ptr(t.data_ptr() if t is not None else None), "ergm_set_rng_step_ptr")
 
     # GEMM helpers ------------------------------------------------------
@@ -194,6 +205,8 @@ class Engine:
         pd_res = cfg.resid_pdrop if (training and dropout is None) else (dropout or 0.0) if training else 0.0
         site0 = self._new_sites(training)
         seed = self.seed
+        if training:
+            self._apply_rng_step()
         self.forward_serial = getattr(self, "forward_serial", 0) + 1
 
         def lname(base, l):
@@ -551,6 +564,7 @@ class Engine:
                                "loss.backward() before the next training forward (accumulate gradients across "
                                "backward calls instead of summing losses)" % (forward_id, sv["id"]))
         self.saved = None
+        self._apply_rng_step()
         cfg, H, nh, Lyr, I, V = self.cfg, self.H, self.nh, self.L, self.I, self.V
         B, T, Tc = sv["B"], sv["T"], sv["Tc"]
         M, Mc = B * T, B * Tc

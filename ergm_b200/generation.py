@@ -102,6 +102,42 @@ def mega_table(eng, st):
     return torch.tensor(rows, dtype=torch.int64).to(eng.device)
 
 
+def stack_weights(eng):
+    """ergm_decode_stack's weight blobs (one contiguous fragment-packed blob per layer / phase / CTA), cached per
+    parameter version next to the slab-packed weights (whose folded biases they share)."""
+    pk = packed_weights(eng)
+    ver = eng.store.weights_epoch
+    hit = eng.__dict__.get("_dec_stack")
+    if hit is not None and hit[0] == ver and hit[1] is eng.store.flat:
+        return hit[2]
+    out = []
+    for l in range(eng.L):
+        pfx = "transformer.h.%d." % l
+        p1, fc, pj = ops.decode_stack_pack(eng.p(pfx + "attn.c_attn.weight"), eng.p(pfx + "ln_1.weight"),
+                                           eng.p(pfx + "attn.c_proj.weight"), eng.p(pfx + "mlp.c_fc.weight"),
+                                           eng.p(pfx + "ln_2.weight"), eng.p(pfx + "mlp.c_proj.weight"),
+                                           H=eng.H, I=eng.I, nh=eng.nh)
+        out.append((p1, fc, pj, pk[pfx + "attn.c_attn"][1], pk[pfx + "attn.c_proj"][1], pk[pfx + "mlp.c_fc"][1],
+                    pk[pfx + "mlp.c_proj"][1]))
+    eng.__dict__["_dec_stack"] = (ver, eng.store.flat, out)
+    return out
+
+
+def stack_supported(eng, B, Tc):
+    """One persistent cluster kernel for all blocks of a decode step (csrc/decode_step.cu): no captions, B <= 64,
+    GPT-2-small-class widths.  ERGM_DEC_STACK=0 selects the per-kernel chain."""
+    return (os.environ.get("ERGM_DEC_STACK", "0") != "0" and Tc == 0 and B <= DEC_TILE
+            and ops.decode_stack_supported(eng.H, eng.I, eng.nh))
+
+
+def stack_table(eng, st):
+    rows = []
+    for l, (p1, fc, pj, b_qkv, b_o, b_fc, b_p2) in enumerate(st.stack_w):
+        rows.append([p1.data_ptr(), fc.data_ptr(), pj.data_ptr(), b_qkv.data_ptr(), b_o.data_ptr(), b_fc.data_ptr(),
+                     b_p2.data_ptr(), st.pool[l].data_ptr()])
+    return torch.tensor(rows, dtype=torch.int64).to(eng.device)
+
+
 def mega_supported(eng, B):
     # opt-in: measured 576-660 us / step against 533 us for the launch chain (profiles/r1_decode.md) - the
     # in-kernel attention phase (4 groups per CTA, two rounds) and the 60 grid barriers still cost more than
@@ -121,6 +157,23 @@ def decode_step(eng, st, sample_kw):
     f32, bf16 = torch.float32, torch.bfloat16
     eps = eng.cfg.layer_norm_epsilon
     pk = st.packed
+    if getattr(st, "stack", None) is not None:
+        # all blocks in ONE persistent cluster kernel: 2 grid-wide synchronisations per block instead of 5 dependent
+        # launches (csrc/decode_step.cu); falls back to the chain below when the device refuses the geometry
+        ops.embed_fuse_fwd(st.next_ids, st.tt, None, eng.p("transformer.wte.weight"), eng.p("transformer.wpe.weight"),
+                           None, None, st.xring[0], past_lens=st.seq_lens)
+        try:
+            ops.decode_stack(st.stack, L=eng.L, H=H, I=I, nh=nh, B=B, xring=st.xring, block_table=st.block_table,
+                             seq_lens=st.seq_lens, eps=eps, sync_ctr=st.sync_ctr)
+        except L.ErgmError as e:
+            if "unsupported" not in str(e):
+                raise
+            st.stack = None   # this device cannot hold all clusters at once: per-kernel chain (nothing was launched)
+            return decode_step(eng, st, sample_kw)
+        _head_on_rows(eng, st.xring[(2 * eng.L) % 3], None, st.logits)
+        ops.sample(st.logits, V=eng.V, step=st.step, out_ids=st.out_ids, next_ids=st.next_ids, finished=st.finished,
+                   seq_lens=st.seq_lens, advance_step=True, **sample_kw)
+        return
     x = ws.get("dec_x", (B, H), f32)
     ops.embed_fuse_fwd(st.next_ids, st.tt, None, eng.p("transformer.wte.weight"), eng.p("transformer.wpe.weight"),
                        None, None, x, past_lens=st.seq_lens)
@@ -200,7 +253,13 @@ def generate(model, input_ids, token_type_ids=None, max_new_tokens=64, do_sample
         st = GenState(eng, B, max_ctx, Tc, max_new_tokens)
         st.packed = packed_weights(eng)
         st.mega = None
-        if mega_supported(eng, B):
+        st.stack = None
+        if stack_supported(eng, B, Tc):
+            st.stack_w = stack_weights(eng)
+            st.xring = [torch.zeros(B, eng.H, dtype=torch.float32, device=dev) for _ in range(3)]
+            st.sync_ctr = torch.zeros(1, dtype=torch.int32, device=dev)
+            st.stack = stack_table(eng, st)
+        elif mega_supported(eng, B):
             st.sync_ctr = torch.zeros(1, dtype=torch.int32, device=dev)
             st.mega = mega_table(eng, st)
         if sp2_id is not None:

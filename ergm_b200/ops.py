@@ -66,13 +66,14 @@ def gemm(a, b, d, *, M, N, K, a_major=L.ERGM_MAJOR_K, b_major=L.ERGM_MAJOR_MN, l
         e0.record()
         L.check(L.lib().ergm_gemm_bf16(ctypes.byref(args), _stream()), "ergm_gemm_bf16")
         e1.record()
-        PROFILE.append(("ergm_gemm_bf16", (M, N, K, a_major, b_major, split_k), e0, e1))
+        # dyn: 0 static extents, 1 / 2 = M / K bounded at run time by a device count (algorithmic FLOPs need the count)
+        PROFILE.append(("ergm_gemm_bf16", (M, N, K, a_major, b_major, split_k, args.dyn_dim if args.dyn_count else 0), e0, e1))
         return
     L.check(L.lib().ergm_gemm_bf16(ctypes.byref(args), _stream()), "ergm_gemm_bf16")
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim)
-_LAUNCHES = {"ergm_attn_bwd": 2, "ergm_decode_layers": 1}
+_LAUNCHES = {"ergm_attn_bwd": 2, "ergm_decode_layers": 1, "ergm_decode_stack_pack": 4}
 _launch_count = 0
 PROFILE = None  # set to a list to collect (name, info, start_event, end_event) per call
 
@@ -338,6 +339,31 @@ def decode_layers(table, *, L, H, I, nh, B, x, qkv, ctx, q2, g, block_table, seq
     """All transformer blocks of one decode step in one persistent kernel (see header)."""
     _call("ergm_decode_layers", table.data_ptr(), L, H, I, nh, B, x.data_ptr(), qkv.data_ptr(), ctx.data_ptr(),
           _p(q2), g.data_ptr(), block_table.data_ptr(), seq_lens.data_ptr(), block_table.shape[1], Tc, float(eps),
+          sync_ctr.data_ptr())
+
+
+def decode_stack_pack(w_qkv, gamma1, w_o, w_fc, gamma2, w_p2, *, H, I, nh):
+    """Per-(cluster, CTA) weight blobs of one block for ergm_decode_stack -> (p1, fc, pj) bf16 tensors."""
+    import ctypes as C
+    sizes = [C.c_int64(0) for _ in range(3)]
+    L.check(L.lib().ergm_decode_stack_blob_bytes(H, I, nh, *[C.byref(s) for s in sizes]), "ergm_decode_stack_blob_bytes")
+    blobs = [torch.empty(s.value // 2, dtype=torch.bfloat16, device=w_qkv.device) for s in sizes]
+    _call("ergm_decode_stack_pack", w_qkv.data_ptr(), gamma1.data_ptr(), w_o.data_ptr(), w_fc.data_ptr(), gamma2.data_ptr(),
+          w_p2.data_ptr(), H, I, nh, *[b.data_ptr() for b in blobs])
+    return blobs
+
+
+def decode_stack_supported(H, I, nh):
+    import ctypes as C
+    s = [C.c_int64(0) for _ in range(3)]
+    return L.lib().ergm_decode_stack_blob_bytes(H, I, nh, *[C.byref(x) for x in s]) == 0
+
+
+def decode_stack(table, *, L, H, I, nh, B, xring, block_table, seq_lens, eps, sync_ctr):
+    """All transformer blocks of one decode step in one persistent cluster kernel (see header); the result is in
+    xring[(2 * L) % 3]."""
+    _call("ergm_decode_stack", table.data_ptr(), L, H, I, nh, B, xring[0].data_ptr(), xring[1].data_ptr(),
+          xring[2].data_ptr(), block_table.data_ptr(), seq_lens.data_ptr(), block_table.shape[1], float(eps),
           sync_ctr.data_ptr())
 
 

@@ -135,10 +135,20 @@ class GraphedTrainStep:
         self.eng.store.mark_shadow_fresh()
 
     def close(self):
-        """Drops the captured graphs (needed before tearing down the process group)."""
+        """Drops the captured graphs (needed before tearing down the process group) and unregisters this trainer's
+        dropout step counter from the library."""
         torch.cuda.synchronize()
         self.graphs.clear()
         torch.cuda.synchronize()
+        if self.eng.rng_step is self.rng_step:
+            self.eng.set_rng_step_tensor(None)
+
+    def __del__(self):
+        try:
+            if self.eng.rng_step is self.rng_step:
+                self.eng.set_rng_step_tensor(None)
+        except Exception:
+            pass
 
     def __call__(self, batch):
         key, st = self.copy_in(batch)

@@ -254,6 +254,26 @@ int ergm_decode_layers(const void* layer_table, int L, int H, int I, int nh, int
 /* consumes a LayerNorm output (model.py:298,318,332,578) the affine parameters are   */
 /* folded in here: packed = bf16(diag(gamma) W), bias_out = bias_in + beta @ W        */
 /* (gamma / beta / bias_in nullable; bias_out [N] required when beta or bias_in).     */
+/* ------------------------------------------------------------------------ */
+/* ergm_decode_stack: ALL transformer blocks of one decode step (L x model.py:286-341 on one new token per
+ * sequence, B <= 64, no captions) in one persistent kernel of head-clusters (8 CTAs per head): two grid-wide
+ * synchronisations per block, everything else through distributed shared memory (csrc/decode_step.cu).
+ * Weights: per layer three blob arrays made by ergm_decode_stack_pack (sizes from ergm_decode_stack_blob_bytes);
+ * ln_1 / ln_2 gamma are folded into the q|k|v / fc blobs, their beta into the biases the caller passes (the
+ * folded biases ergm_dec_pack_weight returns).
+ * layer_table: device array of L records of 8 pointers {p1 blobs, fc blobs, proj blobs, b_qkv[3H], b_o[H],
+ * b_fc[I], b_p2[H], K/V page pool}.  x0 holds the embeddings; x1 / x2 are scratch of the same size; the block
+ * stack's output is in x{(2L) % 3}.  Appends the new token's K / V at slot seq_lens[b] like
+ * ergm_attn_decode_paged.  sync_ctr: one device uint32 of scratch.
+ * ERGM_ERR_UNSUPPORTED (-2): geometry outside H in {128,256,512,768}, I = 4H, head_dim 64, B <= 64, or the device
+ * cannot hold all clusters at once: callers fall back to the per-kernel chain.                          */
+int ergm_decode_stack_blob_bytes(int H, int I, int nh, int64_t* p1_bytes, int64_t* fc_bytes, int64_t* pj_bytes);
+int ergm_decode_stack_pack(const float* w_qkv, const float* gamma1, const float* w_o, const float* w_fc,
+                           const float* gamma2, const float* w_p2, int H, int I, int nh, void* p1_blobs,
+                           void* fc_blobs, void* pj_blobs, void* stream);
+int ergm_decode_stack(const void* layer_table, int L, int H, int I, int nh, int B, float* x0, float* x1, float* x2,
+                      const int* block_table, const int* seq_lens, int max_pages, float eps, uint32_t* sync_ctr,
+                      void* stream);
 int ergm_dec_pack_weight(const float* w_f32, int64_t ld, int K, int N, int w_is_nk, const float* gamma,
                          const float* beta, const float* bias_in, void* packed, float* bias_out,
                          void* stream);
