@@ -150,7 +150,8 @@ def test_sparse_head_edge_label_patterns(cuda_device):
             lab = b["input_ids"].clone()
         out = m(input_ids=b["input_ids"].cuda(), token_type_ids=b["token_type_ids"].cuda(), labels=lab.cuda())
         o = O.forward(sd, cfg, b["input_ids"], b["token_type_ids"], lab)
-        assert abs(out.loss.item() - o["lm_loss"].item()) < 2e-3, pattern
+        # one scored token: the loss IS one bf16-operand logit row (no averaging): 5e-3; all positions: 2e-3
+        assert abs(out.loss.item() - o["lm_loss"].item()) < (5e-3 if pattern == "one" else 2e-3), pattern
         out.loss.backward()
         m.zero_grad()
     stale = m(input_ids=b["input_ids"].cuda(), token_type_ids=b["token_type_ids"].cuda(), labels=lab.cuda())
