@@ -30,7 +30,7 @@ constexpr int DS_THREADS = 512;
 constexpr int DS_CS = 8;      // CTAs per cluster
 constexpr int DS_M = 64;      // sequences (rows) per step
 constexpr int DS_PAGE = 16;   // tokens per KV page (decode.cu)
-constexpr int DS_UNR = 4;     // tokens in flight per 8-lane group
+constexpr int DS_UNR = 8;     // tokens in flight per 8-lane group
 constexpr int DS_ACC_LD = 36; // fp32 words per row of the k-split accumulation tile
 
 struct DsLayer {   // device resident, one per block
@@ -53,8 +53,9 @@ struct DsParams {
   int max_pages;
   float eps, scale;
   unsigned int* sync_ctr;            // zeroed by the host before every launch
+  long long* trace;                  // nullable profiling aid: %globaltimer stamps of CTA 0 (16 per block, see DS_STAMP)
   int a_stride;                      // bytes per row of the normalised A operand
-  int off_a, off_w0, off_w1, off_qkv, off_ctx, off_acc, off_merge, off_tab;
+  int off_a, off_w0, off_w1, off_qkv, off_ctx, off_acc, off_merge, off_tab, off_bias;
   int p1_bytes, qkv_part_bytes, fc_bytes, pj_bytes;
 };
 
@@ -201,14 +202,31 @@ ERGM_DEVINL void ds_mma_ksplit(uint32_t a_sm, int a_stride, uint32_t w, int KB, 
 // x_next[64, cols of this CTA] += A[64 x (16 * KB)] @ W (+ bias + x_cur for the designated cluster): the residual
 // projections.  W fragment-packed [n8][kb][lane][4]; this CTA owns columns [col0, col0 + 8 * NTILES).
 ERGM_DEVINL void ds_mma_residual(const DsParams& p, uint32_t a_sm, int a_stride, uint32_t w, int KB, int ntiles, int col0,
-                                 const float* bias, const float* x_cur, float* x_next, bool lead) {
+                                 const float* bias_sm, const float* x_cur, float* x_next, bool lead) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = warp & 3, ng = warp >> 2;
   float acc[3][4];
+  // The designated cluster adds the bias and carries the residual stream over: its accumulators START from
+  // x_cur + bias (loads issued before the k loop, so their L2 latency hides behind the MMAs)
 #pragma unroll
-  for (int n = 0; n < 3; ++n)
+  for (int n = 0; n < 3; ++n) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
+    const int n8 = ng + 4 * n;
+    if (lead && n8 < ntiles) {
+      const int cl = n8 * 8 + (lane & 3) * 2;
+      const float b0 = bias_sm[cl], b1 = bias_sm[cl + 1];
+#pragma unroll
+      for (int hrow = 0; hrow < 2; ++hrow) {
+        const int rr = mt * 16 + (lane >> 2) + 8 * hrow;
+        if (rr < p.B) {
+          const float2 xc = __ldcg(reinterpret_cast<const float2*>(x_cur + (int64_t)rr * p.H + col0 + cl));
+          acc[n][2 * hrow] = xc.x + b0;
+          acc[n][2 * hrow + 1] = xc.y + b1;
+        }
+      }
+    }
+  }
   const uint32_t a_base = a_sm + (uint32_t)(mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * a_stride + (uint32_t)(lane >> 4) * 16;
 #pragma unroll 4
   for (int k = 0; k < KB; ++k) {
@@ -233,16 +251,20 @@ ERGM_DEVINL void ds_mma_residual(const DsParams& p, uint32_t a_sm, int a_stride,
     for (int hrow = 0; hrow < 2; ++hrow) {
       const int r = row + 8 * hrow;
       if (r >= p.B) continue;
-      float v0 = acc[n][2 * hrow], v1 = acc[n][2 * hrow + 1];
-      if (lead) {  // exactly one cluster adds the bias and carries the residual stream over
-        const float2 xc = __ldcg(reinterpret_cast<const float2*>(x_cur + (int64_t)r * p.H + col));
-        v0 += xc.x + __ldg(bias + col);
-        v1 += xc.y + __ldg(bias + col + 1);
-      }
-      ds_red_global_v2(x_next + (int64_t)r * p.H + col, v0, v1);
+      ds_red_global_v2(x_next + (int64_t)r * p.H + col, acc[n][2 * hrow], acc[n][2 * hrow + 1]);
     }
   }
 }
+
+// profiling aid (ergm_decode_stack's `trace` argument): thread 0 of CTA 0 records where the block's time goes
+#define DS_STAMP(slot)                                                                   \
+  do {                                                                                   \
+    if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) {                                \
+      long long t_;                                                                      \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                             \
+      p.trace[l * 16 + (slot)] = t_;                                                     \
+    }                                                                                    \
+  } while (0)
 
 template <int NV>
 __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DsParams p) {
@@ -260,6 +282,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DsPar
   const uint32_t a_sm = sm0 + (uint32_t)p.off_a, acc_sm = sm0 + (uint32_t)p.off_acc;
   const uint32_t qkv_sm = sm0 + (uint32_t)p.off_qkv, ctx_sm = sm0 + (uint32_t)p.off_ctx;
   float* merge_sm = reinterpret_cast<float*>(smem + p.off_merge);
+  float* bias_sm = reinterpret_cast<float*>(smem + p.off_bias);   // [0, 32): q|k|v or fc bias of my columns; [32, 32 + HC): residual bias
   int* tab_sm = reinterpret_cast<int*>(smem + p.off_tab);   // [8][max_pages] block-table rows, then [8] lengths
   uint32_t wpar = 0;                                         // parities of the two weight-region barriers
   unsigned int epoch = 0;
@@ -301,24 +324,30 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DsPar
       const float* x_cur = ring[ph % 3];
       float* x_next = ring[(ph + 1) % 3];
       float* x_zero = ring[(ph + 2) % 3];
+      DS_STAMP(0);
       if (l > 0) ds_grid_sync(p.sync_ctr, epoch);   // x_cur complete (block l-1's MLP reductions have landed)
+      DS_STAMP(1);
       for (int i = (int)blockIdx.x * DS_THREADS + tid; i < p.B * H / 4; i += (int)gridDim.x * DS_THREADS)
         reinterpret_cast<float4*>(x_zero)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      // this phase's biases -> smem now, so that no epilogue waits for an L2 round trip
+      if (tid < 24) bias_sm[tid] = __ldg(ly.b_qkv + (tid >> 3) * H + c * 64 + r * 8 + (tid & 7));
+      else if (tid >= 32 && tid < 32 + HC) bias_sm[tid] = __ldg(ly.b_o + HC * r + tid - 32);
       ds_layernorm<NV>(p, smem, x_cur);
+      DS_STAMP(2);
       wait_w(r1);
       __syncthreads();
       ds_mma_ksplit<3>(a_sm, p.a_stride, wreg[r1], KB, acc_sm);   // q | k | v columns 8r .. 8r+7 of head c
       __syncthreads();
+      DS_STAMP(3);
       // bias, bf16, and hand every sequence's 24 values to the CTA that owns the sequence (rank = row / 8)
       for (int i = tid; i < DS_M * 12; i += DS_THREADS) {
         const int row = i / 12, rem = i - row * 12, which = rem >> 2, pr = rem & 3;
         const float2 a = *reinterpret_cast<const float2*>(smem + p.off_acc + (size_t)(row * DS_ACC_LD + which * 8 + 2 * pr) * 4);
-        const int gcol = which * H + c * 64 + r * 8 + 2 * pr;
-        const uint32_t v = pack_bf16x2(a.x + __ldg(ly.b_qkv + gcol), a.y + __ldg(ly.b_qkv + gcol + 1));
+        const uint32_t v = pack_bf16x2(a.x + bias_sm[which * 8 + 2 * pr], a.y + bias_sm[which * 8 + 2 * pr + 1]);
         const uint32_t dst = qkv_sm + (uint32_t)(((row & 7) * 192 + which * 64 + r * 8 + 2 * pr) * 2);
         ds_st_cluster_b32(mapa_cluster(dst, (uint32_t)(row >> 3)), v);
       }
-      cluster_sync();   // q / k / v of my 8 sequences are complete in my shared memory
+      cluster_arrive();   // my share of q / k / v has been handed out ...
       // ---- paged one-query attention: 2 warps per sequence, 8 eight-lane groups with private softmax states ----
       {
         const int ls = warp >> 1, half = warp & 1;
@@ -327,15 +356,12 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DsPar
         const int n_old = b < p.B ? tab_sm[DS_CS * p.max_pages + ls] : 0;
         const int* bt = tab_sm + ls * p.max_pages;
         const unsigned char* qrow = smem + p.off_qkv + (size_t)ls * 384;
-        const uint4 qv = *reinterpret_cast<const uint4*>(qrow + gl * 16);
         auto kv_row = [&](int tok, int which) -> const uint4* {
           const int page = bt[tok / DS_PAGE];
           return reinterpret_cast<const uint4*>(ly.pool + ((((int64_t)page * 2 + which) * nh + c) * DS_PAGE + tok % DS_PAGE) * 64) + gl;
         };
-        float m_run = -INFINITY, l_run = 0.f;
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int tb = 0; tb < n_old; tb += 8 * DS_UNR) {
-          uint4 kk[DS_UNR], vv[DS_UNR];
+        uint4 kk[DS_UNR], vv[DS_UNR];
+        auto load_pass = [&](int tb) {
 #pragma unroll
           for (int u = 0; u < DS_UNR; ++u) {
             const int tok = tb + u * 8 + g8;
@@ -343,6 +369,15 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DsPar
             kk[u] = ok ? __ldcg(kv_row(tok, 0)) : make_uint4(0u, 0u, 0u, 0u);
             vv[u] = ok ? __ldcg(kv_row(tok, 1)) : make_uint4(0u, 0u, 0u, 0u);
           }
+        };
+        load_pass(0);     // the cached K / V do not depend on this step's q: in flight across the cluster barrier
+        cluster_wait();   // ... and everybody else's share for my 8 sequences has arrived
+        DS_STAMP(4);
+        const uint4 qv = *reinterpret_cast<const uint4*>(qrow + gl * 16);
+        float m_run = -INFINITY, l_run = 0.f;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int tb = 0; tb < n_old; tb += 8 * DS_UNR) {
+          if (tb > 0) load_pass(tb);
           float sc[DS_UNR];
           float m_new = m_run;
 #pragma unroll
@@ -369,6 +404,18 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DsPar
               acc[4] += w * v2.x; acc[5] += w * v2.y; acc[6] += w * v3.x; acc[7] += w * v3.y;
             }
             m_run = m_new;
+          }
+        }
+        DS_STAMP(5);
+        if (l + 1 < p.L && b < p.B) {
+          // next block's K / V pages of this (sequence, head): pull them into L2 now (2 KB per page and K / V),
+          // so that the next block's attention reads hit L2 instead of paying the DRAM latency in the chain
+          const __nv_bfloat16* npool = p.layers[l + 1].pool;
+          const int npg = (n_old + DS_PAGE - 1) / DS_PAGE;
+          for (int i = half * 32 + lane; i < 2 * npg; i += 64) {
+            const int page = bt[i >> 1], which = i & 1;
+            const __nv_bfloat16* src = npool + (((int64_t)page * 2 + which) * nh + c) * DS_PAGE * 64;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(DS_PAGE * 64 * 2) : "memory");
           }
         }
         if (half == 0) {
@@ -442,9 +489,11 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DsPar
         }
       }
       cluster_sync();   // ctx tile [64 x 64] of head c complete everywhere
+      DS_STAMP(6);
       // ---- out-proj partial of head c: x_next[:, HC*r .. ] += ctx_c @ W_o[64c:64c+64, HC*r ..] ----
-      ds_mma_residual(p, ctx_sm, 144, wreg[r1] + (uint32_t)p.qkv_part_bytes, 4, HC / 8, HC * r, ly.b_o, x_cur, x_next, c == 0);
+      ds_mma_residual(p, ctx_sm, 144, wreg[r1] + (uint32_t)p.qkv_part_bytes, 4, HC / 8, HC * r, bias_sm + 32, x_cur, x_next, c == 0);
       __syncthreads();  // region r1 is free: the MLP-proj weights of this block move in
+      DS_STAMP(7);
       load_w(r1, ly.wp2 + (size_t)blob * (p.pj_bytes / 2), p.pj_bytes);
     }
     // =========================== phase 2: MLP ===========================
@@ -454,30 +503,39 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DsPar
       float* x_next = ring[(ph + 1) % 3];
       float* x_zero = ring[(ph + 2) % 3];
       ds_grid_sync(p.sync_ctr, epoch);              // x_cur complete (all heads' out-proj reductions have landed)
+      DS_STAMP(8);
       for (int i = (int)blockIdx.x * DS_THREADS + tid; i < p.B * H / 4; i += (int)gridDim.x * DS_THREADS)
         reinterpret_cast<float4*>(x_zero)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (tid < 32) bias_sm[tid] = __ldg(ly.b_fc + c * IC + r * 32 + tid);
+      else if (tid < 32 + HC) bias_sm[tid] = __ldg(ly.b_p2 + HC * r + tid - 32);
       ds_layernorm<NV>(p, smem, x_cur);
+      DS_STAMP(9);
       wait_w(r2);
       __syncthreads();
       ds_mma_ksplit<4>(a_sm, p.a_stride, wreg[r2], KB, acc_sm);   // fc columns IC*c + 32r .. +32
       __syncthreads();  // region r2 is free: the phase-1 weights of the next block move in
+      DS_STAMP(10);
       if (l + 1 < p.L) load_w(r2, p.layers[l + 1].w1 + (size_t)blob * (p.p1_bytes / 2), p.p1_bytes);
-      cluster_sync();   // every CTA of the cluster is done reading its A operand: the g tile may overwrite it
+      cluster_arrive();   // I am done reading my A operand ...
       {
         // bias + gelu_new, bf16, broadcast my 32 columns of g to all 8 CTAs (g tile [64 x IC] aliases the A region)
         const int row = tid >> 3, c4 = (tid & 7) * 4;
         const float4 a = *reinterpret_cast<const float4*>(smem + p.off_acc + (size_t)(row * DS_ACC_LD + c4) * 4);
-        const float4 bb = __ldg(reinterpret_cast<const float4*>(ly.b_fc + c * IC + r * 32 + c4));
+        const float4 bb = *reinterpret_cast<const float4*>(bias_sm + c4);
         const uint32_t lo = pack_bf16x2(gelu_new<false>(a.x + bb.x), gelu_new<false>(a.y + bb.y));
         const uint32_t hi = pack_bf16x2(gelu_new<false>(a.z + bb.z), gelu_new<false>(a.w + bb.w));
         const uint32_t dst = a_sm + (uint32_t)(row * (2 * IC + 16) + (r * 32 + c4) * 2);
+        cluster_wait();   // ... and so is every other CTA of the cluster: the g tile may overwrite the A operands
 #pragma unroll
         for (int peer = 0; peer < DS_CS; ++peer) ds_st_cluster_v2(mapa_cluster(dst, (uint32_t)peer), lo, hi);
       }
-      cluster_sync();   // g tile complete everywhere
-      wait_w(r1);
-      ds_mma_residual(p, a_sm, 2 * IC + 16, wreg[r1], IC / 16, HC / 8, HC * r, ly.b_p2, x_cur, x_next, c == 0);
+      cluster_arrive();
+      wait_w(r1);         // MLP-proj weights (in flight since the end of phase 1)
+      cluster_wait();     // g tile complete everywhere
+      DS_STAMP(11);
+      ds_mma_residual(p, a_sm, 2 * IC + 16, wreg[r1], IC / 16, HC / 8, HC * r, bias_sm + 32, x_cur, x_next, c == 0);
       __syncthreads();  // region r1 is free: the fc weights of the next block move in
+      DS_STAMP(12);
       if (l + 1 < p.L) load_w(r1, p.layers[l + 1].wfc + (size_t)blob * (p.fc_bytes / 2), p.fc_bytes);
     }
   }
@@ -577,7 +635,7 @@ extern "C" int ergm_decode_stack_pack(const float* w_qkv, const float* gamma1, c
 
 extern "C" int ergm_decode_stack(const void* layer_table, int L, int H, int I, int nh, int B, float* x0, float* x1,
                                  float* x2, const int* block_table, const int* seq_lens, int max_pages, float eps,
-                                 unsigned int* sync_ctr, void* stream) {
+                                 unsigned int* sync_ctr, int64_t* trace, void* stream) {
   if (!layer_table || !x0 || !x1 || !x2 || !block_table || !seq_lens || !sync_ctr || L <= 0 || max_pages <= 0)
     return ERGM_ERR_ARG;
   if (!ds_supported(H, I, nh, B)) return ERGM_ERR_UNSUPPORTED;
@@ -589,6 +647,7 @@ extern "C" int ergm_decode_stack(const void* layer_table, int L, int H, int I, i
   p.block_table = block_table; p.seq_lens = seq_lens; p.max_pages = max_pages;
   p.eps = eps; p.scale = 0.125f;
   p.sync_ctr = sync_ctr;
+  p.trace = reinterpret_cast<long long*>(trace);
   p.qkv_part_bytes = g.qkv_part_bytes; p.p1_bytes = g.p1_bytes; p.fc_bytes = g.fc_bytes; p.pj_bytes = g.pj_bytes;
   p.a_stride = 2 * H + 16;
   int a_bytes = DS_M * p.a_stride;
@@ -605,7 +664,8 @@ extern "C" int ergm_decode_stack(const void* layer_table, int L, int H, int I, i
   p.off_acc = al(p.off_ctx + DS_M * 144);
   p.off_merge = al(p.off_acc + DS_M * DS_ACC_LD * 4);
   p.off_tab = al(p.off_merge + DS_CS * 2 * 68 * 4);
-  const int smem = al(p.off_tab + (DS_CS * max_pages + DS_CS) * 4);
+  p.off_bias = al(p.off_tab + (DS_CS * max_pages + DS_CS) * 4);
+  const int smem = al(p.off_bias + (32 + H / DS_CS) * 4);
   if (smem > 232448) return ERGM_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   ERGM_CUDA_TRY(cudaMemsetAsync(sync_ctr, 0, sizeof(unsigned int), st));

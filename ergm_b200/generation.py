@@ -164,7 +164,7 @@ def decode_step(eng, st, sample_kw):
                            None, None, st.xring[0], past_lens=st.seq_lens)
         try:
             ops.decode_stack(st.stack, L=eng.L, H=H, I=I, nh=nh, B=B, xring=st.xring, block_table=st.block_table,
-                             seq_lens=st.seq_lens, eps=eps, sync_ctr=st.sync_ctr)
+                             seq_lens=st.seq_lens, eps=eps, sync_ctr=st.sync_ctr, trace=getattr(st, "trace", None))
         except L.ErgmError as e:
             if "unsupported" not in str(e):
                 raise
@@ -259,6 +259,9 @@ def generate(model, input_ids, token_type_ids=None, max_new_tokens=64, do_sample
             st.xring = [torch.zeros(B, eng.H, dtype=torch.float32, device=dev) for _ in range(3)]
             st.sync_ctr = torch.zeros(1, dtype=torch.int32, device=dev)
             st.stack = stack_table(eng, st)
+            # profiling aid: ERGM_DS_TRACE=1 records per-phase device timestamps of CTA 0 (scripts/decode_stack_check.py)
+            st.trace = (torch.zeros(16 * eng.L, dtype=torch.int64, device=dev)
+                        if os.environ.get("ERGM_DS_TRACE") == "1" else None)
         elif mega_supported(eng, B):
             st.sync_ctr = torch.zeros(1, dtype=torch.int32, device=dev)
             st.mega = mega_table(eng, st)

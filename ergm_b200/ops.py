@@ -359,12 +359,12 @@ def decode_stack_supported(H, I, nh):
     return L.lib().ergm_decode_stack_blob_bytes(H, I, nh, *[C.byref(x) for x in s]) == 0
 
 
-def decode_stack(table, *, L, H, I, nh, B, xring, block_table, seq_lens, eps, sync_ctr):
+def decode_stack(table, *, L, H, I, nh, B, xring, block_table, seq_lens, eps, sync_ctr, trace=None):
     """All transformer blocks of one decode step in one persistent cluster kernel (see header); the result is in
     xring[(2 * L) % 3]."""
     _call("ergm_decode_stack", table.data_ptr(), L, H, I, nh, B, xring[0].data_ptr(), xring[1].data_ptr(),
           xring[2].data_ptr(), block_table.data_ptr(), seq_lens.data_ptr(), block_table.shape[1], float(eps),
-          sync_ctr.data_ptr())
+          sync_ctr.data_ptr(), _p(trace))
 
 
 def kv_to_pages(kv, pool, block_table, lens, *, B, T, nh, k_col0, v_col0):

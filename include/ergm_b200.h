@@ -264,7 +264,8 @@ int ergm_decode_layers(const void* layer_table, int L, int H, int I, int nh, int
  * layer_table: device array of L records of 8 pointers {p1 blobs, fc blobs, proj blobs, b_qkv[3H], b_o[H],
  * b_fc[I], b_p2[H], K/V page pool}.  x0 holds the embeddings; x1 / x2 are scratch of the same size; the block
  * stack's output is in x{(2L) % 3}.  Appends the new token's K / V at slot seq_lens[b] like
- * ergm_attn_decode_paged.  sync_ctr: one device uint32 of scratch.
+ * ergm_attn_decode_paged.  sync_ctr: one device uint32 of scratch.  trace: NULL, or (profiling aid) a device
+ * int64[16 * L] that receives %globaltimer stamps of CTA 0 at the phase boundaries of every block.
  * ERGM_ERR_UNSUPPORTED (-2): geometry outside H in {128,256,512,768}, I = 4H, head_dim 64, B <= 64, or the device
  * cannot hold all clusters at once: callers fall back to the per-kernel chain.                          */
 int ergm_decode_stack_blob_bytes(int H, int I, int nh, int64_t* p1_bytes, int64_t* fc_bytes, int64_t* pj_bytes);
@@ -273,7 +274,7 @@ int ergm_decode_stack_pack(const float* w_qkv, const float* gamma1, const float*
                            void* fc_blobs, void* pj_blobs, void* stream);
 int ergm_decode_stack(const void* layer_table, int L, int H, int I, int nh, int B, float* x0, float* x1, float* x2,
                       const int* block_table, const int* seq_lens, int max_pages, float eps, uint32_t* sync_ctr,
-                      void* stream);
+                      int64_t* trace, void* stream);
 int ergm_dec_pack_weight(const float* w_f32, int64_t ld, int K, int N, int w_is_nk, const float* gamma,
                          const float* beta, const float* bias_in, void* packed, float* bias_out,
                          void* stream);

@@ -37,6 +37,16 @@ for mode in ("0", "1"):
             e0.record(); st.graph.replay(); e1.record(); torch.cuda.synchronize()
             lat.append(e0.elapsed_time(e1))
         print("mode", mode, "decode step p50 %.1f us  min %.1f us" % (1e3 * statistics.median(lat), 1e3 * min(lat)), flush=True)
+        tr = getattr(st, "trace", None)
+        if tr is not None:
+            t = tr.cpu().view(-1, 16).double()
+            names = ["gridsync1", "ln1", "qkv_mma", "qkv_push+csync", "attn_loop", "attn_tail+push+csync", "oproj", "gridsync2",
+                     "ln2", "fc_mma", "g_push+2csync", "proj"]
+            d = (t[:, 1:13] - t[:, 0:12]) / 1e3
+            print("per-phase us of CTA 0, median over blocks 1..L-1:")
+            for i, n in enumerate(names):
+                print("  %-22s %6.2f" % (n, d[1:, i].median().item()))
+            print("  block total            %6.2f" % ((t[1:, 12] - t[1:, 0]) / 1e3).median().item())
 ref = outs[("0", True)]
 for k, v in outs.items():
     agree = (v == ref).float().mean().item()
