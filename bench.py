@@ -302,7 +302,8 @@ def main():
     dp = None
     if world > 1:
         from ergm_b200.parallel import DataParallel
-        dp = DataParallel(model, bucket_mb=float(os.environ.get("ERGM_BUCKET_MB", "128")))
+        dp = DataParallel(model, bucket_mb=float(os.environ.get("ERGM_BUCKET_MB", "128")),
+                          grad_dtype=os.environ.get("ERGM_DP_GRAD", "bf16"))
     step = GraphedTrainStep(model, opt, dp=dp, use_graph=not args.no_graph)
     batch = host_batch(B_PER_GPU, SEQ, seed=1234 + rank, sequences=medium, kf=4 if medium else 1)
     H, L = model.config.n_embd, model.config.n_layer
@@ -473,6 +474,9 @@ def main():
                                           " from on-device pooled + projected feature sequences" if medium else "",
                                           args.dropout, B_PER_GPU, SEQ, "IEMOCAP/MEDIC" if medium else "MELD"),
                            "per_gpu_batch": B_PER_GPU, "seq_len": SEQ, "parallelism": "dp%d" % world,
+                           "dp_gradient_allreduce": (None if dp is None else
+                                                     "%s buckets of >= %s MB, NCCL, overlapped with the backward, in the step's CUDA graph"
+                                                     % (dp.grad_dtype, os.environ.get("ERGM_BUCKET_MB", "128"))),
                            "l2": "no flush needed: the step streams >5 GB of activations/weights/grads per "
                                  "iteration, far above the 126 MB L2",
                            "cuda_graph": bool(step.use_graph)},

@@ -23,7 +23,13 @@
 
 namespace ergm {
 
-constexpr int AB_THREADS = 384;
+// 4 helper warps (TMA producer, MMA issuer, TMEM allocator, spare) + 16 element-wise warps.  The first version had 8
+// element-wise warps (64 score elements per thread and iteration, 168 registers): with one CTA per SM (512 TMEM
+// columns) that left 2 warps per scheduler to hide the TMEM-load / MUFU / shared-store latencies of the
+// P^T / dS^T stage, and ncu showed 18 % warps active, 21 % issue slots used.  16 warps halve each thread's share
+// (one 32-column slab in two 16-column pieces, ~100 registers) and double the latency hiding.
+constexpr int AB_CWARPS = 16;
+constexpr int AB_THREADS = 128 + AB_CWARPS * 32;
 constexpr int AB_TILE = 128 * 64 * 2;  // 16 KB
 // K, V, 2x(Q,dO), PT (2 tiles), dST (2 tiles), lse/delta (2 stages x 2 x 128 floats)
 constexpr int AB_SMEM = 2 * AB_TILE + 4 * AB_TILE + 2 * AB_TILE + 2 * AB_TILE + 2048 + 1024 + 256;
@@ -68,6 +74,18 @@ ERGM_DEVINL void attn_bwd_colsum(const uint32_t (&v)[32], bool row_ok, float* ds
   // transpose-reduce butterfly: 16 + 8 + 4 + 2 + 1 = 31 shuffles; lane l ends up with column l's total
   colsum_fold<16>(x, lane); colsum_fold<8>(x, lane); colsum_fold<4>(x, lane); colsum_fold<2>(x, lane); colsum_fold<1>(x, lane);
   atomicAdd(dst + lane, x[0]);
+}
+
+// 16-column variant: this warp's [32 keys x 16 columns] slab -> lanes 0..15 add column totals
+ERGM_DEVINL void attn_bwd_colsum16(const uint32_t (&v)[16], bool row_ok, float* dst, int lane) {
+  float x[32];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = row_ok ? __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[i]))) : 0.f;
+  // folds over lane bits 8, 4, 2, 1 leave column (lane & 15) summed over the 16 lanes sharing bit 16; one more
+  // exchange joins the two halves
+  colsum_fold<8>(x, lane); colsum_fold<4>(x, lane); colsum_fold<2>(x, lane); colsum_fold<1>(x, lane);
+  const float tot = x[0] + __shfl_xor_sync(0xffffffffu, x[0], 16);
+  if (lane < 16) atomicAdd(dst + lane, tot);
 }
 
 template <bool CAUSAL>
@@ -121,7 +139,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(bar_sdp, 1); mbar_init(bar_pds, 256); mbar_init(bar_dq, 1);
+    mbar_init(bar_sdp, 1); mbar_init(bar_pds, AB_CWARPS * 32); mbar_init(bar_dq, 1);
     fence_mbar_init();
   }
   if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -186,7 +204,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
   } else if (warp >= 4 && active) {
     const int qr = warp & 3;             // TMEM lane quarter
-    const int half = (warp - 4) >> 2;    // column half: q columns [64*half, 64*half+64)
+    const int cg = (warp - 4) >> 2;      // column group: q columns [32*cg, 32*cg+32) of the 128-query block
     const int r = qr * 32 + lane;        // key row inside the block == TMEM lane
     const int kj = k0 + r;
     const bool key_ok = kj < kv_len;
@@ -195,11 +213,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t thr16 = p.drop.thr16();
     const float keep_scale = p.do_drop ? 65536.f / (65536.f - (float)thr16) : 1.f;
     const uint32_t drop_shift = (kj & 1) ? 16u : 0u;  // which 16-bit lane of hash2(row, kj >> 1) is ours
-    const int ct = threadIdx.x - 128;    // 0..255 inside the compute group
+    const int ct = threadIdx.x - 128;    // 0..511 inside the compute group
     for (int it = 0; it < n_iter; ++it) {
       const int q0 = (i_min + it) * 128;
       // stage this query block's lse (pre-multiplied by log2 e) / delta in smem
-      {
+      if (ct < 256) {
         const uint32_t dst = sStat + (it & 1) * 1024 + ct * 4;
         const int qi = q0 + (ct & 127);
         float val = 0.f;
@@ -209,30 +227,30 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst), "f"(val) : "memory");
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, 512;" ::: "memory");
       // warp-uniform: does this (key rows, query block) tile need any masking?
       const bool need_mask = (k0 + qr * 32 + 31 > kv_len - 1) || (q0 + 127 > p.Tq - 1) ||
                              (CAUSAL && (k0 + qr * 32 + 31 > q0 + p.causal_off));
       mbar_wait(bar_sdp, it & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int cc = 64 * half; cc < 64 * half + 64; cc += 32) {
-        uint32_t sv[32], dv_[32];
-        tmem_ld_32x32b_x32(tS + lane_addr + cc, sv);
-        tmem_ld_32x32b_x32(tDP + lane_addr + cc, dv_);
-        float ls[32], dl[32];
+      for (int cc = 32 * cg; cc < 32 * cg + 32; cc += 16) {
+        uint32_t sv[16], dv_[16];
+        tmem_ld_32x32b_x16(tS + lane_addr + cc, sv);
+        tmem_ld_32x32b_x16(tDP + lane_addr + cc, dv_);
+        float ls[16], dl[16];
         const uint32_t stat = sStat + (it & 1) * 1024 + cc * 4;
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
+        for (int i = 0; i < 16; i += 4) {
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                        : "=f"(ls[i]), "=f"(ls[i + 1]), "=f"(ls[i + 2]), "=f"(ls[i + 3]) : "r"(stat + i * 4));
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                        : "=f"(dl[i]), "=f"(dl[i + 1]), "=f"(dl[i + 2]), "=f"(dl[i + 3]) : "r"(stat + 512 + i * 4));
         }
         tmem_ld_wait();
-        float pt[32], ds[32];
+        float pt[16], ds[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < 16; ++i) {
           float pr = ex2_fast(fminf(fmaf(__uint_as_float(sv[i]), c, -ls[i]), 0.f));
           if (need_mask) {
             const int qi = q0 + cc + i;
@@ -253,7 +271,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         const uint32_t rowoff = (cc >> 6) * AB_TILE + r * 128;
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
+        for (int i = 0; i < 16; i += 8) {
           const uint32_t piece = (uint32_t)(((cc & 63) + i) >> 3);
           const uint32_t off = rowoff + ((piece ^ (uint32_t)(r & 7)) << 4);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sPT + off),
@@ -269,18 +287,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(bar_pds);
-      // dQ_i: TMEM lanes are queries here; this warp handles rows qr*32.., columns 32*half..
+      // dQ_i: TMEM lanes are queries here; this warp handles rows qr*32.., columns 16*cg..+16
       mbar_wait(bar_dq, it & 1);
       tc_fence_after();
       {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tDQ + lane_addr + 32 * half, v);
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(tDQ + lane_addr + 16 * cg, v);
         tmem_ld_wait();
         const int qi = q0 + r;
         if (qi < p.Tq) {
-          float* dst = p.dq_accum + ((int64_t)b * p.Tq + qi) * p.ld_dq + h * 64 + 32 * half;
+          float* dst = p.dq_accum + ((int64_t)b * p.Tq + qi) * p.ld_dq + h * 64 + 16 * cg;
 #pragma unroll
-          for (int i = 0; i < 32; i += 4)
+          for (int i = 0; i < 16; i += 4)
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i),
                          "f"(__uint_as_float(v[i])), "f"(__uint_as_float(v[i + 1])),
                          "f"(__uint_as_float(v[i + 2])), "f"(__uint_as_float(v[i + 3]))
@@ -289,46 +307,46 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
       tc_fence_before();
     }
-    // dK_j, dV_j: lanes are keys; this warp writes rows qr*32.., columns 32*half..+32.
+    // dK_j, dV_j: lanes are keys; this warp writes rows qr*32.., columns 16*cg..+16.
     // tcgen05.ld is warp-collective (.sync.aligned): issue it unconditionally, guard the stores.
     {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(tDK + lane_addr + 32 * half, v);
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(tDK + lane_addr + 16 * cg, v);
       tmem_ld_wait();
       if (kj < p.Tk) {
-        __nv_bfloat16* dkp = p.dk + ((int64_t)b * p.Tk + kj) * p.ld_dk + p.dk_col0 + h * 64 + 32 * half;
+        __nv_bfloat16* dkp = p.dk + ((int64_t)b * p.Tk + kj) * p.ld_dk + p.dk_col0 + h * 64 + 16 * cg;
 #pragma unroll
-        for (int i = 0; i < 32; i += 8)
+        for (int i = 0; i < 16; i += 8)
           *reinterpret_cast<uint4*>(dkp + i) = make_uint4(
               pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])),
               pack_bf16x2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])),
               pack_bf16x2(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])),
               pack_bf16x2(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])));
       }
-      if (p.dk_colsum) attn_bwd_colsum(v, kj < p.Tk, p.dk_colsum + h * 64 + 32 * half, lane);
-      tmem_ld_32x32b_x32(tDV + lane_addr + 32 * half, v);
+      if (p.dk_colsum) attn_bwd_colsum16(v, kj < p.Tk, p.dk_colsum + h * 64 + 16 * cg, lane);
+      tmem_ld_32x32b_x16(tDV + lane_addr + 16 * cg, v);
       tmem_ld_wait();
       if (kj < p.Tk) {
-        __nv_bfloat16* dvp = p.dv + ((int64_t)b * p.Tk + kj) * p.ld_dv + p.dv_col0 + h * 64 + 32 * half;
+        __nv_bfloat16* dvp = p.dv + ((int64_t)b * p.Tk + kj) * p.ld_dv + p.dv_col0 + h * 64 + 16 * cg;
 #pragma unroll
-        for (int i = 0; i < 32; i += 8)
+        for (int i = 0; i < 16; i += 8)
           *reinterpret_cast<uint4*>(dvp + i) = make_uint4(
               pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])),
               pack_bf16x2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])),
               pack_bf16x2(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])),
               pack_bf16x2(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])));
       }
-      if (p.dv_colsum) attn_bwd_colsum(v, kj < p.Tk, p.dv_colsum + h * 64 + 32 * half, lane);
+      if (p.dv_colsum) attn_bwd_colsum16(v, kj < p.Tk, p.dv_colsum + h * 64 + 16 * cg, lane);
     }
   } else if (warp >= 4 && !active) {
     // keys that no query sees (or beyond kv_len): zero gradients
-    const int r = (warp & 3) * 32 + lane, half = (warp - 4) >> 2;
+    const int r = (warp & 3) * 32 + lane, cg = (warp - 4) >> 2;
     const int kj = k0 + r;
     if (kj < p.Tk) {
-      __nv_bfloat16* dkp = p.dk + ((int64_t)b * p.Tk + kj) * p.ld_dk + p.dk_col0 + h * 64 + 32 * half;
-      __nv_bfloat16* dvp = p.dv + ((int64_t)b * p.Tk + kj) * p.ld_dv + p.dv_col0 + h * 64 + 32 * half;
+      __nv_bfloat16* dkp = p.dk + ((int64_t)b * p.Tk + kj) * p.ld_dk + p.dk_col0 + h * 64 + 16 * cg;
+      __nv_bfloat16* dvp = p.dv + ((int64_t)b * p.Tk + kj) * p.ld_dv + p.dv_col0 + h * 64 + 16 * cg;
 #pragma unroll
-      for (int i = 0; i < 32; i += 8) {
+      for (int i = 0; i < 16; i += 8) {
         *reinterpret_cast<uint4*>(dkp + i) = make_uint4(0u, 0u, 0u, 0u);
         *reinterpret_cast<uint4*>(dvp + i) = make_uint4(0u, 0u, 0u, 0u);
       }

@@ -262,8 +262,9 @@ __global__ void scalar_mul_kernel(const float* a, const float* b, float* dst) { 
 // ------------------------------------------------------------------------------------------
 // AdamW over a flat fp32 buffer; hyper = [lr, beta1, beta2, eps, weight_decay, bc1, bc2] on device
 // ------------------------------------------------------------------------------------------
+template <bool GBF16>   // gradient buffer dtype: fp32, or bf16 (data-parallel buckets reduced in bf16)
 __global__ void __launch_bounds__(256)
-adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+adamw_flat_kernel(float* __restrict__ p, const void* __restrict__ g, float* __restrict__ m,
                   float* __restrict__ v, __nv_bfloat16* __restrict__ shadow, int64_t n4,
                   const float* __restrict__ hyper, const float* __restrict__ grad_scale) {
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4],
@@ -272,7 +273,14 @@ adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __r
   const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2), decay = 1.f - lr * wd;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
-    float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 gg;
+    if (GBF16) {
+      const uint2 u = reinterpret_cast<const uint2*>(g)[i];
+      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+      gg = make_float4(a.x, a.y, b.x, b.y);
+    } else {
+      gg = reinterpret_cast<const float4*>(g)[i];
+    }
     float4 mm = reinterpret_cast<float4*>(m)[i];
     float4 vv = reinterpret_cast<float4*>(v)[i];
     float* pa = &pp.x; float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
@@ -459,13 +467,18 @@ extern "C" int ergm_scalar_mul(const float* a, const float* b, float* dst, void*
   return (int)cudaGetLastError();
 }
 
-extern "C" int ergm_adamw_flat(float* p, const float* g, float* m, float* v, void* shadow_bf16,
+extern "C" int ergm_adamw_flat(float* p, const void* g, int g_is_bf16, float* m, float* v, void* shadow_bf16,
                                int64_t n, const float* hyper, const float* grad_scale, void* stream) {
   if (!p || !g || !m || !v || !hyper || n <= 0 || n % 4) return ERGM_ERR_ARG;
+  if (reinterpret_cast<uintptr_t>(g) & (g_is_bf16 ? 7 : 15)) return ERGM_ERR_ARG;
   const int64_t n4 = n / 4;
   int64_t blocks = (n4 + 255) / 256;
   if (blocks > num_sms() * 16) blocks = num_sms() * 16;
-  adamw_flat_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
-      p, g, m, v, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), n4, hyper, grad_scale);
+  if (g_is_bf16)
+    adamw_flat_kernel<true><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+        p, g, m, v, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), n4, hyper, grad_scale);
+  else
+    adamw_flat_kernel<false><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+        p, g, m, v, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), n4, hyper, grad_scale);
   return (int)cudaGetLastError();
 }

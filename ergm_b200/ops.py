@@ -303,8 +303,8 @@ def scalar_mul(a, b, dst):
 
 
 def adamw_flat(p, g, m, v, shadow, hyper, grad_scale=None):
-    _call("ergm_adamw_flat", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _p(shadow), p.numel(),
-          hyper.data_ptr(), _p(grad_scale))
+    _call("ergm_adamw_flat", p.data_ptr(), g.data_ptr(), int(g.dtype == torch.bfloat16), m.data_ptr(), v.data_ptr(),
+          _p(shadow), p.numel(), hyper.data_ptr(), _p(grad_scale))
 
 
 def attn_decode_paged(qkv, pool, block_table, seq_lens, out, *, B, nh, H):

@@ -92,19 +92,21 @@ class FusedAdamW:
         self._plan = plan
         self.state["hyper"].copy_(h, non_blocking=True)
 
-    def apply(self, grad_scale=None, lo=0, hi=None, last=True):
+    def apply(self, grad_scale=None, lo=0, hi=None, last=True, grads=None):
         """Device part of a step (graph-capturable): one kernel per contiguous range of participating
         parameters (ONE launch when every parameter has a gradient), restricted to the element range [lo, hi)
         (DataParallel updates the layer parameters while the embedding bucket is still being all-reduced).
-        `last`: this call completes the step."""
+        `last`: this call completes the step.  `grads`: a same-layout gradient buffer to read instead of the flat
+        fp32 one (DataParallel's bf16 buckets)."""
         eng, st = self._ensure()
         hi = st.total if hi is None else hi
         if self._plan is None:
             raise RuntimeError("FusedAdamW.apply() without load_hyper()")
+        g = st.grad if grads is None else grads
         for a, b, row in self._plan:
             a, b = max(a, lo), min(b, hi)
             if b > a:
-                ops.adamw_flat(st.flat[a:b], st.grad[a:b], self.state["m"][a:b], self.state["v"][a:b],
+                ops.adamw_flat(st.flat[a:b], g[a:b], self.state["m"][a:b], self.state["v"][a:b],
                                st.shadow[a:b], self.state["hyper"][row], grad_scale)
         if last:
             st.mark_shadow_fresh()

@@ -61,12 +61,13 @@ class GraphedTrainStep:
             # bytes, final only after the embedding backward) is still being all-reduced
             # (wte + wpe, 25 % of the bytes, and the A3 projections: final only after the embedding backward)
             self.dp.backward(self.one, False, defer_last=True)
+            gb = self.dp.grad_bf16   # bf16 buckets (grad_dtype="bf16"): the optimiser reads them directly
             for lo, hi in self.dp.early_ranges():
-                self.opt.apply(lo=lo, hi=hi, last=False)
+                self.opt.apply(lo=lo, hi=hi, last=False, grads=gb)
             self.dp.finish()
             late = self.dp.deferred_ranges()
             for i, (lo, hi) in enumerate(late):
-                self.opt.apply(lo=lo, hi=hi, last=(i == len(late) - 1))
+                self.opt.apply(lo=lo, hi=hi, last=(i == len(late) - 1), grads=gb)
         else:
             if self.dp is not None:
                 self.dp.backward(self.one, False)

@@ -323,8 +323,9 @@ int ergm_int_add(int* dev_ptr, int inc, void* stream);
 /* ------------------------------------------------------------------------ */
 /* Flat AdamW, torch.optim.AdamW arithmetic (main.py:68,155).  hyper (device) */
 /* = [lr, beta1, beta2, eps, weight_decay, 1-beta1^t, 1-beta2^t]; also writes */
-/* the bf16 weight shadow consumed by the GEMMs.                              */
-int ergm_adamw_flat(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n,
+/* the bf16 weight shadow consumed by the GEMMs.  g: fp32, or bf16 when        */
+/* g_is_bf16 (data-parallel gradient buckets all-reduced in bf16). */
+int ergm_adamw_flat(float* p, const void* g, int g_is_bf16, float* m, float* v, void* shadow_bf16, int64_t n,
                     const float* hyper, const float* grad_scale, void* stream);
 
 #ifdef __cplusplus

@@ -24,6 +24,7 @@ from oracle import ergm_oracle as O, synthetic
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(rank)
 dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+GRAD = %(grad)r   # dtype of the all-reduced gradient buckets
 PROJ = %(proj)r   # A3 extension: visual_proj / audio_proj gradients are written at the very end of the backward
 cfg = O.OracleConfig(vocab_size=1024, n_positions=256, n_embd=128, n_layer=3, n_head=2,
                      visual_dim=96 if PROJ else None, audio_dim=96 if PROJ else None)
@@ -53,7 +54,7 @@ oo = O.forward(sdo, cfg, b["input_ids"], b["token_type_ids"], b["labels"], b["em
 oo["loss"].backward()
 # data-parallel step through the public model API
 m = build()
-dp = DataParallel(m, bucket_mb=0.25)
+dp = DataParallel(m, bucket_mb=0.25, grad_dtype=GRAD)
 o = m(**mine); o.loss.backward()
 ok = abs(o.loss.item() - ref_loss) < 1e-5
 ok_oracle = abs(o.loss.item() - oo["loss"].item()) < 2.5e-3
@@ -67,7 +68,7 @@ for n, p in m.named_parameters():
 FusedAdamW(m, lr=1e-3).step()
 wdiff = max((p.detach() - q.detach()).abs().max().item() for p, q in zip(m.parameters(), ref.parameters()))
 # graph-captured DP train step (the bench path) runs and agrees with itself across ranks
-m2 = build(); dp2 = DataParallel(m2, bucket_mb=0.25)
+m2 = build(); dp2 = DataParallel(m2, bucket_mb=0.25, grad_dtype=GRAD)
 step = GraphedTrainStep(m2, FusedAdamW(m2, lr=1e-3), dp=dp2)
 pinned = {k: v.cpu().pin_memory() for k, v in mine.items()}
 losses = [step(pinned) for _ in range(3)]
@@ -78,7 +79,10 @@ w0 = m2.transformer.h[1].mlp.c_fc.weight.detach().clone(); w1 = w0.clone(); dist
 flat = m2.engine.store.flat.detach().clone(); flat0 = flat.clone(); dist.broadcast(flat0, 0)
 allsync = bool(torch.equal(flat, flat0))
 print("RANK%%d loss_ok=%%s oracle_loss_ok=%%s worst_grad_rel=%%.2e worst_grad_rel_vs_oracle=%%.2e wdiff=%%.2e graph_losses=%%s same=%%s wsync=%%s allsync=%%s" %% (rank, ok, ok_oracle, worst, worst_oracle, wdiff, ["%%.4f" %% x for x in losses], same, bool(torch.equal(w0, w1)), allsync), flush=True)
-assert ok and ok_oracle and worst < 2e-3 and worst_oracle < 6e-2 and wdiff < 1e-5 and same and torch.equal(w0, w1) and allsync and losses[2] < losses[0]
+# fp32 buckets: the N-rank step IS the single-GPU step (fp32 rounding); bf16 buckets: gradients carry one bf16 rounding
+# (2^-9 relative) and AdamW at lr 1e-3 turns a flipped noise-level gradient sign into at most ~2 lr of weight difference
+gtol, wtol = (2e-3, 1e-5) if GRAD == "fp32" else (1.5e-2, 2.5e-3)
+assert ok and ok_oracle and worst < gtol and worst_oracle < 6e-2 and wdiff < wtol and same and torch.equal(w0, w1) and allsync and losses[2] < losses[0]
 step.close()
 dist.barrier()
 dist.destroy_process_group()
@@ -93,14 +97,14 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world,proj", [(2, False), (2, True)])
-def test_dp_step_equals_single_gpu_step(world, proj, tmp_path):
+@pytest.mark.parametrize("world,proj,grad", [(2, False, "fp32"), (2, True, "fp32"), (2, False, "bf16")])
+def test_dp_step_equals_single_gpu_step(world, proj, grad, tmp_path):
     """N-rank step on the split batch == single-GPU step == the ORACLE on the concatenated batch; with proj the
     model carries the A3 projection parameters, whose gradients only exist after the embedding backward."""
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     script = tmp_path / "dp_worker.py"
-    script.write_text(WORKER % {"root": ROOT, "proj": proj})
+    script.write_text(WORKER % {"root": ROOT, "proj": proj, "grad": grad})
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
