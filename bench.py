@@ -410,6 +410,34 @@ def main():
             dist.all_reduce(t_nc, op=dist.ReduceOp.MAX)
         nocap = {"ms_per_step": float(t_nc[0]), "train_tokens_per_s": tokens / (float(t_nc[0]) / 1e3)}
     nonpad = int((batch["token_type_ids"] != 50256).sum())  # padding carries the eos id as its token type
+    # ---- secondary: packed variable-length batches: only the real positions (+ position T-1 of padded
+    #      samples, which the emotion head reads) are computed; same batch, same step, one CUDA graph ----
+    packed = None
+    if not medium:
+        try:
+            b_pk = dict(batch)
+            b_pk["seq_lens"] = (batch["token_type_ids"] != 50256).sum(1).to(torch.int32).pin_memory()
+            for _ in range(3):
+                step(b_pk)
+            k_pk, st_pk = step.copy_in(b_pk)
+            barrier()
+            e0.record()
+            for _ in range(args.steps):
+                step.run_device(k_pk, st_pk)
+            e1.record()
+            barrier()
+            t_pk = torch.tensor([e0.elapsed_time(e1) / args.steps], device=device)
+            if world > 1:
+                dist.all_reduce(t_pk, op=dist.ReduceOp.MAX)
+            rows_pk = int(model.engine.get_pack(B_PER_GPU, SEQ).n_rows.item())
+            packed = {"ms_per_step": float(t_pk[0]), "train_tokens_per_s_incl_padding": tokens / (float(t_pk[0]) / 1e3),
+                      "useful_tokens_per_s_rank0_rate": nonpad * world / (float(t_pk[0]) / 1e3),
+                      "rows_computed_rank0": rows_pk, "rows_padded_layout": B_PER_GPU * SEQ,
+                      "semantics": "reference called with the right-padded attention_mask (emotion head on position T-1)"}
+        except Exception as e:
+            packed = {"error": "%s: %s" % (type(e).__name__, e)}
+            if world > 1:
+                raise
     fl_tok, gemm_fl_tok = train_flops_per_token(H, L, VOCAB, SEQ, SEQ, caption=True)
     model_tf = value / world * fl_tok / 1e12
 
@@ -489,7 +517,7 @@ def main():
                 "model_tflops_per_gpu": model_tf, "model_flops_per_token": fl_tok,
                 "mfu_of_measured_sustained": model_tf / pk["tf_sust"], "last_loss": loss,
                 "tokens_per_step": {"all_positions_incl_padding": tokens, "non_pad_rank0": nonpad},
-                "nocaption_mode": nocap, "generation": gen}
+                "nocaption_mode": nocap, "packed_mode": packed, "generation": gen}
         print(json.dumps(line), flush=True)
     if world > 1:
         # the JSON line is out; never let a teardown hang keep the launcher waiting

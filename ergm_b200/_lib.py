@@ -34,6 +34,12 @@ class GemmArgs(ctypes.Structure):
     ]
 
 
+class PackDesc(ctypes.Structure):
+    """ergm_pack of include/ergm_b200.h: device int32 arrays describing a packed variable-length batch."""
+    _fields_ = [("cu_rows", ctypes.c_void_p), ("row_b", ctypes.c_void_p), ("row_t", ctypes.c_void_p),
+                ("n_rows", ctypes.c_void_p), ("kv_lens", ctypes.c_void_p)]
+
+
 _lib = None
 
 

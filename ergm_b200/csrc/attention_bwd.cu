@@ -43,6 +43,8 @@ struct AttnBwdParams {
   float* dk_colsum;     // nullable [nh*64]: += column sums of dK as stored (bias gradient of the K projection)
   float* dv_colsum;     // nullable [nh*64]
   const int* kv_lens;
+  const int* cu_q;      // nullable [B+1]: packed batch (queries, dO, dQ rows of sample b start at cu_q[b])
+  const int* cu_k;      // nullable [B+1]: keys / values / dK / dV packed the same way (self attention)
   int64_t ld_dq, ld_dk, ld_dv;
   int dk_col0, dv_col0;
   int Tq, Tk, nh;
@@ -114,6 +116,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   // work; blockIdx.z is the slowest-varying index of the block scheduler
   const int jb = blockIdx.z, h = blockIdx.y, b = blockIdx.x;
   const int k0 = jb * 128;
+  // packed batches: per-sample extents and row bases (TMA batch coordinate 0: one long row sequence)
+  int q_row0 = 0, q_bat = b, k_row0 = 0, k_bat = b;
+  int64_t dq_row0 = (int64_t)b * p.Tq, dk_row0 = (int64_t)b * p.Tk;
+  if (p.cu_q) { q_row0 = p.cu_q[b]; q_bat = 0; dq_row0 = q_row0; p.Tq = p.cu_q[b + 1] - q_row0; }
+  if (p.cu_k) {
+    k_row0 = p.cu_k[b]; k_bat = 0; dk_row0 = k_row0; p.Tk = p.cu_k[b + 1] - k_row0;
+    if (k0 >= p.Tk) return;   // CTA-uniform, before any barrier / TMEM allocation: no key rows of this sample here
+  }
+  const int64_t stat_row0 = ((int64_t)b * p.nh + h) * p_in.Tq;   // lse / delta / dropout rows: padded [B, nh, T] indexing
   int kv_len = p.Tk;
   if (p.kv_lens) kv_len = min(kv_len, p.kv_lens[b]);
   const int n_q = (p.Tq + 127) / 128;
@@ -131,11 +142,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     fence_mbar_init();
     if (active) {
       mbar_expect_tx(bar_kv, 2 * AB_TILE);
-      tma_load_3d(sK, &tm_k, bar_kv, p.k_col0 + h * 64, k0, b);
-      tma_load_3d(sV, &tm_v, bar_kv, p.v_col0 + h * 64, k0, b);
+      tma_load_3d(sK, &tm_k, bar_kv, p.k_col0 + h * 64, k_row0 + k0, k_bat);
+      tma_load_3d(sV, &tm_v, bar_kv, p.v_col0 + h * 64, k_row0 + k0, k_bat);
       mbar_expect_tx(qdo_full(0), 2 * AB_TILE);
-      tma_load_3d(sQ, &tm_q, qdo_full(0), p.q_col0 + h * 64, i_min * 128, b);
-      tma_load_3d(sDO, &tm_do, qdo_full(0), h * 64, i_min * 128, b);
+      tma_load_3d(sQ, &tm_q, qdo_full(0), p.q_col0 + h * 64, q_row0 + i_min * 128, q_bat);
+      tma_load_3d(sDO, &tm_do, qdo_full(0), h * 64, q_row0 + i_min * 128, q_bat);
     }
   }
   if (warp == 1 && lane == 0) {
@@ -156,8 +167,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const int st = it & 1;
         mbar_wait(qdo_empty(st), ((it >> 1) & 1) ^ 1);
         mbar_expect_tx(qdo_full(st), 2 * AB_TILE);
-        tma_load_3d(sQ + st * AB_TILE, &tm_q, qdo_full(st), p.q_col0 + h * 64, (i_min + it) * 128, b);
-        tma_load_3d(sDO + st * AB_TILE, &tm_do, qdo_full(st), h * 64, (i_min + it) * 128, b);
+        tma_load_3d(sQ + st * AB_TILE, &tm_q, qdo_full(st), p.q_col0 + h * 64, q_row0 + (i_min + it) * 128, q_bat);
+        tma_load_3d(sDO + st * AB_TILE, &tm_do, qdo_full(st), h * 64, q_row0 + (i_min + it) * 128, q_bat);
       }
     }
   } else if (warp == 1) {
@@ -222,7 +233,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const int qi = q0 + (ct & 127);
         float val = 0.f;
         if (qi < p.Tq) {
-          const int64_t idx = ((int64_t)b * p.nh + h) * p.Tq + qi;
+          const int64_t idx = stat_row0 + qi;
           val = ct < 128 ? p.lse[idx] * 1.4426950408889634f : p.delta[idx];
         }
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst), "f"(val) : "memory");
@@ -261,7 +272,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           float dp = __uint_as_float(dv_[i]);
           float pd = pr;
           if (p.do_drop) {
-            const uint32_t hsh = p.drop.hash2((uint32_t)((b * p.nh + h) * p.Tq + q0 + cc + i), (uint32_t)kj >> 1);
+            const uint32_t hsh = p.drop.hash2((uint32_t)(stat_row0 + q0 + cc + i), (uint32_t)kj >> 1);
             const bool keep = ((hsh >> drop_shift) & 0xffffu) >= thr16;
             dp = keep ? dp * keep_scale : 0.f;
             pd = keep ? pr * keep_scale : 0.f;
@@ -296,7 +307,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tmem_ld_wait();
         const int qi = q0 + r;
         if (qi < p.Tq) {
-          float* dst = p.dq_accum + ((int64_t)b * p.Tq + qi) * p.ld_dq + h * 64 + 16 * cg;
+          float* dst = p.dq_accum + (dq_row0 + qi) * p.ld_dq + h * 64 + 16 * cg;
 #pragma unroll
           for (int i = 0; i < 16; i += 4)
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i),
@@ -314,7 +325,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tmem_ld_32x32b_x16(tDK + lane_addr + 16 * cg, v);
       tmem_ld_wait();
       if (kj < p.Tk) {
-        __nv_bfloat16* dkp = p.dk + ((int64_t)b * p.Tk + kj) * p.ld_dk + p.dk_col0 + h * 64 + 16 * cg;
+        __nv_bfloat16* dkp = p.dk + (dk_row0 + kj) * p.ld_dk + p.dk_col0 + h * 64 + 16 * cg;
 #pragma unroll
         for (int i = 0; i < 16; i += 8)
           *reinterpret_cast<uint4*>(dkp + i) = make_uint4(
@@ -327,7 +338,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tmem_ld_32x32b_x16(tDV + lane_addr + 16 * cg, v);
       tmem_ld_wait();
       if (kj < p.Tk) {
-        __nv_bfloat16* dvp = p.dv + ((int64_t)b * p.Tk + kj) * p.ld_dv + p.dv_col0 + h * 64 + 16 * cg;
+        __nv_bfloat16* dvp = p.dv + (dk_row0 + kj) * p.ld_dv + p.dv_col0 + h * 64 + 16 * cg;
 #pragma unroll
         for (int i = 0; i < 16; i += 8)
           *reinterpret_cast<uint4*>(dvp + i) = make_uint4(
@@ -343,8 +354,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int r = (warp & 3) * 32 + lane, cg = (warp - 4) >> 2;
     const int kj = k0 + r;
     if (kj < p.Tk) {
-      __nv_bfloat16* dkp = p.dk + ((int64_t)b * p.Tk + kj) * p.ld_dk + p.dk_col0 + h * 64 + 16 * cg;
-      __nv_bfloat16* dvp = p.dv + ((int64_t)b * p.Tk + kj) * p.ld_dv + p.dv_col0 + h * 64 + 16 * cg;
+      __nv_bfloat16* dkp = p.dk + (dk_row0 + kj) * p.ld_dk + p.dk_col0 + h * 64 + 16 * cg;
+      __nv_bfloat16* dvp = p.dv + (dk_row0 + kj) * p.ld_dv + p.dv_col0 + h * 64 + 16 * cg;
 #pragma unroll
       for (int i = 0; i < 16; i += 8) {
         *reinterpret_cast<uint4*>(dkp + i) = make_uint4(0u, 0u, 0u, 0u);
@@ -362,11 +373,17 @@ __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ dout, int64_t ld_do,
                   const __nv_bfloat16* __restrict__ out, int64_t ld_o,
                   const float* __restrict__ out_f32, float* __restrict__ delta,
-                  int rows, int Tq, int nh) {
+                  int rows, int Tq, int nh, const int* __restrict__ cu_q, const int* __restrict__ row_b,
+                  const int* __restrict__ n_rows) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   if (row >= rows) return;
-  const int b = row / Tq, q = row - b * Tq;
+  int b = row / Tq, q = row - b * Tq;
+  if (cu_q) {   // packed batch: row is a packed row; delta keeps the padded [B, nh, T] indexing
+    if (row >= *n_rows) return;
+    b = row_b[row];
+    q = row - cu_q[b];
+  }
   // lanes 0..15 cover one head (16 lanes x 4 elements), a warp covers 2 heads per step
   for (int h0 = 0; h0 < nh; h0 += 2) {
     const int h = h0 + (lane >> 4);
@@ -400,8 +417,12 @@ extern "C" int ergm_attn_bwd(const void* q, int64_t ld_q, int q_col0, const void
                              float* delta, float* dq_accum, int64_t ld_dq, void* dk, int64_t ld_dk,
                              int dk_col0, void* dv, int64_t ld_dv, int dv_col0, float* dk_colsum, float* dv_colsum,
                              const int* kv_lens, int B, int nh, int Tq, int Tk, int head_dim, int causal, int causal_off,
-                             float dropout_p, uint64_t seed, uint64_t offset, void* stream) {
+                             float dropout_p, uint64_t seed, uint64_t offset, const ergm_pack* pack, int pack_kv,
+                             void* stream) {
   if (!q || !k || !v || !out || !dout || !lse || !delta || !dq_accum || !dk || !dv) return ERGM_ERR_ARG;
+  if (pack && (!pack->cu_rows || !pack->row_b || !pack->n_rows || (pack_kv && !pack->kv_lens))) return ERGM_ERR_ARG;
+  const uint64_t q_rows = pack ? (uint64_t)B * Tq : (uint64_t)Tq, q_bat = pack ? 1 : (uint64_t)B;
+  const uint64_t k_rows = (pack && pack_kv) ? (uint64_t)B * Tk : (uint64_t)Tk, k_bat = (pack && pack_kv) ? 1 : (uint64_t)B;
   if (B <= 0 || nh <= 0 || Tq <= 0 || Tk <= 0) return ERGM_ERR_ARG;
   if (head_dim != 64) return ERGM_ERR_UNSUPPORTED;
   if (ld_q % 8 || ld_k % 8 || ld_v % 8 || ld_out % 8 || ld_do % 8 || ld_dq % 4 || ld_dk % 8 || ld_dv % 8 ||
@@ -410,22 +431,26 @@ extern "C" int ergm_attn_bwd(const void* q, int64_t ld_q, int q_col0, const void
   cudaStream_t s = (cudaStream_t)stream;
   attn_delta_kernel<<<(B * Tq + 7) / 8, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dout), ld_do,
                                                     reinterpret_cast<const __nv_bfloat16*>(out), ld_out,
-                                                    out_f32, delta, B * Tq, Tq, nh);
+                                                    out_f32, delta, B * Tq, Tq, nh, pack ? pack->cu_rows : nullptr,
+                                                    pack ? pack->row_b : nullptr, pack ? pack->n_rows : nullptr);
   CUtensorMap tq, tk, tv, tdo;
   int rc;
-  if ((rc = encode_tmap_3d(&tq, q, 2, (uint64_t)(q_col0 + nh * 64), (uint64_t)Tq, (uint64_t)B,
-                           (uint64_t)ld_q * 2, (uint64_t)Tq * ld_q * 2, 64, 128, 1))) return rc;
-  if ((rc = encode_tmap_3d(&tk, k, 2, (uint64_t)(k_col0 + nh * 64), (uint64_t)Tk, (uint64_t)B,
-                           (uint64_t)ld_k * 2, (uint64_t)Tk * ld_k * 2, 64, 128, 1))) return rc;
-  if ((rc = encode_tmap_3d(&tv, v, 2, (uint64_t)(v_col0 + nh * 64), (uint64_t)Tk, (uint64_t)B,
-                           (uint64_t)ld_v * 2, (uint64_t)Tk * ld_v * 2, 64, 128, 1))) return rc;
-  if ((rc = encode_tmap_3d(&tdo, dout, 2, (uint64_t)(nh * 64), (uint64_t)Tq, (uint64_t)B,
-                           (uint64_t)ld_do * 2, (uint64_t)Tq * ld_do * 2, 64, 128, 1))) return rc;
+  if ((rc = encode_tmap_3d(&tq, q, 2, (uint64_t)(q_col0 + nh * 64), q_rows, q_bat,
+                           (uint64_t)ld_q * 2, q_rows * ld_q * 2, 64, 128, 1))) return rc;
+  if ((rc = encode_tmap_3d(&tk, k, 2, (uint64_t)(k_col0 + nh * 64), k_rows, k_bat,
+                           (uint64_t)ld_k * 2, k_rows * ld_k * 2, 64, 128, 1))) return rc;
+  if ((rc = encode_tmap_3d(&tv, v, 2, (uint64_t)(v_col0 + nh * 64), k_rows, k_bat,
+                           (uint64_t)ld_v * 2, k_rows * ld_v * 2, 64, 128, 1))) return rc;
+  if ((rc = encode_tmap_3d(&tdo, dout, 2, (uint64_t)(nh * 64), q_rows, q_bat,
+                           (uint64_t)ld_do * 2, q_rows * ld_do * 2, 64, 128, 1))) return rc;
   AttnBwdParams p;
   p.lse = lse; p.delta = delta; p.dq_accum = dq_accum;
   p.dk = reinterpret_cast<__nv_bfloat16*>(dk); p.dv = reinterpret_cast<__nv_bfloat16*>(dv);
   p.dk_colsum = dk_colsum; p.dv_colsum = dv_colsum;
   p.kv_lens = kv_lens;
+  p.cu_q = pack ? pack->cu_rows : nullptr;
+  p.cu_k = (pack && pack_kv) ? pack->cu_rows : nullptr;
+  if (pack && pack_kv) p.kv_lens = pack->kv_lens;
   p.ld_dq = ld_dq; p.ld_dk = ld_dk; p.ld_dv = ld_dv; p.dk_col0 = dk_col0; p.dv_col0 = dv_col0;
   p.Tq = Tq; p.Tk = Tk; p.nh = nh;
   p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;

@@ -35,6 +35,8 @@ struct AttnFwdParams {
   float* lse;          // [B, nh, Tq]
   float* out_f32;      // nullable [B*Tq, nh*64]: un-rounded context, used by backward's delta
   const int* kv_lens;  // nullable [B]: keys >= kv_lens[b] are masked
+  const int* cu_q;     // nullable [B+1]: packed batch, queries (and outputs) of sample b are rows cu_q[b] .. cu_q[b+1]
+  const int* cu_k;     // nullable [B+1]: keys / values packed the same way (self attention); NULL: rows b*Tk ..
   int64_t ld_out;
   int Tq, Tk, nh;
   int q_col0, k_col0, v_col0;
@@ -65,6 +67,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   // first (blockIdx.z is the slowest-varying index of the block scheduler) and the light ones fill the tail
   const int qb = (int)gridDim.z - 1 - (int)blockIdx.z, h = blockIdx.y, b = blockIdx.x;
   const int q0 = qb * 128;
+  // packed batches: per-sample extents and row bases (TMA batch coordinate 0: the tensor is one long row sequence)
+  int q_row0 = 0, q_bat = b, k_row0 = 0, k_bat = b;
+  int64_t out_row0 = (int64_t)b * p.Tq;
+  if (p.cu_q) {
+    q_row0 = p.cu_q[b]; q_bat = 0; out_row0 = q_row0;
+    p.Tq = p.cu_q[b + 1] - q_row0;          // p is this thread's copy: from here on Tq is the sample's own
+    if (q0 >= p.Tq) return;                 // CTA-uniform, before any barrier / TMEM allocation
+  }
+  if (p.cu_k) { k_row0 = p.cu_k[b]; k_bat = 0; p.Tk = p.cu_k[b + 1] - k_row0; }
+  const int64_t stat_row0 = ((int64_t)b * p.nh + h) * p_in.Tq;   // lse / dropout rows keep the padded [B, nh, T] indexing
   int kv_len = p.Tk;
   if (p.kv_lens) kv_len = min(kv_len, p.kv_lens[b]);
   int n_kv = max(1, (kv_len + 127) / 128);
@@ -80,10 +92,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     for (int s = 0; s < 2; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
     fence_mbar_init();
     mbar_expect_tx(bar_q, AT_TILE);
-    tma_load_3d(sQ, &tm_q, bar_q, p.q_col0 + h * AT_D, q0, b);
+    tma_load_3d(sQ, &tm_q, bar_q, p.q_col0 + h * AT_D, q_row0 + q0, q_bat);
     mbar_expect_tx(kv_full(0), 2 * AT_TILE);
-    tma_load_3d(sK, &tm_k, kv_full(0), p.k_col0 + h * AT_D, 0, b);
-    tma_load_3d(sV, &tm_v, kv_full(0), p.v_col0 + h * AT_D, 0, b);
+    tma_load_3d(sK, &tm_k, kv_full(0), p.k_col0 + h * AT_D, k_row0, k_bat);
+    tma_load_3d(sV, &tm_v, kv_full(0), p.v_col0 + h * AT_D, k_row0, k_bat);
   }
   if (warp == 1 && lane == 0) {
     mbar_init(bar_s, 1); mbar_init(bar_p, 256); mbar_init(bar_o, 1);
@@ -113,8 +125,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const int st = j & 1;
         mbar_wait(kv_empty(st), ((j >> 1) & 1) ^ 1);
         mbar_expect_tx(kv_full(st), 2 * AT_TILE);
-        tma_load_3d(sK + st * AT_TILE, &tm_k, kv_full(st), p.k_col0 + h * AT_D, j * 128, b);
-        tma_load_3d(sV + st * AT_TILE, &tm_v, kv_full(st), p.v_col0 + h * AT_D, j * 128, b);
+        tma_load_3d(sK + st * AT_TILE, &tm_k, kv_full(st), p.k_col0 + h * AT_D, k_row0 + j * 128, k_bat);
+        tma_load_3d(sV + st * AT_TILE, &tm_v, kv_full(st), p.v_col0 + h * AT_D, k_row0 + j * 128, k_bat);
       }
     }
   } else if (warp == 1) {
@@ -161,7 +173,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const float c = p.scale * 1.4426950408889634f;  // exp(x*scale) = exp2(x*c)
     const uint32_t thr16 = p.drop.thr16();
     const float keep_scale = p.do_drop ? p.drop.keep_scale() : 1.f;
-    const uint32_t drop_row = (uint32_t)((b * p.nh + h) * p.Tq + qi);
+    const uint32_t drop_row = (uint32_t)(stat_row0 + qi);
     const int vis = CAUSAL ? min(kv_len - 1, qi + p.causal_off) : kv_len - 1;  // last visible key
     const uint32_t xch_mine = sX + (hf * 128 + r) * 4;
     const uint32_t xch_other = sX + ((hf ^ 1) * 128 + r) * 4;
@@ -259,7 +271,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     l += lo;
     if (qi < p.Tq) {
       const float inv = l > 0.f ? 1.f / l : 0.f;
-      __nv_bfloat16* op = p.out + ((int64_t)b * p.Tq + qi) * p.ld_out + h * AT_D + 32 * hf;
+      __nv_bfloat16* op = p.out + (out_row0 + qi) * p.ld_out + h * AT_D + 32 * hf;
 #pragma unroll
       for (int i = 0; i < 32; i += 8) {
         const uint4 u = make_uint4(pack_bf16x2(o[i] * inv, o[i + 1] * inv), pack_bf16x2(o[i + 2] * inv, o[i + 3] * inv),
@@ -267,13 +279,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         *reinterpret_cast<uint4*>(op + i) = u;
       }
       if (p.out_f32) {
-        float* of = p.out_f32 + ((int64_t)b * p.Tq + qi) * (p.nh * AT_D) + h * AT_D + 32 * hf;
+        float* of = p.out_f32 + (out_row0 + qi) * (p.nh * AT_D) + h * AT_D + 32 * hf;
 #pragma unroll
         for (int i = 0; i < 32; i += 4)
           *reinterpret_cast<float4*>(of + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
       }
       if (p.lse && hf == 0)
-        p.lse[((int64_t)b * p.nh + h) * p.Tq + qi] = (m == -INFINITY ? 0.f : m) * p.scale + logf(l);
+        p.lse[stat_row0 + qi] = (m == -INFINITY ? 0.f : m) * p.scale + logf(l);
     }
   }
   tc_fence_before();
@@ -290,25 +302,33 @@ extern "C" int ergm_attn_fwd(const void* q, int64_t ld_q, int q_col0, const void
                              int k_col0, const void* v, int64_t ld_v, int v_col0, void* out,
                              int64_t ld_out, float* out_f32, float* lse, const int* kv_lens, int B,
                              int nh, int Tq, int Tk, int head_dim, int causal, int causal_off,
-                             float dropout_p, uint64_t seed, uint64_t offset, void* stream) {
+                             float dropout_p, uint64_t seed, uint64_t offset, const ergm_pack* pack, int pack_kv,
+                             void* stream) {
   if (!q || !k || !v || !out || B <= 0 || nh <= 0 || Tq <= 0 || Tk <= 0) return ERGM_ERR_ARG;
+  if (pack && (!pack->cu_rows || (pack_kv && !pack->kv_lens))) return ERGM_ERR_ARG;
+  // packed batch: Q (and K / V when pack_kv) are ONE row sequence of capacity B * T; sample b starts at cu_rows[b]
+  const uint64_t q_rows = pack ? (uint64_t)B * Tq : (uint64_t)Tq, q_bat = pack ? 1 : (uint64_t)B;
+  const uint64_t k_rows = (pack && pack_kv) ? (uint64_t)B * Tk : (uint64_t)Tk, k_bat = (pack && pack_kv) ? 1 : (uint64_t)B;
   if (head_dim != AT_D) return ERGM_ERR_UNSUPPORTED;
   if (ld_q % 8 || ld_k % 8 || ld_v % 8 || ld_out % 8 || q_col0 % 8 || k_col0 % 8 || v_col0 % 8)
     return ERGM_ERR_ARG;
   CUtensorMap tq, tk, tv;
   int rc;
-  if ((rc = encode_tmap_3d(&tq, q, 2, (uint64_t)(q_col0 + nh * AT_D), (uint64_t)Tq, (uint64_t)B,
-                           (uint64_t)ld_q * 2, (uint64_t)Tq * ld_q * 2, AT_D, 128, 1)))
+  if ((rc = encode_tmap_3d(&tq, q, 2, (uint64_t)(q_col0 + nh * AT_D), q_rows, q_bat,
+                           (uint64_t)ld_q * 2, q_rows * ld_q * 2, AT_D, 128, 1)))
     return rc;
-  if ((rc = encode_tmap_3d(&tk, k, 2, (uint64_t)(k_col0 + nh * AT_D), (uint64_t)Tk, (uint64_t)B,
-                           (uint64_t)ld_k * 2, (uint64_t)Tk * ld_k * 2, AT_D, 128, 1)))
+  if ((rc = encode_tmap_3d(&tk, k, 2, (uint64_t)(k_col0 + nh * AT_D), k_rows, k_bat,
+                           (uint64_t)ld_k * 2, k_rows * ld_k * 2, AT_D, 128, 1)))
     return rc;
-  if ((rc = encode_tmap_3d(&tv, v, 2, (uint64_t)(v_col0 + nh * AT_D), (uint64_t)Tk, (uint64_t)B,
-                           (uint64_t)ld_v * 2, (uint64_t)Tk * ld_v * 2, AT_D, 128, 1)))
+  if ((rc = encode_tmap_3d(&tv, v, 2, (uint64_t)(v_col0 + nh * AT_D), k_rows, k_bat,
+                           (uint64_t)ld_v * 2, k_rows * ld_v * 2, AT_D, 128, 1)))
     return rc;
   AttnFwdParams p;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.lse = lse; p.out_f32 = out_f32; p.kv_lens = kv_lens; p.ld_out = ld_out;
+  p.cu_q = pack ? pack->cu_rows : nullptr;
+  p.cu_k = (pack && pack_kv) ? pack->cu_rows : nullptr;
+  if (pack && pack_kv) p.kv_lens = pack->kv_lens;
   p.Tq = Tq; p.Tk = Tk; p.nh = nh;
   p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
   p.causal_off = causal_off;

@@ -361,6 +361,25 @@ ERGM_DEVINL float warp_max(float v) {
 }  // namespace ergm
 
 // ----------------------------------------------------------------------------
+// Packed variable-length batches (collate of custom_dataset.py:102-132 right-pads every sample to
+// the batch maximum and model.py then computes every pad position): with an ergm_pack the row kernels and GEMMs
+// work on the concatenation of the samples' real rows.  Device view of include/ergm_b200.h's ergm_pack.
+// ----------------------------------------------------------------------------
+namespace ergm {
+struct PackView {
+  const int* cu;       // [B + 1] first packed row of every sample
+  const int* row_b;    // [capacity] sample of a packed row
+  const int* row_t;    // [capacity] position (column of the padded [B, T] layout) of a packed row
+  const int* n_rows;   // [1] packed rows of this batch (run-time value)
+  const int* kv_lens;  // [B] attendable keys per sample (its real tokens)
+  ERGM_DEVINL bool on() const { return row_b != nullptr; }
+};
+}  // namespace ergm
+#define ERGM_PACK_VIEW(pack) \
+  ((pack) ? ergm::PackView{(pack)->cu_rows, (pack)->row_b, (pack)->row_t, (pack)->n_rows, (pack)->kv_lens} \
+          : ergm::PackView{nullptr, nullptr, nullptr, nullptr, nullptr})
+
+// ----------------------------------------------------------------------------
 // host-side helpers shared by the C-ABI translation units
 // ----------------------------------------------------------------------------
 #define ERGM_OK 0

@@ -29,6 +29,7 @@ struct EmbedFwdParams {
   DropoutSite drop;
   int do_drop;
   int* err_flag;            // set to 1 on an out-of-range id (device-side assert replacement)
+  PackView pk;              // packed batch: output row r <- (sample row_b[r], position row_t[r])
 };
 
 __global__ void __launch_bounds__(ROW_WARPS * 32) embed_fuse_fwd_kernel(const EmbedFwdParams p_in) {
@@ -37,10 +38,13 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) embed_fuse_fwd_kernel(const Em
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rows = p.B * p.T;
   const float keep_scale = p.do_drop ? p.drop.keep_scale() : 1.f;
-  for (int row = blockIdx.x * ROW_WARPS + warp; row < rows; row += gridDim.x * ROW_WARPS) {
-    const int b = row / p.T, t = row - b * p.T;
-    const int64_t id = p.ids[row];
-    const int64_t tt = p.tts ? p.tts[row] : -1;
+  const int n_rows = p.pk.on() ? min(rows, *p.pk.n_rows) : rows;
+  for (int row = blockIdx.x * ROW_WARPS + warp; row < n_rows; row += gridDim.x * ROW_WARPS) {
+    int b = row / p.T, t = row - b * p.T;
+    if (p.pk.on()) { b = p.pk.row_b[row]; t = p.pk.row_t[row]; }
+    const int src = b * p.T + t;   // index into the padded [B, T] id / type arrays
+    const int64_t id = p.ids[src];
+    const int64_t tt = p.tts ? p.tts[src] : -1;
     const int64_t pos = p.pos_ids ? p.pos_ids[b * p.pos_stride_b + t]
                                   : (int64_t)((p.past_lens ? p.past_lens[b] : p.past_len) + t);
     if (id < 0 || id >= p.vocab || pos < 0 || pos >= p.n_pos || (p.tts && (tt < 0 || tt >= p.vocab))) {
@@ -116,6 +120,7 @@ struct EmbedBwdParams {
   int do_drop;
   int vocab, n_pos;         // table heights: an index outside [0, height) is skipped and flagged
   int* err_flag;            // nullable
+  PackView pk;              // packed batch: dh row r belongs to (sample row_b[r], position row_t[r])
 };
 
 ERGM_DEVINL void red_add4(float* addr, const float4 v) {
@@ -130,7 +135,7 @@ __global__ void embed_bwd_kernel(const EmbedBwdParams p_in) {
   const int c = threadIdx.x;  // float4 column
   if (c >= p.H / 4) return;
   const int r0 = blockIdx.x * p.rows_per_cta;
-  const int r1 = min(r0 + p.rows_per_cta, p.rows);
+  const int r1 = min(r0 + p.rows_per_cta, p.pk.on() ? min(p.rows, *p.pk.n_rows) : p.rows);
   const float keep_scale = p.do_drop ? p.drop.keep_scale() : 1.f;
   int64_t cur[3] = {-1, -1, -1};
   float4 acc[3];
@@ -144,11 +149,13 @@ __global__ void embed_bwd_kernel(const EmbedBwdParams p_in) {
       g.x = (k & 1u) ? g.x * keep_scale : 0.f; g.y = (k & 2u) ? g.y * keep_scale : 0.f;
       g.z = (k & 4u) ? g.z * keep_scale : 0.f; g.w = (k & 8u) ? g.w * keep_scale : 0.f;
     }
-    const int t = row % p.T;
+    int bq = row / p.T, t = row % p.T;
+    if (p.pk.on()) { bq = p.pk.row_b[row]; t = p.pk.row_t[row]; }
+    const int src = bq * p.T + t;
     int64_t idx[3];
-    idx[0] = p.ids ? p.ids[row] : -1;
-    idx[1] = p.tts ? p.tts[row] : -1;
-    idx[2] = p.dwpe ? (p.pos_ids ? p.pos_ids[(row / p.T) * p.pos_stride_b + t] : (int64_t)(p.past_len + t)) : -1;
+    idx[0] = p.ids ? p.ids[src] : -1;
+    idx[1] = p.tts ? p.tts[src] : -1;
+    idx[2] = p.dwpe ? (p.pos_ids ? p.pos_ids[bq * p.pos_stride_b + t] : (int64_t)(p.past_len + t)) : -1;
     // never scatter outside the gradient tables (the forward flagged the same row): skip + flag
     const bool bad0 = p.ids && (idx[0] < 0 || idx[0] >= p.vocab), bad1 = p.tts && (idx[1] < 0 || idx[1] >= p.vocab),
                bad2 = p.dwpe && (idx[2] < 0 || idx[2] >= p.n_pos);
@@ -169,8 +176,8 @@ __global__ void embed_bwd_kernel(const EmbedBwdParams p_in) {
         acc[s].x += g.x; acc[s].y += g.y; acc[s].z += g.z; acc[s].w += g.w;
       }
     }
-    if (p.dimgs && t == 0) red_add4(p.dimgs + (int64_t)(row / p.T) * p.H + 4 * c, g);
-    if (p.dauds && t == 1) red_add4(p.dauds + (int64_t)(row / p.T) * p.H + 4 * c, g);
+    if (p.dimgs && t == 0) red_add4(p.dimgs + (int64_t)bq * p.H + 4 * c, g);
+    if (p.dauds && t == 1) red_add4(p.dauds + (int64_t)bq * p.H + 4 * c, g);
   }
 #pragma unroll
   for (int s = 0; s < 3; ++s)
@@ -185,11 +192,12 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ beta, __nv_bfloat16* __restrict__ y_bf16,
               float* __restrict__ y_f32, float* __restrict__ mean_out, float* __restrict__ rstd_out,
-              int rows, float eps, const int* __restrict__ row_idx) {
+              int rows, float eps, const int* __restrict__ row_idx, const int* __restrict__ rows_dyn) {
   constexpr int H = NV * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();  // the next kernel's blocks may be scheduled as ours drain ...
   pdl_wait();               // ... and we touch nothing before everything upstream has completed
+  if (rows_dyn) rows = min(rows, *rows_dyn);   // packed batch: run-time row count
   float4 g[NV], bt[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -255,6 +263,7 @@ struct LnBwdParams {
   int dy_f32;
   DropoutSite drop;      // mask applied to the bf16 copy only
   int do_drop;
+  const int* rows_dyn;   // nullable: run-time row count (packed batch); rows beyond it are not touched
 };
 
 // HBM-bound (dy + x + dres read, dx fp32 + dx bf16 written: 16 B / element at fp32 dy).  v1 (one warp
@@ -278,6 +287,7 @@ __global__ void __launch_bounds__(LNB_THREADS, 1) ln_bwd_kernel(const LnBwdParam
   extern __shared__ __align__(128) unsigned char lnb_smem[];
   LnBwdParams p = p_in;
   p.drop = p_in.drop.resolved();
+  if (p.rows_dyn) p.rows = min(p.rows, *p.rows_dyn);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t dy_row = (uint32_t)H * (p.dy_f32 ? 4u : 2u), f_row = (uint32_t)H * 4u;
   const uint32_t dy_bytes = LNB_ROWS * dy_row, f_bytes = LNB_ROWS * f_row;
@@ -455,8 +465,10 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ src, int64_t ld, int rows, 
 // demand loads that queue behind the mainloop's saturated TMA stream (measured +80 us per GEMM).
 __global__ void __launch_bounds__(256)
 gelu_bwd_colsum_kernel(__nv_bfloat16* __restrict__ dg, const __nv_bfloat16* __restrict__ u, int64_t ld,
-                       int rows, int N, float* __restrict__ colsum, int rows_per_cta, int exact) {
+                       int rows, int N, float* __restrict__ colsum, int rows_per_cta, int exact,
+                       const int* __restrict__ rows_dyn) {
   __shared__ float red[8][256];
+  if (rows_dyn) rows = min(rows, *rows_dyn);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int col0 = blockIdx.x * 256 + lane * 8;
   const int r0 = blockIdx.y * rows_per_cta, r1 = min(r0 + rows_per_cta, rows);
@@ -497,8 +509,10 @@ gelu_bwd_colsum_kernel(__nv_bfloat16* __restrict__ dg, const __nv_bfloat16* __re
 // rounded values (used for dQ: fp32 atomic accumulator -> bf16 operand + bias gradient)
 __global__ void __launch_bounds__(256)
 cast_f32_bf16_2d_kernel(const float* __restrict__ src, int64_t ld_src, __nv_bfloat16* __restrict__ dst,
-                        int64_t ld_dst, int rows, int N, float* __restrict__ colsum, int rows_per_cta) {
+                        int64_t ld_dst, int rows, int N, float* __restrict__ colsum, int rows_per_cta,
+                        const int* __restrict__ rows_dyn) {
   __shared__ float red[8][128];
+  if (rows_dyn) rows = min(rows, *rows_dyn);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int col0 = blockIdx.x * 128 + lane * 4;
   const int r0 = blockIdx.y * rows_per_cta, r1 = min(r0 + rows_per_cta, rows);
@@ -616,12 +630,13 @@ extern "C" int ergm_embed_fuse_fwd(const int64_t* ids, const int64_t* token_type
                                    const float* imgs, int64_t ld_img, const float* auds,
                                    int64_t ld_aud, float* out, int B, int T, int H, int past_len,
                                    int vocab, int n_pos, float dropout_p, uint64_t seed,
-                                   uint64_t offset, int* err_flag, void* stream) {
+                                   uint64_t offset, int* err_flag, const ergm_pack* pack, void* stream) {
   if (!ids || !wte || !wpe || !out || !err_flag || B <= 0 || T <= 0 || H % 128) return ERGM_ERR_ARG;
   if ((imgs && ld_img % 4) || (auds && ld_aud % 4)) return ERGM_ERR_ARG;
+  if (pack && (!pack->row_b || !pack->row_t || !pack->n_rows)) return ERGM_ERR_ARG;
   EmbedFwdParams p{ids, token_type_ids, position_ids, pos_stride_b, past_lens, wte, wpe, imgs, auds, out, ld_img, ld_aud,
                    B, T, H, past_len, vocab, n_pos,
-                   make_site(seed, offset, dropout_p, (uint32_t)H), dropout_p > 0.f, err_flag};
+                   make_site(seed, offset, dropout_p, (uint32_t)H), dropout_p > 0.f, err_flag, ERGM_PACK_VIEW(pack)};
   embed_fuse_fwd_kernel<<<row_grid(B * T), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
   return (int)cudaGetLastError();
 }
@@ -637,13 +652,15 @@ extern "C" int ergm_gather_rows_bf16(const int64_t* ids, const float* table, voi
 extern "C" int ergm_embed_bwd(const float* dh, const int64_t* ids, const int64_t* token_type_ids,
                               const int64_t* position_ids, int64_t pos_stride_b, float* dwte, float* dwpe, float* dimgs,
                               float* dauds, int rows, int T, int H, int past_len, int vocab, int n_pos,
-                              float dropout_p, uint64_t seed, uint64_t offset, int* err_flag, void* stream) {
+                              float dropout_p, uint64_t seed, uint64_t offset, int* err_flag, const ergm_pack* pack,
+                              void* stream) {
   if (!dh || rows <= 0 || T <= 0 || H % 128 || H / 4 > 1024) return ERGM_ERR_ARG;
+  if (pack && (!pack->row_b || !pack->row_t || !pack->n_rows)) return ERGM_ERR_ARG;
   if ((ids || token_type_ids) && (!dwte || vocab <= 0)) return ERGM_ERR_ARG;
   if (dwpe && n_pos <= 0) return ERGM_ERR_ARG;
   EmbedBwdParams p{dh, ids, token_type_ids, position_ids, pos_stride_b, dwte, dwpe, dimgs, dauds, rows, T, H,
                    past_len, 32, make_site(seed, offset, dropout_p, (uint32_t)H),
-                   dropout_p > 0.f, vocab, n_pos, err_flag};
+                   dropout_p > 0.f, vocab, n_pos, err_flag, ERGM_PACK_VIEW(pack)};
   const int threads = ((H / 4 + 31) / 32) * 32;
   embed_bwd_kernel<<<(rows + 31) / 32, threads, 0, (cudaStream_t)stream>>>(p);
   return (int)cudaGetLastError();
@@ -651,12 +668,12 @@ extern "C" int ergm_embed_bwd(const float* dh, const int64_t* ids, const int64_t
 
 extern "C" int ergm_ln_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16,
                            float* y_f32, float* mean, float* rstd, int rows, int H, float eps,
-                           const int* row_idx, void* stream) {
+                           const int* row_idx, const int* rows_dyn, void* stream) {
   if (!x || !gamma || !beta || rows <= 0 || H % 128) return ERGM_ERR_ARG;
   return dispatch_nv(H, [&](auto nv) {
     return (int)launch_pdl(ln_fwd_kernel<decltype(nv)::value>, dim3((unsigned)row_grid(rows)), dim3(ROW_WARPS * 32), 0,
                            (cudaStream_t)stream, 1, x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y_bf16), y_f32, mean,
-                           rstd, rows, eps, row_idx);
+                           rstd, rows, eps, row_idx, rows_dyn);
   });
 }
 
@@ -664,12 +681,12 @@ extern "C" int ergm_ln_bwd(const void* dy, int dy_is_f32, const float* x, const 
                            const float* rstd, const float* gamma, const float* dres_in,
                            float* dx_out, void* dx_bf16, float* dgamma, float* dbeta,
                            float* dbias_next, int rows, int H, float dropout_p, uint64_t seed,
-                           uint64_t offset, void* stream) {
+                           uint64_t offset, const int* rows_dyn, void* stream) {
   if (!dy || !x || !mean || !rstd || !gamma || !dgamma || !dbeta || rows <= 0 || H % 128)
     return ERGM_ERR_ARG;
   LnBwdParams p{dy, x, mean, rstd, gamma, dres_in, dx_out, reinterpret_cast<__nv_bfloat16*>(dx_bf16),
                 dgamma, dbeta, dbias_next, rows, dy_is_f32,
-                make_site(seed, offset, dropout_p, (uint32_t)H), dropout_p > 0.f};
+                make_site(seed, offset, dropout_p, (uint32_t)H), dropout_p > 0.f, rows_dyn};
   if (reinterpret_cast<uintptr_t>(dy) & 15 || reinterpret_cast<uintptr_t>(x) & 15 ||
       (dres_in && (reinterpret_cast<uintptr_t>(dres_in) & 15)))
     return ERGM_ERR_ARG;
@@ -714,7 +731,7 @@ extern "C" int ergm_colsum_bf16(const void* src, int64_t ld, int rows, int N, fl
 }
 
 extern "C" int ergm_gelu_bwd_colsum(void* dg_bf16, const void* u_bf16, int64_t ld, int rows, int N,
-                                    float* colsum, int exact, void* stream) {
+                                    float* colsum, int exact, const int* rows_dyn, void* stream) {
   if (!dg_bf16 || !u_bf16 || rows <= 0 || N <= 0 || N % 8 || ld % 8) return ERGM_ERR_ARG;
   const int col_ctas = (N + 255) / 256;
   int row_splits = (4 * num_sms() + col_ctas - 1) / col_ctas;
@@ -722,19 +739,19 @@ extern "C" int ergm_gelu_bwd_colsum(void* dg_bf16, const void* u_bf16, int64_t l
   const int rpc = (rows + row_splits - 1) / row_splits;
   gelu_bwd_colsum_kernel<<<dim3(col_ctas, (rows + rpc - 1) / rpc), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<__nv_bfloat16*>(dg_bf16), reinterpret_cast<const __nv_bfloat16*>(u_bf16), ld, rows, N,
-      colsum, rpc, exact);
+      colsum, rpc, exact, rows_dyn);
   return (int)cudaGetLastError();
 }
 
 extern "C" int ergm_cast_f32_bf16_2d(const float* src, int64_t ld_src, void* dst, int64_t ld_dst,
-                                     int rows, int N, float* colsum, void* stream) {
+                                     int rows, int N, float* colsum, const int* rows_dyn, void* stream) {
   if (!src || !dst || rows <= 0 || N <= 0 || N % 4 || ld_src % 4 || ld_dst % 4) return ERGM_ERR_ARG;
   const int col_ctas = (N + 127) / 128;
   int row_splits = (2 * num_sms() + col_ctas - 1) / col_ctas;
   if (row_splits > (rows + 63) / 64) row_splits = (rows + 63) / 64;
   const int rpc = (rows + row_splits - 1) / row_splits;
   cast_f32_bf16_2d_kernel<<<dim3(col_ctas, (rows + rpc - 1) / rpc), 256, 0, (cudaStream_t)stream>>>(
-      src, ld_src, reinterpret_cast<__nv_bfloat16*>(dst), ld_dst, rows, N, colsum, rpc);
+      src, ld_src, reinterpret_cast<__nv_bfloat16*>(dst), ld_dst, rows, N, colsum, rpc, rows_dyn);
   return (int)cudaGetLastError();
 }
 

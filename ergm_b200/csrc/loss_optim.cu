@@ -176,11 +176,13 @@ emotion_fwd_kernel(const float* __restrict__ x_final, const float* __restrict__ 
                    const float* __restrict__ beta, const float* __restrict__ w_emo,
                    const int64_t* __restrict__ emo_labels, int B, int T, int H,
                    float* __restrict__ hlast, float* __restrict__ logits_out,
-                   float* __restrict__ dlogits_out, float* __restrict__ sums, int* err_flag) {
+                   float* __restrict__ dlogits_out, float* __restrict__ sums, int* err_flag,
+                   const int* __restrict__ cu_rows) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * 4 + warp;
   if (b >= B) return;
-  const int row = b * T + T - 1;  // last (possibly padded) position, model.py:700
+  // last (possibly padded) position, model.py:700; packed batches: the sample's last packed row (position T-1)
+  const int row = cu_rows ? cu_rows[b + 1] - 1 : b * T + T - 1;
   const float mu = mean[row], rs = rstd[row];
   float acc[NUM_EMO];
 #pragma unroll
@@ -219,7 +221,8 @@ emotion_fwd_kernel(const float* __restrict__ x_final, const float* __restrict__ 
 __global__ void __launch_bounds__(256)
 emotion_bwd_kernel(const float* __restrict__ dlog, const float* __restrict__ hlast,
                    const float* __restrict__ w_emo, const float* __restrict__ scale_ptr, int B,
-                   int T, int H, float* __restrict__ dw_emo, float* __restrict__ dyf) {
+                   int T, int H, float* __restrict__ dw_emo, float* __restrict__ dyf,
+                   const int* __restrict__ cu_rows) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= H) return;
   const float s = *scale_ptr;
@@ -235,7 +238,7 @@ emotion_bwd_kernel(const float* __restrict__ dlog, const float* __restrict__ hla
       dw[j] += d * h;
       dh += d * w[j];
     }
-    if (dyf) dyf[((int64_t)b * T + T - 1) * H + c] += dh;
+    if (dyf) dyf[(int64_t)(cu_rows ? cu_rows[b + 1] - 1 : b * T + T - 1) * H + c] += dh;
   }
   if (dw_emo) {
 #pragma unroll
@@ -312,15 +315,25 @@ adamw_flat_kernel(float* __restrict__ p, const void* __restrict__ g, float* __re
 constexpr int PLAN_THREADS = 1024;
 __global__ void __launch_bounds__(PLAN_THREADS)
 lm_rows_plan_kernel(const int64_t* __restrict__ labels, int rows, int T, int* __restrict__ row_idx,
-                    int64_t* __restrict__ labels_c, int* __restrict__ count_out) {
+                    int64_t* __restrict__ labels_c, int* __restrict__ count_out, const PackView pk) {
   __shared__ int s_warp[PLAN_THREADS / 32];
   __shared__ int s_base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_base = 0;
   __syncthreads();
+  const int cap = rows;
+  if (pk.on()) rows = min(rows, *pk.n_rows);   // packed batch: row r is (sample row_b[r], position row_t[r])
   for (int r0 = 0; r0 < rows; r0 += PLAN_THREADS) {
     const int row = r0 + tid;
-    const int64_t tgt = row < rows ? shifted_target(labels, row, T) : (int64_t)-100;
+    int64_t tgt = -100;
+    if (row < rows) {
+      if (pk.on()) {
+        const int t = pk.row_t[row];
+        tgt = (t + 1 < T) ? labels[pk.row_b[row] * T + t + 1] : (int64_t)-100;
+      } else {
+        tgt = shifted_target(labels, row, T);
+      }
+    }
     const bool keep = tgt != -100;
     const unsigned m = __ballot_sync(0xffffffffu, keep);
     if (lane == 0) s_warp[warp] = __popc(m);
@@ -342,7 +355,7 @@ lm_rows_plan_kernel(const int64_t* __restrict__ labels, int rows, int T, int* __
   }
   const int n = s_base;
   // pad up to the next multiple of 128 rows: ignored targets, "no source row"
-  for (int i = n + tid; i < ((n + 127) & ~127) && i < rows; i += PLAN_THREADS) { row_idx[i] = -1; labels_c[i] = -100; }
+  for (int i = n + tid; i < ((n + 127) & ~127) && i < cap; i += PLAN_THREADS) { row_idx[i] = -1; labels_c[i] = -100; }
   if (tid == 0) *count_out = n;
 }
 
@@ -376,14 +389,74 @@ scatter_rows_dyn_kernel(const float* __restrict__ src, const int* __restrict__ r
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Packed variable-length batches: plan of the packed row layout from the per-sample token counts.
+// Sample b contributes its lens[b] real positions and, when it is padded (lens[b] < T), ONE more row for position
+// T-1: the emotion head reads the last position (model.py:700) whatever it holds, and under the right-padded
+// attention mask that position attends to the sample's real tokens only - so its hidden state needs no other pad row.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+pack_plan_kernel(const int* __restrict__ lens, int B, int T, int* __restrict__ cu, int* __restrict__ row_b,
+                 int* __restrict__ row_t, int* __restrict__ n_rows, int* __restrict__ kv_lens, int cap) {
+  __shared__ int s_cu[1025];
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    int acc = 0;
+    for (int b = 0; b < B; ++b) {
+      const int len = max(1, min(lens[b], T));
+      s_cu[b] = acc;
+      acc += len + (len < T ? 1 : 0);
+    }
+    s_cu[B] = acc;
+    *n_rows = acc;
+  }
+  __syncthreads();
+  for (int b = tid; b <= B; b += 1024) cu[b] = s_cu[b];
+  for (int b = 0; b < B; ++b) {
+    const int len = max(1, min(lens[b], T)), base = s_cu[b], n = s_cu[b + 1] - base;
+    if (tid == 0) kv_lens[b] = len;
+    for (int i = tid; i < n; i += 1024) { row_b[base + i] = b; row_t[base + i] = i < len ? i : T - 1; }
+  }
+  const int total = s_cu[B];
+  for (int i = total + tid; i < ((total + 127) & ~127) && i < cap; i += 1024) { row_b[i] = 0; row_t[i] = 0; }
+}
+
+// rows [*count, roundup(*count, 128)) of a [cap, row_bytes] buffer := 0 (operands of run-time-K GEMMs)
+__global__ void __launch_bounds__(256)
+zero_rows_dyn_kernel(unsigned char* __restrict__ buf, int64_t row_bytes, const int* __restrict__ count, int cap) {
+  const int n = *count;
+  const int n_pad = min((n + 127) & ~127, cap);
+  const int64_t total16 = (int64_t)(n_pad - n) * row_bytes / 16;
+  uint4* base = reinterpret_cast<uint4*>(buf + (int64_t)n * row_bytes);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total16; i += (int64_t)gridDim.x * blockDim.x)
+    base[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 }  // namespace ergm
 
 using namespace ergm;
 
+extern "C" int ergm_pack_plan(const int* lens, int B, int T, int* cu_rows, int* row_b, int* row_t, int* n_rows,
+                              int* kv_lens, int cap, void* stream) {
+  if (!lens || !cu_rows || !row_b || !row_t || !n_rows || !kv_lens || B <= 0 || B > 1024 || T <= 0 || cap < B * T)
+    return ERGM_ERR_ARG;
+  pack_plan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(lens, B, T, cu_rows, row_b, row_t, n_rows, kv_lens, cap);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int ergm_zero_rows_dyn(void* buf, int64_t row_bytes, const int* count, int cap, void* stream) {
+  if (!buf || !count || row_bytes <= 0 || row_bytes % 16 || cap <= 0 || (reinterpret_cast<uintptr_t>(buf) & 15))
+    return ERGM_ERR_ARG;
+  zero_rows_dyn_kernel<<<num_sms(), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned char*>(buf), row_bytes, count, cap);
+  return (int)cudaGetLastError();
+}
+
 extern "C" int ergm_lm_rows_plan(const int64_t* labels, int rows, int T, int* row_idx, int64_t* labels_c,
-                                 int* count, void* stream) {
+                                 int* count, const ergm_pack* pack, void* stream) {
   if (!labels || !row_idx || !labels_c || !count || rows <= 0 || T <= 0) return ERGM_ERR_ARG;
-  lm_rows_plan_kernel<<<1, PLAN_THREADS, 0, (cudaStream_t)stream>>>(labels, rows, T, row_idx, labels_c, count);
+  if (pack && (!pack->row_b || !pack->row_t || !pack->n_rows)) return ERGM_ERR_ARG;
+  lm_rows_plan_kernel<<<1, PLAN_THREADS, 0, (cudaStream_t)stream>>>(labels, rows, T, row_idx, labels_c, count,
+                                                                     ERGM_PACK_VIEW(pack));
   return (int)cudaGetLastError();
 }
 
@@ -437,20 +510,20 @@ extern "C" int ergm_emotion_head_fwd(const float* x_final, const float* mean, co
                                      const float* gamma, const float* beta, const float* w_emo,
                                      const int64_t* emotion_labels, int B, int T, int H,
                                      float* hlast, float* logits, float* dlogits, float* sums,
-                                     int* err_flag, void* stream) {
+                                     int* err_flag, const int* cu_rows, void* stream) {
   if (!x_final || !mean || !rstd || !gamma || !beta || !w_emo || !hlast || !logits || B <= 0)
     return ERGM_ERR_ARG;
   if (emotion_labels && (!dlogits || !sums || !err_flag)) return ERGM_ERR_ARG;
   emotion_fwd_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
-      x_final, mean, rstd, gamma, beta, w_emo, emotion_labels, B, T, H, hlast, logits, dlogits, sums, err_flag);
+      x_final, mean, rstd, gamma, beta, w_emo, emotion_labels, B, T, H, hlast, logits, dlogits, sums, err_flag, cu_rows);
   return (int)cudaGetLastError();
 }
 
 extern "C" int ergm_emotion_head_bwd(const float* dlogits, const float* hlast, const float* w_emo,
                                      const float* scale_ptr, int B, int T, int H, float* dw_emo,
-                                     float* dyf, void* stream) {
+                                     float* dyf, const int* cu_rows, void* stream) {
   if (!dlogits || !hlast || !w_emo || !scale_ptr || B <= 0) return ERGM_ERR_ARG;
-  emotion_bwd_kernel<<<(H + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dlogits, hlast, w_emo, scale_ptr, B, T, H, dw_emo, dyf);
+  emotion_bwd_kernel<<<(H + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dlogits, hlast, w_emo, scale_ptr, B, T, H, dw_emo, dyf, cu_rows);
   return (int)cudaGetLastError();
 }
 

@@ -36,7 +36,9 @@ class Workspace:
         key = (name, tuple(shape), dtype)
         t = self.bufs.get(key)
         if t is None:
-            t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.device)
+            # always zero-initialised: with packed batches rows behind the run-time row count are never written, yet
+            # the TMA tiles of the last row block read them (they must hold finite values, never stale NaN patterns)
+            t = torch.zeros(shape, dtype=dtype, device=self.device)
             self.bufs[key] = t
         return t
 
@@ -92,6 +94,14 @@ class Engine:
         self.V = st.entries["transformer.wte.weight"][2][0]
         self.n_pos = st.entries["transformer.wpe.weight"][2][0]
 
+    def get_pack(self, B, T):
+        """Device-side row layout of a packed [B, T] batch (cached per shape: static addresses for CUDA graphs)."""
+        packs = self.__dict__.setdefault("_packs", {})
+        pk = packs.get((B, T))
+        if pk is None:
+            pk = packs[(B, T)] = ops.Pack(B, T, self.device)
+        return pk
+
     def ensure_params(self):
         if not self.store.valid():
             self.store.build()
@@ -134,6 +144,7 @@ class Engine:
     # GEMM helpers ------------------------------------------------------
     @staticmethod
     def _fwd_gemm(x, w_b, out, M, N, K, **kw):
+        # dyn_m (keyword): device int32 run-time row count of a packed batch
         ops.gemm(x, w_b, out, M=M, N=N, K=K, a_major=K_MAJOR, b_major=MN_MAJOR, **kw)
 
     @staticmethod
@@ -141,7 +152,7 @@ class Engine:
         # out[M, N_out] = dy[M, K_red] @ W[N_out, K_red]^T   (W is Conv1D [in=N_out, out=K_red])
         ops.gemm(dy, w_b, out, M=M, N=N_out, K=K_red, a_major=K_MAJOR, b_major=K_MAJOR, **kw)
 
-    def _wgrad_gemm(self, x, dy, dw, K_in, N_out, M_red):
+    def _wgrad_gemm(self, x, dy, dw, K_in, N_out, M_red, dyn=None):
         # dw[K_in, N_out] += x[M_red, K_in]^T @ dy[M_red, N_out]
         # 128x256 tiles, K (= tokens) split so that tiles * splits fills the 148 SMs once
         # (measured, profiles/r1_gemm_epilogue.md: 768x3072 44.1 -> 32.4 us, 768x768 15.1 -> 12.9 us
@@ -152,7 +163,7 @@ class Engine:
 
         def launch():
             ops.gemm(x, dy, dw, M=K_in, N=N_out, K=M_red, a_major=MN_MAJOR, b_major=MN_MAJOR,
-                     epilogue=L.EPI_ATOMIC, split_k=split, block_n=bn)
+                     epilogue=L.EPI_ATOMIC, split_k=split, block_n=bn, dyn_k=dyn)
 
         self._side_launch(launch)
 
@@ -183,10 +194,14 @@ class Engine:
     # ------------------------------------------------------------------
     def forward(self, input_ids, token_type_ids=None, labels=None, emotion_labels=None, imgs=None, auds=None,
                 caption_ids=None, position_ids=None, past_len=0, kv_lens=None, training=False, save=False,
-                want_logits=True, logits_fp32=False, dropout=None, heads=True, gen_state=None, legacy_past=None):
+                want_logits=True, logits_fp32=False, dropout=None, heads=True, gen_state=None, legacy_past=None,
+                pack=None):
         """Runs the full forward.  Returns a dict of device tensors (views into the workspace):
         logits [B,T,V] (bf16 or fp32, leading dim padded), emotion_logits [B,7], losses [5]
-        (loss, lm_loss, emo_loss, 1/n_valid, 1/n_samples), hidden (bf16 ln_f output)."""
+        (loss, lm_loss, emo_loss, 1/n_valid, 1/n_samples), hidden (bf16 ln_f output).
+        pack (ops.Pack, already planned from the per-sample token counts): packed variable-length batch
+        - every [B*T, .] matrix then holds the samples' real rows back to back (plus one row for position T-1 of a
+        padded sample, which the emotion head reads), and the run-time row count bounds every kernel."""
         self.ensure_params()
         self.store.refresh_shadow()
         cfg, H, nh, Lyr, I, V = self.cfg, self.H, self.nh, self.L, self.I, self.V
@@ -212,6 +227,14 @@ class Engine:
         def lname(base, l):
             return "%s_%d" % (base, l) if save else base
 
+        dyn = None
+        if pack is not None:
+            if legacy_past is not None or gen_state is not None or past_len or position_ids is not None or not heads:
+                raise L.ErgmError("packed batches are a training / scoring layout (no KV cache, default positions)")
+            if pack.B != B or pack.T != T:
+                raise ValueError("pack was planned for a [%d, %d] batch, got [%d, %d]" % (pack.B, pack.T, B, T))
+            dyn = pack.n_rows
+            kv_lens = None   # the pack carries the per-sample key counts
         fuse = imgs is not None and past_len == 0  # boundary decision (3): fusion on the prefill only
         if imgs is not None and auds is None:
             raise ValueError("imgs given without auds (model.py:495-498 uses both)")
@@ -223,7 +246,7 @@ class Engine:
         x = ws.get(lname("x", 0), (M, H), f32)
         ops.embed_fuse_fwd(input_ids, token_type_ids, position_ids, self.p("transformer.wte.weight"),
                            self.p("transformer.wpe.weight"), img2, aud2, x, past_len=past_len,
-                           dropout_p=pd_embd, seed=seed, offset=site0)
+                           dropout_p=pd_embd, seed=seed, offset=site0, pack=pack)
         enc = None
         Tc = Mc = 0
         if caption_ids is not None:
@@ -236,7 +259,7 @@ class Engine:
         sv = dict(B=B, T=T, Tc=Tc, layers=[], site0=site0, seed=seed, pd=(pd_embd, pd_attn, pd_res),
                   past_len=past_len, kv_lens=kv_lens, ids=input_ids, tts=token_type_ids, pos=position_ids,
                   cap=caption_ids, enc=enc, labels=labels, emo=emotion_labels, fuse=fuse,
-                  proj=proj_saved) if save else None
+                  proj=proj_saved, pack=pack) if save else None
         kv_present = []
         for l in range(Lyr):
             pfx = "transformer.h.%d." % l
@@ -246,10 +269,10 @@ class Engine:
             a1 = ws.get(lname("a1", l), (M, H), bf16)
             mean1 = ws.get(lname("mean1", l), (M,), f32)
             rstd1 = ws.get(lname("rstd1", l), (M,), f32)
-            ops.ln_fwd(x, self.p(pfx + "ln_1.weight"), self.p(pfx + "ln_1.bias"), a1, None, mean1, rstd1, eps)
+            ops.ln_fwd(x, self.p(pfx + "ln_1.weight"), self.p(pfx + "ln_1.bias"), a1, None, mean1, rstd1, eps, rows_dyn=dyn)
             qkv = ws.get("qkv_%d" % l if (save or past_len == 0) else "qkv", (M, 3 * H), bf16)
             self._fwd_gemm(a1, self.pb(pfx + "attn.c_attn.weight"), qkv, M, 3 * H, H,
-                           bias=self.p(pfx + "attn.c_attn.bias"))
+                           bias=self.p(pfx + "attn.c_attn.bias"), dyn_m=dyn)
             ctx = ws.get(lname("ctx", l), (M, H), bf16)
             ctx32 = ws.get(lname("ctx32", l), (M, H), f32) if save else None
             lse1 = ws.get(lname("lse1", l), (B, nh, T), f32)
@@ -265,7 +288,7 @@ class Engine:
             else:
                 ops.attn_fwd(qkv, qkv, qkv, ctx, lse1, B=B, nh=nh, Tq=T, Tk=T, q_col0=0, k_col0=H, v_col0=2 * H,
                              causal=True, kv_lens=kv_lens, dropout_p=pd_attn, seed=seed, offset=s_attn,
-                             out_f32=ctx32)
+                             out_f32=ctx32, pack=pack, pack_kv=pack is not None)
                 kv_present.append(qkv)
             if gen_state is not None:
                 ops.kv_to_pages(qkv, gen_state.pool[l], gen_state.block_table, kv_lens, B=B, T=T, nh=nh,
@@ -273,7 +296,7 @@ class Engine:
             x1 = ws.get(lname("x1", l), (M, H), f32) if save else x
             self._fwd_gemm(ctx, self.pb(pfx + "attn.c_proj.weight"), x1, M, H, H,
                            bias=self.p(pfx + "attn.c_proj.bias"), residual=x, dropout_p=pd_res, seed=seed,
-                           offset=s_res1)
+                           offset=s_res1, dyn_m=dyn)
             rec.update(x=x, a1=a1, mean1=mean1, rstd1=rstd1, qkv=qkv, ctx=ctx, ctx32=ctx32, lse1=lse1, x1=x1)
             # ---- cross attention over caption embeddings (model.py:311-329) ----
             x2 = x1
@@ -282,10 +305,10 @@ class Engine:
                 mean2 = ws.get(lname("mean2", l), (M,), f32)
                 rstd2 = ws.get(lname("rstd2", l), (M,), f32)
                 ops.ln_fwd(x1, self.p(pfx + "ln_cross_attn.weight"), self.p(pfx + "ln_cross_attn.bias"), a2, None,
-                           mean2, rstd2, eps)
+                           mean2, rstd2, eps, rows_dyn=dyn)
                 q2 = ws.get(lname("q2", l), (M, H), bf16)
                 self._fwd_gemm(a2, self.pb(pfx + "crossattention.q_attn.weight"), q2, M, H, H,
-                               bias=self.p(pfx + "crossattention.q_attn.bias"))
+                               bias=self.p(pfx + "crossattention.q_attn.bias"), dyn_m=dyn)
                 kv2 = gen_state.kv2[l] if gen_state is not None else ws.get(lname("kv2", l), (Mc, 2 * H), bf16)
                 self._fwd_gemm(enc, self.pb(pfx + "crossattention.c_attn.weight"), kv2, Mc, 2 * H, H,
                                bias=self.p(pfx + "crossattention.c_attn.bias"))
@@ -293,24 +316,24 @@ class Engine:
                 ctx2_32 = ws.get(lname("ctx2_32", l), (M, H), f32) if save else None
                 lse2 = ws.get(lname("lse2", l), (B, nh, T), f32)
                 ops.attn_fwd(q2, kv2, kv2, ctx2, lse2, B=B, nh=nh, Tq=T, Tk=Tc, q_col0=0, k_col0=0, v_col0=H,
-                             causal=False, dropout_p=pd_attn, seed=seed, offset=s_xattn, out_f32=ctx2_32)
+                             causal=False, dropout_p=pd_attn, seed=seed, offset=s_xattn, out_f32=ctx2_32, pack=pack)
                 x2 = ws.get(lname("x2", l), (M, H), f32) if save else x1
                 self._fwd_gemm(ctx2, self.pb(pfx + "crossattention.c_proj.weight"), x2, M, H, H,
                                bias=self.p(pfx + "crossattention.c_proj.bias"), residual=x1, dropout_p=pd_res,
-                               seed=seed, offset=s_res2)
+                               seed=seed, offset=s_res2, dyn_m=dyn)
                 rec.update(a2=a2, mean2=mean2, rstd2=rstd2, q2=q2, kv2=kv2, ctx2=ctx2, ctx2_32=ctx2_32, lse2=lse2, x2=x2)
             # ---- MLP (model.py:331-334, 262-267) ----
             a3 = ws.get(lname("a3", l), (M, H), bf16)
             mean3 = ws.get(lname("mean3", l), (M,), f32)
             rstd3 = ws.get(lname("rstd3", l), (M,), f32)
-            ops.ln_fwd(x2, self.p(pfx + "ln_2.weight"), self.p(pfx + "ln_2.bias"), a3, None, mean3, rstd3, eps)
+            ops.ln_fwd(x2, self.p(pfx + "ln_2.weight"), self.p(pfx + "ln_2.bias"), a3, None, mean3, rstd3, eps, rows_dyn=dyn)
             g = ws.get(lname("g", l), (M, I), bf16)
             u = ws.get(lname("u", l), (M, I), bf16) if save else None
             self._fwd_gemm(a3, self.pb(pfx + "mlp.c_fc.weight"), g, M, I, H, bias=self.p(pfx + "mlp.c_fc.bias"),
-                           preact=u, epilogue=L.EPI_GELU)
+                           preact=u, epilogue=L.EPI_GELU, dyn_m=dyn)
             x3 = ws.get(lname("x", l + 1), (M, H), f32) if save else x2
             self._fwd_gemm(g, self.pb(pfx + "mlp.c_proj.weight"), x3, M, H, I, bias=self.p(pfx + "mlp.c_proj.bias"),
-                           residual=x2, dropout_p=pd_res, seed=seed, offset=s_res3)
+                           residual=x2, dropout_p=pd_res, seed=seed, offset=s_res3, dyn_m=dyn)
             rec.update(a3=a3, mean3=mean3, rstd3=rstd3, g=g, u=u)
             if save:
                 sv["layers"].append(rec)
@@ -321,8 +344,9 @@ class Engine:
         hn = ws.get("hn", (M, H), bf16)
         meanf = ws.get("meanf", (M,), f32)
         rstdf = ws.get("rstdf", (M,), f32)
-        ops.ln_fwd(x, self.p("transformer.ln_f.weight"), self.p("transformer.ln_f.bias"), hn, None, meanf, rstdf, eps)
-        out = dict(hidden=hn, kv_present=kv_present, B=B, T=T)
+        ops.ln_fwd(x, self.p("transformer.ln_f.weight"), self.p("transformer.ln_f.bias"), hn, None, meanf, rstdf, eps,
+                   rows_dyn=dyn)
+        out = dict(hidden=hn, kv_present=kv_present, B=B, T=T, pack=pack)
         ldl = (V + 63) // 64 * 64  # padded leading dimension: 16-byte rows for TMA / vector access
         logits = None
         # Label-sparse LM head: with labels, only the rows whose shifted label is not -100 enter the loss and the
@@ -331,6 +355,8 @@ class Engine:
         # (outputs.logits, main.py:160) are produced by full_logits() only when somebody reads them.
         sparse = (labels is not None and not want_logits and not logits_fp32
                   and getattr(self.model, "ergm_sparse_lm_head", True))
+        if pack is not None and labels is not None and not sparse:
+            raise L.ErgmError("packed batches score the LM loss through the label-sparse head (ergm_sparse_lm_head)")
         need_lm = (want_logits or labels is not None) and not sparse
         if need_lm:
             logits = self.full_logits(hn, ws, logits_fp32)
@@ -344,7 +370,7 @@ class Engine:
         emo_dlog = ws.get("emo_dlog", (B, 7), f32)
         ops.emotion_head_fwd(x, meanf, rstdf, self.p("transformer.ln_f.weight"), self.p("transformer.ln_f.bias"),
                              self.p("emotion_head.weight"), emotion_labels, hlast, emo_logits, emo_dlog, sums,
-                             B=B, T=T)
+                             B=B, T=T, cu_rows=pack.cu if pack is not None else None)
         out["emotion_logits"] = emo_logits
         lse = row_loss = None
         sp = None
@@ -354,7 +380,7 @@ class Engine:
                       count=ws.get("lm_count", (1,), i32), hn_c=ws.get("lm_hn_c", (M, H), bf16),
                       logits_c=ws.get("lm_logits_c", (M, ldl), bf16))
             wte_b = self.pb("transformer.wte.weight")
-            ops.lm_rows_plan(labels, sp["row_idx"], sp["labels_c"], sp["count"], T=T)
+            ops.lm_rows_plan(labels, sp["row_idx"], sp["labels_c"], sp["count"], T=T, pack=pack)
             ops.gather_rows_dyn(hn, sp["row_idx"], sp["count"], sp["hn_c"])
             ops.gemm(sp["hn_c"], wte_b, sp["logits_c"], M=M, N=V, K=H, a_major=K_MAJOR, b_major=K_MAJOR,
                      dyn_m=sp["count"])
@@ -568,6 +594,8 @@ class Engine:
         cfg, H, nh, Lyr, I, V = self.cfg, self.H, self.nh, self.L, self.I, self.V
         B, T, Tc = sv["B"], sv["T"], sv["Tc"]
         M, Mc = B * T, B * Tc
+        pack = sv.get("pack")
+        dyn = pack.n_rows if pack is not None else None
         ws = self.ws_train
         f32, bf16 = torch.float32, torch.bfloat16
         seed, site0 = sv["seed"], sv["site0"]
@@ -621,18 +649,23 @@ class Engine:
             dhn.zero_()
         if sv["emo"] is not None:
             ops.emotion_head_bwd(sv["emo_dlog"], sv["hlast"], self.p("emotion_head.weight"), scales[1:2],
-                                 self.pg("emotion_head.weight"), dhn, B=B, T=T)
+                                 self.pg("emotion_head.weight"), dhn, B=B, T=T, cu_rows=pack.cu if pack is not None else None)
         # residual-stream gradient dx (fp32) and its bf16 (dropout-masked) operand copy dxb
         dx = ws.get("dx", (M, H), f32)
         dxb = ws.get("dxb", (M, H), bf16)
         last = "transformer.h.%d." % (Lyr - 1)
-        ops.ln_bwd(dhn, sv["xf"], sv["meanf"], sv["rstdf"], self.p("transformer.ln_f.weight"), None, dx, dxb,
-                   self.pg("transformer.ln_f.weight"), self.pg("transformer.ln_f.bias"),
-                   self.pg(last + "mlp.c_proj.bias"), dropout_p=pd_res, seed=seed,
-                   offset=site0 + 8 * (Lyr - 1) + 5)
         dI = ws.get("du", (M, I), bf16)
         dH = ws.get("dact", (M, H), bf16)
         dqkv = ws.get("dqkv", (M, 3 * H), bf16)
+        if pack is not None:
+            # gradient-side operands of the run-time-K weight-gradient GEMMs: rows [n, roundup(n, 128)) must be zero
+            # (no producer of this step writes them; a previous, longer batch may have)
+            for buf in (dxb, dI, dqkv):
+                ops.zero_rows_dyn(buf, dyn)
+        ops.ln_bwd(dhn, sv["xf"], sv["meanf"], sv["rstdf"], self.p("transformer.ln_f.weight"), None, dx, dxb,
+                   self.pg("transformer.ln_f.weight"), self.pg("transformer.ln_f.bias"),
+                   self.pg(last + "mlp.c_proj.bias"), dropout_p=pd_res, seed=seed,
+                   offset=site0 + 8 * (Lyr - 1) + 5, rows_dyn=dyn)
         dq_acc = ws.get("dq_acc", (M, H), f32)
         delta = ws.get("delta", (B, nh, T), f32)
         denc = None
@@ -641,43 +674,46 @@ class Engine:
             denc.zero_()
             dq2 = ws.get("dq2", (M, H), bf16)
             dkv2 = ws.get("dkv2", (Mc, 2 * H), bf16)
+            if pack is not None:
+                ops.zero_rows_dyn(dq2, dyn)
         for l in reversed(range(Lyr)):
             pfx = "transformer.h.%d." % l
             r = sv["layers"][l]
             s_attn, s_res1, s_xattn, s_res2, s_res3 = [site0 + 8 * l + 1 + i for i in range(5)]
             has_x = "a2" in r
             # ---- MLP backward ----
-            self._wgrad_gemm(r["g"], dxb, self.pg(pfx + "mlp.c_proj.weight"), I, H, M)
-            if M % 256 == 0 and I % 256 == 0:
+            self._wgrad_gemm(r["g"], dxb, self.pg(pfx + "mlp.c_proj.weight"), I, H, M, dyn)
+            if M % 256 == 0 and I % 256 == 0 and pack is None:
                 # GELU' and the c_fc bias gradient ride in the dgrad epilogue (lean FM_GELU_GRAD mode)
                 self._dgrad_gemm(dxb, self.pb(pfx + "mlp.c_proj.weight"), dI, M, I, H, gelu_grad_of=r["u"],
                                  colsum=self.pg(pfx + "mlp.c_fc.bias"), block_n=2256)
             else:
-                self._dgrad_gemm(dxb, self.pb(pfx + "mlp.c_proj.weight"), dI, M, I, H)
-                ops.gelu_bwd_colsum(dI, r["u"], self.pg(pfx + "mlp.c_fc.bias"))
-            self._wgrad_gemm(r["a3"], dI, self.pg(pfx + "mlp.c_fc.weight"), H, I, M)
-            self._dgrad_gemm(dI, self.pb(pfx + "mlp.c_fc.weight"), dH, M, H, I)
+                # (packed batches: the fused epilogue's column sums only exist on whole 32-row slabs)
+                self._dgrad_gemm(dxb, self.pb(pfx + "mlp.c_proj.weight"), dI, M, I, H, dyn_m=dyn)
+                ops.gelu_bwd_colsum(dI, r["u"], self.pg(pfx + "mlp.c_fc.bias"), rows_dyn=dyn)
+            self._wgrad_gemm(r["a3"], dI, self.pg(pfx + "mlp.c_fc.weight"), H, I, M, dyn)
+            self._dgrad_gemm(dI, self.pb(pfx + "mlp.c_fc.weight"), dH, M, H, I, dyn_m=dyn)
             x_in = r["x2"] if has_x else r["x1"]
             nb = pfx + ("crossattention.c_proj.bias" if has_x else "attn.c_proj.bias")
             self._side_join()  # dxb is about to be overwritten
             ops.ln_bwd(dH, x_in, r["mean3"], r["rstd3"], self.p(pfx + "ln_2.weight"), dx, dx, dxb,
                        self.pg(pfx + "ln_2.weight"), self.pg(pfx + "ln_2.bias"), self.pg(nb), dropout_p=pd_res,
-                       seed=seed, offset=s_res2 if has_x else s_res1)
+                       seed=seed, offset=s_res2 if has_x else s_res1, rows_dyn=dyn)
             # ---- cross attention backward ----
             if has_x:
-                self._wgrad_gemm(r["ctx2"], dxb, self.pg(pfx + "crossattention.c_proj.weight"), H, H, M)
-                self._dgrad_gemm(dxb, self.pb(pfx + "crossattention.c_proj.weight"), dH, M, H, H)
+                self._wgrad_gemm(r["ctx2"], dxb, self.pg(pfx + "crossattention.c_proj.weight"), H, H, M, dyn)
+                self._dgrad_gemm(dxb, self.pb(pfx + "crossattention.c_proj.weight"), dH, M, H, H, dyn_m=dyn)
                 dq_acc.zero_()
                 self._side_join()  # dkv2 is about to be overwritten
                 gbx = self.pg(pfx + "crossattention.c_attn.bias")  # K / V bias gradients come out of attn_bwd
                 ops.attn_bwd(r["q2"], r["kv2"], r["kv2"], r["ctx2"], dH, r["lse2"], delta, dq_acc, dkv2, dkv2,
                              B=B, nh=nh, Tq=T, Tk=Tc, q_col0=0, k_col0=0, v_col0=H, dk_col0=0, dv_col0=H,
                              causal=False, dropout_p=pd_attn, seed=seed, offset=s_xattn, out_f32=r["ctx2_32"],
-                             dk_colsum=gbx[:H], dv_colsum=gbx[H:])
-                ops.cast_f32_bf16_2d(dq_acc, dq2, self.pg(pfx + "crossattention.q_attn.bias"))
-                self._wgrad_gemm(r["a2"], dq2, self.pg(pfx + "crossattention.q_attn.weight"), H, H, M)
+                             dk_colsum=gbx[:H], dv_colsum=gbx[H:], pack=pack)
+                ops.cast_f32_bf16_2d(dq_acc, dq2, self.pg(pfx + "crossattention.q_attn.bias"), rows_dyn=dyn)
+                self._wgrad_gemm(r["a2"], dq2, self.pg(pfx + "crossattention.q_attn.weight"), H, H, M, dyn)
                 self._wgrad_gemm(sv["enc"], dkv2, self.pg(pfx + "crossattention.c_attn.weight"), H, 2 * H, Mc)
-                self._dgrad_gemm(dq2, self.pb(pfx + "crossattention.q_attn.weight"), dH, M, H, H)
+                self._dgrad_gemm(dq2, self.pb(pfx + "crossattention.q_attn.weight"), dH, M, H, H, dyn_m=dyn)
                 # d enc accumulates over layers (the caption embeddings feed every block, model.py:521)
                 # (off the critical path too: denc is only consumed by the embedding backward at the very end)
                 wkv = self.pb(pfx + "crossattention.c_attn.weight")
@@ -685,10 +721,10 @@ class Engine:
                 self._side_join()
                 ops.ln_bwd(dH, r["x1"], r["mean2"], r["rstd2"], self.p(pfx + "ln_cross_attn.weight"), dx, dx, dxb,
                            self.pg(pfx + "ln_cross_attn.weight"), self.pg(pfx + "ln_cross_attn.bias"),
-                           self.pg(pfx + "attn.c_proj.bias"), dropout_p=pd_res, seed=seed, offset=s_res1)
+                           self.pg(pfx + "attn.c_proj.bias"), dropout_p=pd_res, seed=seed, offset=s_res1, rows_dyn=dyn)
             # ---- self attention backward ----
-            self._wgrad_gemm(r["ctx"], dxb, self.pg(pfx + "attn.c_proj.weight"), H, H, M)
-            self._dgrad_gemm(dxb, self.pb(pfx + "attn.c_proj.weight"), dH, M, H, H)
+            self._wgrad_gemm(r["ctx"], dxb, self.pg(pfx + "attn.c_proj.weight"), H, H, M, dyn)
+            self._dgrad_gemm(dxb, self.pb(pfx + "attn.c_proj.weight"), dH, M, H, H, dyn_m=dyn)
             dq_acc.zero_()
             self._side_join()  # dqkv is about to be overwritten
             qkv = r["qkv"]
@@ -696,20 +732,20 @@ class Engine:
             ops.attn_bwd(qkv, qkv, qkv, r["ctx"], dH, r["lse1"], delta, dq_acc, dqkv, dqkv, B=B, nh=nh, Tq=T, Tk=T,
                          q_col0=0, k_col0=H, v_col0=2 * H, dk_col0=H, dv_col0=2 * H, causal=True,
                          kv_lens=sv["kv_lens"], dropout_p=pd_attn, seed=seed, offset=s_attn, out_f32=r["ctx32"],
-                         dk_colsum=gb[H:2 * H], dv_colsum=gb[2 * H:])
-            ops.cast_f32_bf16_2d(dq_acc, dqkv[:, :H], gb[:H])
-            self._wgrad_gemm(r["a1"], dqkv, self.pg(pfx + "attn.c_attn.weight"), H, 3 * H, M)
-            self._dgrad_gemm(dqkv, self.pb(pfx + "attn.c_attn.weight"), dH, M, H, 3 * H)
+                         dk_colsum=gb[H:2 * H], dv_colsum=gb[2 * H:], pack=pack, pack_kv=pack is not None)
+            ops.cast_f32_bf16_2d(dq_acc, dqkv[:, :H], gb[:H], rows_dyn=dyn)
+            self._wgrad_gemm(r["a1"], dqkv, self.pg(pfx + "attn.c_attn.weight"), H, 3 * H, M, dyn)
+            self._dgrad_gemm(dqkv, self.pb(pfx + "attn.c_attn.weight"), dH, M, H, 3 * H, dyn_m=dyn)
             self._side_join()
             if l > 0:
                 prev = "transformer.h.%d." % (l - 1)
                 ops.ln_bwd(dH, r["x"], r["mean1"], r["rstd1"], self.p(pfx + "ln_1.weight"), dx, dx, dxb,
                            self.pg(pfx + "ln_1.weight"), self.pg(pfx + "ln_1.bias"),
                            self.pg(prev + "mlp.c_proj.bias"), dropout_p=pd_res, seed=seed,
-                           offset=site0 + 8 * (l - 1) + 5)
+                           offset=site0 + 8 * (l - 1) + 5, rows_dyn=dyn)
             else:
                 ops.ln_bwd(dH, r["x"], r["mean1"], r["rstd1"], self.p(pfx + "ln_1.weight"), dx, dx, None,
-                           self.pg(pfx + "ln_1.weight"), self.pg(pfx + "ln_1.bias"), None)
+                           self.pg(pfx + "ln_1.weight"), self.pg(pfx + "ln_1.bias"), None, rows_dyn=dyn)
             if on_layer_done is not None:
                 # every gradient of layer l is final now: its mlp.c_proj.bias was completed earlier by
                 # layer l+1's ln_1 backward, and this layer's ln_1 backward only touched layer l-1's slot
@@ -722,7 +758,7 @@ class Engine:
             dfeat[what].zero_()
         ops.embed_bwd(dx, sv["ids"], sv["tts"], sv["pos"], self.pg("transformer.wte.weight"),
                       self.pg("transformer.wpe.weight"), T=T, past_len=sv["past_len"], dimgs=dfeat.get("imgs"),
-                      dauds=dfeat.get("auds"), dropout_p=pd_embd, seed=seed, offset=site0)
+                      dauds=dfeat.get("auds"), dropout_p=pd_embd, seed=seed, offset=site0, pack=pack)
         for what, (pname, pooled, D) in proj.items():
             # Linear(D -> H) backward: dW[H, D] += dfeat^T @ pooled, db += colsum(dfeat)
             dfb = ws.get("d" + what + "_bf16", (B, H), bf16)

@@ -363,6 +363,11 @@ class GPT2LMHeadModel(GPT2PreTrainedModel):
         # label-sparse LM head (engine.forward): with labels, head + CE + their backward run only on the rows whose
         # shifted label is not -100; identical loss and gradients, outputs.logits computed on first access
         self.ergm_sparse_lm_head = True
+        # packed variable-length batches: with a right-padded attention_mask, compute only the real
+        # positions of every sample (plus position T-1, which the emotion head reads).  Results equal the reference
+        # called WITH that attention_mask at every real position and in the emotion head; main.py passes no mask
+        # (its pad positions attend to earlier pads), so this is opt-in.
+        self.ergm_packed = False
         # "bf16" = bf16 tensor-core operands, fp32 accumulation / residual / statistics (throughput mode);
         # "fp32" = split-operand fp32-accurate products (forward only; logits within 1e-4 of the reference)
         self.ergm_precision = "bf16"
@@ -482,8 +487,13 @@ class GPT2LMHeadModel(GPT2PreTrainedModel):
                 return self._forward_with_legacy_past(input_ids, token_type_ids, pos, past_key_values,
                                                       attention_mask, caption_ids, use_cache, return_dict)
             kv_lens = None
+            pack = None
             if attention_mask is not None:
                 kv_lens = self._kv_lens_from_mask(attention_mask.to(dev), B, T)
+                if self.ergm_packed and self.ergm_precision != "fp32":
+                    pack = eng.get_pack(B, T).plan(kv_lens.contiguous())
+                    kv_lens = None
+                    use_cache = False
             save = training and (labels is not None or emotion_labels is not None)
             if self.ergm_precision == "fp32":
                 if save:
@@ -496,7 +506,7 @@ class GPT2LMHeadModel(GPT2PreTrainedModel):
                 # with labels the LM head runs label-sparse and .logits (all positions) is computed on first access
                 out = eng.forward(input_ids, token_type_ids, labels, emotion_labels, imgs, auds, caption_ids, pos,
                                   past_len=0, kv_lens=kv_lens, training=self.training, save=save,
-                                  want_logits=labels is None, logits_fp32=self.fp32_logits)
+                                  want_logits=labels is None, logits_fp32=self.fp32_logits, pack=pack)
             loss = lm_loss = emo_loss = None
             if labels is not None or emotion_labels is not None:
                 if self._dp is not None:
@@ -523,6 +533,13 @@ class GPT2LMHeadModel(GPT2PreTrainedModel):
                                           "(the label-sparse LM head computes all-position logits on demand)")
                     with torch.cuda.device(dev):
                         buf = eng.full_logits(*logits_src)
+                if pack is not None:
+                    # packed rows -> the padded [B, T, V] layout the caller expects (pad positions: zeros)
+                    n = int(pack.n_rows.item())
+                    dst = (pack.row_b[:n].long() * T + pack.row_t[:n].long())
+                    full = torch.zeros(B * T, V, dtype=torch.float32, device=buf.device)
+                    full[dst] = buf[:n, :V].to(torch.float32)
+                    return full.view(B, T, V)
                 return buf[:, :V].to(torch.float32).view(B, T, V)
 
             past_fn = _past_fn(out["kv_present"], B, eng.H, eng.nh, False) if use_cache else None

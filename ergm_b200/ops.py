@@ -155,12 +155,44 @@ def poll_err_flag(device):
     _err_pending[key] = (host, ev)
 
 
+class Pack:
+    """Packed variable-length batch: device-side row layout made by ergm_pack_plan from the per-sample
+    token counts.  All sizes are static (capacity B*T); the packed row count lives on the device (`n_rows`), so one
+    CUDA graph serves every batch.  `desc` is the ergm_pack the C entry points take."""
+
+    def __init__(self, B, T, device):
+        i32 = torch.int32
+        self.B, self.T, self.cap = B, T, B * T
+        self.cu = torch.zeros(B + 1, dtype=i32, device=device)
+        self.row_b = torch.zeros(self.cap, dtype=i32, device=device)
+        self.row_t = torch.zeros(self.cap, dtype=i32, device=device)
+        self.n_rows = torch.zeros(1, dtype=i32, device=device)
+        self.kv_lens = torch.zeros(B, dtype=i32, device=device)
+        self.desc = L.PackDesc(self.cu.data_ptr(), self.row_b.data_ptr(), self.row_t.data_ptr(), self.n_rows.data_ptr(),
+                               self.kv_lens.data_ptr())
+
+    def plan(self, lens):
+        """lens: device int32 [B] real tokens per sample (right-padded batch)."""
+        _call("ergm_pack_plan", lens.data_ptr(), self.B, self.T, self.cu.data_ptr(), self.row_b.data_ptr(),
+              self.row_t.data_ptr(), self.n_rows.data_ptr(), self.kv_lens.data_ptr(), self.cap)
+        return self
+
+
+def _pk(pack):
+    return ctypes.byref(pack.desc) if pack is not None else None
+
+
+def zero_rows_dyn(buf, count):
+    """Rows [count, roundup(count, 128)) of a 2-D buffer := 0 (operands of run-time-K GEMMs)."""
+    _call("ergm_zero_rows_dyn", buf.data_ptr(), buf.stride(0) * buf.element_size(), count.data_ptr(), buf.shape[0])
+
+
 def _pos_stride(pos_ids, T):
     return 0 if (pos_ids is None or pos_ids.numel() == T) else T
 
 
 def embed_fuse_fwd(ids, tts, pos_ids, wte, wpe, imgs, auds, out, *, past_len=0, past_lens=None, dropout_p=0.0, seed=0,
-                   offset=0):
+                   offset=0, pack=None):
     """pos_ids: None, [T] (shared by the batch) or [B, T] (per sample)."""
     B, T = ids.shape
     H = wte.shape[1]
@@ -168,7 +200,7 @@ def embed_fuse_fwd(ids, tts, pos_ids, wte, wpe, imgs, auds, out, *, past_len=0, 
           wte.data_ptr(), wpe.data_ptr(),
           _p(imgs), imgs.stride(0) if imgs is not None else 0, _p(auds), auds.stride(0) if auds is not None else 0,
           out.data_ptr(), B, T, H, past_len, wte.shape[0], wpe.shape[0], dropout_p, seed, offset,
-          err_flag(ids.device).data_ptr())
+          err_flag(ids.device).data_ptr(), _pk(pack))
 
 
 def gather_rows_bf16(ids, table, out):
@@ -185,28 +217,29 @@ def mm_pool_fwd(seq, pooled_f32, pooled_bf16, lens=None):
           pooled_bf16.stride(0) if pooled_bf16 is not None else 0)
 
 
-def embed_bwd(dh, ids, tts, pos_ids, dwte, dwpe, *, T, past_len=0, dimgs=None, dauds=None, dropout_p=0.0, seed=0, offset=0):
+def embed_bwd(dh, ids, tts, pos_ids, dwte, dwpe, *, T, past_len=0, dimgs=None, dauds=None, dropout_p=0.0, seed=0, offset=0,
+              pack=None):
     """dwte [vocab, H] / dwpe [n_pos, H] gradient tables: out-of-range indices are skipped and flagged."""
     rows, H = dh.shape
     _call("ergm_embed_bwd", dh.data_ptr(), _p(ids), _p(tts), _p(pos_ids), _pos_stride(pos_ids, T), _p(dwte), _p(dwpe), _p(dimgs), _p(dauds),
           rows, T, H, past_len, dwte.shape[0] if dwte is not None else 0, dwpe.shape[0] if dwpe is not None else 0,
-          dropout_p, seed, offset, err_flag(dh.device).data_ptr())
+          dropout_p, seed, offset, err_flag(dh.device).data_ptr(), _pk(pack))
 
 
-def ln_fwd(x, gamma, beta, y_bf16, y_f32, mean, rstd, eps, row_idx=None):
+def ln_fwd(x, gamma, beta, y_bf16, y_f32, mean, rstd, eps, row_idx=None, rows_dyn=None):
     rows, H = x.shape
     if row_idx is not None:
         rows = row_idx.numel()
     _call("ergm_ln_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _p(y_bf16), _p(y_f32), _p(mean), _p(rstd),
-          rows, H, eps, _p(row_idx))
+          rows, H, eps, _p(row_idx), _p(rows_dyn))
 
 
 def ln_bwd(dy, x, mean, rstd, gamma, dres_in, dx_out, dx_bf16, dgamma, dbeta, dbias_next=None, *, dropout_p=0.0,
-           seed=0, offset=0):
+           seed=0, offset=0, rows_dyn=None):
     rows, H = x.shape
     _call("ergm_ln_bwd", dy.data_ptr(), int(dy.dtype == torch.float32), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
           gamma.data_ptr(), _p(dres_in), _p(dx_out), _p(dx_bf16), dgamma.data_ptr(), dbeta.data_ptr(), _p(dbias_next),
-          rows, H, dropout_p, seed, offset)
+          rows, H, dropout_p, seed, offset, _p(rows_dyn))
 
 
 def colsum_bf16(src, out, *, rows=None, N=None, ld=None):
@@ -215,14 +248,15 @@ def colsum_bf16(src, out, *, rows=None, N=None, ld=None):
     _call("ergm_colsum_bf16", src.data_ptr(), src.stride(0) if ld is None else ld, rows, N, out.data_ptr())
 
 
-def gelu_bwd_colsum(dg, u, colsum, exact=False):
+def gelu_bwd_colsum(dg, u, colsum, exact=False, rows_dyn=None):
     rows, N = dg.shape
-    _call("ergm_gelu_bwd_colsum", dg.data_ptr(), u.data_ptr(), dg.stride(0), rows, N, _p(colsum), int(exact))
+    _call("ergm_gelu_bwd_colsum", dg.data_ptr(), u.data_ptr(), dg.stride(0), rows, N, _p(colsum), int(exact), _p(rows_dyn))
 
 
-def cast_f32_bf16_2d(src, dst, colsum=None):
+def cast_f32_bf16_2d(src, dst, colsum=None, rows_dyn=None):
     rows, N = src.shape
-    _call("ergm_cast_f32_bf16_2d", src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), rows, N, _p(colsum))
+    _call("ergm_cast_f32_bf16_2d", src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), rows, N, _p(colsum),
+          _p(rows_dyn))
 
 
 def cast_f32_bf16(src, dst):
@@ -230,19 +264,20 @@ def cast_f32_bf16(src, dst):
 
 
 def attn_fwd(q, k, v, out, lse, *, B, nh, Tq, Tk, q_col0=0, k_col0=0, v_col0=0, causal=True, causal_off=None,
-             kv_lens=None, dropout_p=0.0, seed=0, offset=0, out_f32=None):
-    """q/k/v: bf16 2-D matrices [B*T, ld] (may be the same tensor with different col0)."""
+             kv_lens=None, dropout_p=0.0, seed=0, offset=0, out_f32=None, pack=None, pack_kv=False):
+    """q/k/v: bf16 2-D matrices [B*T, ld] (may be the same tensor with different col0).  pack: queries / outputs are
+    packed rows (sample b at cu[b] ..); pack_kv: keys / values too (self attention)."""
     if causal_off is None:
         causal_off = Tk - Tq
     _call("ergm_attn_fwd", q.data_ptr(), q.stride(0), q_col0, k.data_ptr(), k.stride(0), k_col0, v.data_ptr(),
           v.stride(0), v_col0, out.data_ptr(), out.stride(0), _p(out_f32), _p(lse), _p(kv_lens), B, nh, Tq, Tk, 64,
           int(causal),
-          causal_off, dropout_p, seed, offset)
+          causal_off, dropout_p, seed, offset, _pk(pack), int(pack_kv))
 
 
 def attn_bwd(q, k, v, out, dout, lse, delta, dq_accum, dk, dv, *, B, nh, Tq, Tk, q_col0=0, k_col0=0, v_col0=0,
              dk_col0=0, dv_col0=0, causal=True, causal_off=None, kv_lens=None, dropout_p=0.0, seed=0, offset=0,
-             out_f32=None, dk_colsum=None, dv_colsum=None):
+             out_f32=None, dk_colsum=None, dv_colsum=None, pack=None, pack_kv=False):
     if causal_off is None:
         causal_off = Tk - Tq
     _call("ergm_attn_bwd", q.data_ptr(), q.stride(0), q_col0, k.data_ptr(), k.stride(0), k_col0, v.data_ptr(),
@@ -250,7 +285,7 @@ def attn_bwd(q, k, v, out, dout, lse, delta, dq_accum, dk, dv, *, B, nh, Tq, Tk,
           delta.data_ptr(), dq_accum.data_ptr(), dq_accum.stride(0), dk.data_ptr(), dk.stride(0), dk_col0,
           dv.data_ptr(), dv.stride(0), dv_col0, _p(dk_colsum), _p(dv_colsum), _p(kv_lens), B, nh, Tq, Tk, 64, int(causal),
           causal_off,
-          dropout_p, seed, offset)
+          dropout_p, seed, offset, _pk(pack), int(pack_kv))
 
 
 def ce_fwd(logits, labels, lse, row_loss, sums, *, T, V, hn=None, w=None, rows_dyn=None):
@@ -267,9 +302,9 @@ def ce_bwd(logits, labels, lse, scale, dlogits, *, T, V, rows_dyn=None):
           rows, T, V, lse.data_ptr(), scale.data_ptr(), dlogits.data_ptr(), dlogits.stride(0), _p(rows_dyn))
 
 
-def lm_rows_plan(labels, row_idx, labels_c, count, *, T):
+def lm_rows_plan(labels, row_idx, labels_c, count, *, T, pack=None):
     _call("ergm_lm_rows_plan", labels.data_ptr(), labels.numel(), T, row_idx.data_ptr(), labels_c.data_ptr(),
-          count.data_ptr())
+          count.data_ptr(), _pk(pack))
 
 
 def gather_rows_dyn(src, row_idx, count, dst):
@@ -281,17 +316,17 @@ def scatter_rows_dyn(src, row_idx, count, dst):
     _call("ergm_scatter_rows_dyn", src.data_ptr(), row_idx.data_ptr(), count.data_ptr(), dst.data_ptr(), src.shape[1])
 
 
-def emotion_head_fwd(x_final, mean, rstd, gamma, beta, w_emo, emo_labels, hlast, logits, dlogits, sums, *, B, T):
+def emotion_head_fwd(x_final, mean, rstd, gamma, beta, w_emo, emo_labels, hlast, logits, dlogits, sums, *, B, T, cu_rows=None):
     H = x_final.shape[1]
     _call("ergm_emotion_head_fwd", x_final.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
           beta.data_ptr(), w_emo.data_ptr(), _p(emo_labels), B, T, H, hlast.data_ptr(), logits.data_ptr(),
-          _p(dlogits), _p(sums), err_flag(x_final.device).data_ptr())
+          _p(dlogits), _p(sums), err_flag(x_final.device).data_ptr(), _p(cu_rows))
 
 
-def emotion_head_bwd(dlogits, hlast, w_emo, scale, dw_emo, dyf, *, B, T):
+def emotion_head_bwd(dlogits, hlast, w_emo, scale, dw_emo, dyf, *, B, T, cu_rows=None):
     H = hlast.shape[1]
     _call("ergm_emotion_head_bwd", dlogits.data_ptr(), hlast.data_ptr(), w_emo.data_ptr(), scale.data_ptr(), B, T, H,
-          _p(dw_emo), _p(dyf))
+          _p(dw_emo), _p(dyf), _p(cu_rows))
 
 
 def loss_finalize(sums, has_lm, has_emo, out):

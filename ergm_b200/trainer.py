@@ -17,7 +17,8 @@ import torch
 
 from . import ops
 
-_KEYS = ("input_ids", "token_type_ids", "labels", "emotion_labels", "caption_ids", "imgs", "auds")
+# seq_lens (int32 [B], real tokens of every right-padded sample): selects the packed variable-length path
+_KEYS = ("input_ids", "token_type_ids", "labels", "emotion_labels", "caption_ids", "imgs", "auds", "seq_lens")
 
 
 class GraphedTrainStep:
@@ -50,9 +51,13 @@ class GraphedTrainStep:
     def _device_step(self, b):
         eng, model = self.eng, self.model
         ops.reset_launch_count()
+        pack = None
+        if b.get("seq_lens") is not None:
+            Bq, Tq = b["input_ids"].shape
+            pack = eng.get_pack(Bq, Tq).plan(b["seq_lens"])   # one small kernel: part of the captured step
         out = eng.forward(b["input_ids"], b.get("token_type_ids"), b.get("labels"), b.get("emotion_labels"),
                           b.get("imgs"), b.get("auds"), b.get("caption_ids"), None, training=model.training,
-                          save=True, want_logits=False, logits_fp32=model.fp32_logits)
+                          save=True, want_logits=False, logits_fp32=model.fp32_logits, pack=pack)
         if self.dp is not None:
             self.dp.reduce_loss_sums(out["loss_sums"])
         losses = eng.finalize_loss(out)
@@ -88,7 +93,7 @@ class GraphedTrainStep:
                 continue
             if k == "imgs" and v.dim() == 3 and not self.seq_features:
                 v = v[:, 0]
-            dt = torch.float32 if k in ("imgs", "auds") else torch.int64
+            dt = torch.float32 if k in ("imgs", "auds") else (torch.int32 if k == "seq_lens" else torch.int64)
             st[k] = torch.empty(tuple(v.shape), dtype=dt, device=self.eng.device)
             nbytes += st[k].numel() * st[k].element_size()
         self.static[key] = st

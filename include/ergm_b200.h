@@ -92,6 +92,27 @@ int ergm_gemm_bf16(const ergm_gemm_args* args, void* stream);
 
 
 /* ------------------------------------------------------------------------ */
+/* Packed variable-length batches.  The reference's collate (custom_dataset.py:102-132) right-pads
+ * every sample to the batch maximum and model.py computes every pad position.  With an ergm_pack the path works
+ * on the concatenation of the samples' real rows: sample b contributes its lens[b] real positions plus, when it is
+ * padded, ONE row for position T-1 (the emotion head reads the last position, model.py:700; under the right-padded
+ * attention mask that position attends to the sample's real tokens only).  All members are DEVICE int32 arrays
+ * written by ergm_pack_plan; the row count is a run-time value on the device (one captured graph serves every
+ * batch): row kernels take it as `rows_dyn`, GEMMs as ergm_gemm_args.dyn_count.  Entry points that take
+ * `const ergm_pack* pack` accept NULL (padded [B, T] layout, the reference's).                               */
+typedef struct ergm_pack {
+  const int32_t* cu_rows;  /* [B + 1] first packed row of every sample */
+  const int32_t* row_b;    /* [B * T] sample of a packed row */
+  const int32_t* row_t;    /* [B * T] position of a packed row (column of the padded layout) */
+  const int32_t* n_rows;   /* [1] packed rows in this batch */
+  const int32_t* kv_lens;  /* [B] attendable keys per sample = its real tokens */
+} ergm_pack;
+int ergm_pack_plan(const int* lens, int B, int T, int* cu_rows, int* row_b, int* row_t, int* n_rows, int* kv_lens,
+                   int cap /* >= B * T: capacity of row_b / row_t */, void* stream);
+/* rows [*count, roundup(*count, 128)) of buf[cap, row_bytes] := 0: operands of run-time-K (wgrad) GEMMs */
+int ergm_zero_rows_dyn(void* buf, int64_t row_bytes, const int* count, int cap, void* stream);
+
+/* ------------------------------------------------------------------------ */
 /* Embedding + multimodal fusion (model.py:458-507):                          */
 /*   h[b,t] = ((wte[id] (+imgs[b] if t==0) (+auds[b] if t==1)) + wpe[pos]) + wte[type]
  * then embd dropout.  pos = past_len + t unless position_ids is given, in
@@ -105,7 +126,7 @@ int ergm_embed_fuse_fwd(const int64_t* ids, const int64_t* token_type_ids,
                         const float* imgs, int64_t ld_img, const float* auds, int64_t ld_aud,
                         float* out, int B, int T, int H, int past_len, int vocab, int n_pos,
                         float dropout_p, uint64_t seed, uint64_t offset, int* err_flag,
-                        void* stream);
+                        const ergm_pack* pack /* nullable: out row r <- (row_b[r], row_t[r]) */, void* stream);
 /* A3 extension (north_star "projects per-utterance audio and keyframe-visual   */
 /* feature sequences into the hidden space"; the reference pools offline,        */
 /* feature_extraction.py:63,69, and has no projection - SURVEY Appendix A D7):   */
@@ -126,7 +147,7 @@ int ergm_gather_rows_bf16(const int64_t* ids, const float* table, void* out_bf16
 int ergm_embed_bwd(const float* dh, const int64_t* ids, const int64_t* token_type_ids,
                    const int64_t* position_ids, int64_t pos_stride_b, float* dwte, float* dwpe, float* dimgs,
                    float* dauds, int rows, int T, int H, int past_len, int vocab, int n_pos, float dropout_p,
-                   uint64_t seed, uint64_t offset, int* err_flag, void* stream);
+                   uint64_t seed, uint64_t offset, int* err_flag, const ergm_pack* pack, void* stream);
 
 /* ------------------------------------------------------------------------ */
 /* LayerNorm (model.py:298,318,332,578; eps inside the sqrt, biased variance) */
@@ -134,22 +155,22 @@ int ergm_embed_bwd(const float* dh, const int64_t* ids, const int64_t* token_typ
 int ergm_ln_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16,
                 float* y_f32, float* mean, float* rstd, int rows, int H, float eps,
                 const int* row_idx /* nullable: output row r normalises x[row_idx[r]] */,
-                void* stream);
+                const int* rows_dyn /* nullable device int: run-time row count (packed batch) */, void* stream);
 /* bwd fused with the residual-gradient add: dx_out = dres_in + LN'(dy);      */
 /* dx_bf16 = bf16(dropout_mask(dx_out)) feeds the next dgrad/wgrad GEMMs;     */
 /* dgamma/dbeta/dbias_next are accumulated (+=).                              */
 int ergm_ln_bwd(const void* dy, int dy_is_f32, const float* x, const float* mean,
                 const float* rstd, const float* gamma, const float* dres_in, float* dx_out,
                 void* dx_bf16, float* dgamma, float* dbeta, float* dbias_next, int rows, int H,
-                float dropout_p, uint64_t seed, uint64_t offset, void* stream);
+                float dropout_p, uint64_t seed, uint64_t offset, const int* rows_dyn /* nullable */, void* stream);
 /* out[N] += column sums of a bf16 [rows, N] matrix (Conv1D bias gradients)   */
 int ergm_colsum_bf16(const void* src, int64_t ld, int rows, int N, float* out, void* stream);
 /* MLP backward through gelu_new (model.py:264): dg (bf16 [rows, ld]) is overwritten with
  * dg * gelu_new'(u); colsum[N] += column sums of the result (c_fc bias gradient).   */
 int ergm_gelu_bwd_colsum(void* dg_bf16, const void* u_bf16, int64_t ld, int rows, int N, float* colsum,
-                         int exact, void* stream);
+                         int exact, const int* rows_dyn /* nullable */, void* stream);
 int ergm_cast_f32_bf16_2d(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int rows,
-                          int N, float* colsum, void* stream);
+                          int N, float* colsum, const int* rows_dyn /* nullable */, void* stream);
 int ergm_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------ */
@@ -164,6 +185,8 @@ int ergm_attn_fwd(const void* q, int64_t ld_q, int q_col0, const void* k, int64_
                   float* out_f32 /* nullable [B*Tq, nh*64]: un-rounded copy for backward */,
                   float* lse, const int* kv_lens, int B, int nh, int Tq, int Tk, int head_dim,
                   int causal, int causal_off, float dropout_p, uint64_t seed, uint64_t offset,
+                  const ergm_pack* pack /* nullable: q / out rows of sample b start at cu_rows[b] (capacity B*Tq) */,
+                  int pack_kv /* 1: k / v are packed the same way and kv_lens = pack->kv_lens (self attention) */,
                   void* stream);
 
 /* Backward of ergm_attn_fwd: recomputes P from lse; dq_accum (fp32, pre-zeroed,
@@ -178,7 +201,7 @@ int ergm_attn_bwd(const void* q, int64_t ld_q, int q_col0, const void* k, int64_
                   float* dq_accum, int64_t ld_dq, void* dk, int64_t ld_dk, int dk_col0, void* dv,
                   int64_t ld_dv, int dv_col0, float* dk_colsum, float* dv_colsum, const int* kv_lens, int B, int nh, int Tq, int Tk,
                   int head_dim, int causal, int causal_off, float dropout_p, uint64_t seed,
-                  uint64_t offset, void* stream);
+                  uint64_t offset, const ergm_pack* pack, int pack_kv, void* stream);
 
 /* ------------------------------------------------------------------------ */
 /* Token cross-entropy over LM-head logits with the reference's shift and     */
@@ -200,7 +223,7 @@ int ergm_ce_bwd(const void* logits, int logits_is_f32, int64_t ldl, const int64_
 /* plan: ordered compaction of the rows whose shifted label is not -100 -> row_idx[i] (int32 source row),
  * labels_c[i] (its target), *count; entries up to the next multiple of 128 are padded (-1 / -100).  */
 int ergm_lm_rows_plan(const int64_t* labels, int rows, int T, int* row_idx, int64_t* labels_c, int* count,
-                      void* stream);
+                      const ergm_pack* pack /* nullable: rows are packed rows, labels stay [B, T] */, void* stream);
 /* dst[i] = src[row_idx[i]] (bf16 [.., H]) for i < *count, zero rows up to the next multiple of 128 */
 int ergm_gather_rows_dyn(const void* src_bf16, const int* row_idx, const int* count, void* dst_bf16, int H,
                          int cap, void* stream);
@@ -212,10 +235,12 @@ int ergm_scatter_rows_dyn(const float* src, const int* row_idx, const int* count
 int ergm_emotion_head_fwd(const float* x_final, const float* mean, const float* rstd,
                           const float* gamma, const float* beta, const float* w_emo,
                           const int64_t* emotion_labels, int B, int T, int H, float* hlast,
-                          float* logits, float* dlogits, float* sums, int* err_flag, void* stream);
+                          float* logits, float* dlogits, float* sums, int* err_flag,
+                          const int* cu_rows /* nullable: packed batch, sample b's last row is cu_rows[b+1]-1 */,
+                          void* stream);
 int ergm_emotion_head_bwd(const float* dlogits, const float* hlast, const float* w_emo,
                           const float* scale_ptr, int B, int T, int H, float* dw_emo, float* dyf,
-                          void* stream);
+                          const int* cu_rows /* nullable */, void* stream);
 /* out = [loss, lm_loss, emo_loss, 1/lm_valid, 1/emo_count] (model.py:713)    */
 int ergm_loss_finalize(const float* sums, int has_lm, int has_emotion, float* out, void* stream);
 int ergm_scalar_mul(const float* a, const float* b, float* dst, void* stream);

@@ -62,8 +62,10 @@ def test_argument_errors_without_gpu(lib):
     from ergm_b200 import _lib
     a = _lib.GemmArgs()
     assert lib.ergm_gemm_bf16(ctypes.byref(a), None) == -1  # null operands -> ERGM_ERR_ARG, nothing launched
-    assert lib.ergm_ln_fwd(None, None, None, None, None, None, None, 4, 128, 1e-5, None, None) == -1
-    assert lib.ergm_attn_fwd(1, 8, 0, 1, 8, 0, 1, 8, 0, 1, 8, None, None, None, 1, 1, 8, 8, 32, 1, 0, 0.0, 0, 0, None) == -2
+    assert lib.ergm_ln_fwd(None, None, None, None, None, None, None, 4, 128, 1e-5, None, None, None) == -1
+    assert lib.ergm_attn_fwd(1, 8, 0, 1, 8, 0, 1, 8, 0, 1, 8, None, None, None, 1, 1, 8, 8, 32, 1, 0, 0.0, 0, 0, None, 0, None) == -2
+    assert lib.ergm_pack_plan(None, 4, 16, None, None, None, None, None, 64, None) == -1
+    assert lib.ergm_zero_rows_dyn(None, 16, None, 4, None) == -1
     # decode-side entry points: argument errors are detected before anything touches a device
     assert lib.ergm_dec_pack_weight(None, 768, 768, 768, 0, None, None, None, None, None, None) == -1
     assert lib.ergm_dec_gemm(None, None, 768, 1e-5, None, 768, 768, None, None, 768, 0, 0, 64, None) == -1
