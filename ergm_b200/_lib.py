@@ -30,7 +30,7 @@ class GemmArgs(ctypes.Structure):
         ("block_n", ctypes.c_int32),
         ("dropout_p", ctypes.c_float),
         ("seed", ctypes.c_uint64), ("offset", ctypes.c_uint64),
-        ("dyn_count", ctypes.c_void_p), ("dyn_dim", ctypes.c_int32),
+        ("dyn_count", ctypes.c_void_p), ("dyn_dim", ctypes.c_int32), ("dyn_hint", ctypes.c_int32),
     ]
 
 

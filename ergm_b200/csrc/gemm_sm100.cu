@@ -196,6 +196,7 @@ ERGM_DEVINL void epilogue_chunk(const GemmParams& p, const EpiFlags& ep, int row
                  : "memory");
   }
   __syncwarp();
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);  // GELU' mode with p.colsum: column sums of the stored (bf16) values
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int r = 4 * it + rsub;
@@ -243,9 +244,26 @@ ERGM_DEVINL void epilogue_chunk(const GemmParams& p, const EpiFlags& ep, int row
       else
         *reinterpret_cast<float4*>(dp) = x;
     } else {
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.d) + off) =
-          make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+      const uint2 pk = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.d) + off) = pk;
+      if ((EC == EC_GELU_GRAD) && p.colsum) {
+        const float2 r0 = unpack_bf16x2(pk.x), r1 = unpack_bf16x2(pk.y);
+        cs.x += r0.x; cs.y += r0.y; cs.z += r1.x; cs.w += r1.y;
+      }
     }
+  }
+  if ((EC == EC_GELU_GRAD) && p.colsum && ep.do_gelu_grad) {
+    // boundary slab of a run-time-M problem (packed batch): the lean epilogue only runs on whole 32-row slabs, the
+    // rows below M of this one still belong to the bias gradient.  Warp-uniform branch (p.colsum, flags).
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+      cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+    }
+    if (lane < 8 && col_full)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.colsum + col), "f"(cs.x), "f"(cs.y), "f"(cs.z),
+                   "f"(cs.w)
+                   : "memory");
   }
 }
 
@@ -861,6 +879,31 @@ extern "C" int ergm_gemm_bf16(const ergm_gemm_args* a, void* stream) {
   if (a->dyn_count && a->dyn_dim == 2 && !(a->epilogue & ERGM_EPI_ATOMIC)) return ERGM_ERR_ARG;  // K = 0 must write nothing
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   int bn = a->block_n;
+  if (bn == 0 && a->dyn_count && a->dyn_dim == 1 && a->dyn_hint > 0 && a->dyn_hint < a->M && a->N >= 256) {
+    // Run-time M (packed batch) with a known typical row count: choose the tile by a wave-quantisation cost model on
+    // the rows that will really exist, cost = waves x (per-SM tile area) x (K + epilogue-equivalent) / speed.  The
+    // static-M rules below were measured at M = 8192 and e.g. send K >= 1536 to 256x256 pair tiles whatever the tile
+    // count - at 6156 rows that is 75 tiles on 74 clusters: two waves.
+    const long Mh = a->dyn_hint;
+    const int sk = a->split_k < 1 ? 1 : a->split_k;
+    const int nc = num_sms() / 2, ns = num_sms();
+    const double kw = (double)a->K + 384.0;            // per-element epilogue cost ~ a 384-deep mainloop (r1_gemm_epilogue.md)
+    auto cost = [&](long tiles, int slots, double area_per_sm, double speed) {
+      const long waves = (tiles + slots - 1) / slots;
+      return (double)waves * area_per_sm * kw / speed;
+    };
+    double best = cost(((Mh + 255) / 256) * ((a->N + 255) / 256) * sk, nc, 128.0 * 256.0, a->K >= 1536 ? 1.12 : 1.0);
+    bn = 2256;
+    const long mt = (Mh + BM - 1) / BM;
+    const double c256 = cost(mt * ((a->N + 255) / 256) * sk, ns, 128.0 * 256.0, 1.0);
+    if (c256 < best) { best = c256; bn = 256; }
+    if (a->N % 192 == 0) {
+      const double c192 = cost(mt * (a->N / 192) * sk, ns, 128.0 * 192.0, 0.97);
+      if (c192 < best) { best = c192; bn = 192; }
+    }
+    const double c128 = cost(mt * ((a->N + 127) / 128) * sk, ns, 128.0 * 128.0, 0.92);
+    if (c128 < best) { best = c128; bn = 128; }
+  }
   if (bn == 0 && a->M >= 512 && a->N >= 256) {
     // Measured on the model's shapes (profiles/r1_gemm_epilogue.md): the CTA-pair kernel with 256x256 tiles
     // wins whenever its tiles fill the 74 clusters reasonably or the mainloop is long (K >= 1536: the

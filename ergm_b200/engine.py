@@ -235,6 +235,7 @@ class Engine:
                 raise ValueError("pack was planned for a [%d, %d] batch, got [%d, %d]" % (pack.B, pack.T, B, T))
             dyn = pack.n_rows
             kv_lens = None   # the pack carries the per-sample key counts
+            ops.DYN_HINT = int(getattr(pack, "rows_hint", 0))   # typical row count: steers the GEMM tile shapes
         fuse = imgs is not None and past_len == 0  # boundary decision (3): fusion on the prefill only
         if imgs is not None and auds is None:
             raise ValueError("imgs given without auds (model.py:495-498 uses both)")
@@ -340,6 +341,8 @@ class Engine:
             x = x3
         if not heads:
             return dict(x_final=x, kv_present=kv_present, B=B, T=T)
+        if pack is None:
+            ops.DYN_HINT = 0
         # ---- final LN, heads, losses (model.py:578, 698-721) ----
         hn = ws.get("hn", (M, H), bf16)
         meanf = ws.get("meanf", (M,), f32)
@@ -382,8 +385,10 @@ class Engine:
             wte_b = self.pb("transformer.wte.weight")
             ops.lm_rows_plan(labels, sp["row_idx"], sp["labels_c"], sp["count"], T=T, pack=pack)
             ops.gather_rows_dyn(hn, sp["row_idx"], sp["count"], sp["hn_c"])
+            hint, ops.DYN_HINT = ops.DYN_HINT, 0   # (the packed-batch row hint does not describe the scored-row count)
             ops.gemm(sp["hn_c"], wte_b, sp["logits_c"], M=M, N=V, K=H, a_major=K_MAJOR, b_major=K_MAJOR,
                      dyn_m=sp["count"])
+            ops.DYN_HINT = hint
             lse = ws.get("ce_lse", (M,), f32)
             row_loss = ws.get("ce_row_loss", (M,), f32)
             ops.ce_fwd(sp["logits_c"], sp["labels_c"], lse, row_loss, sums, T=0, V=V, hn=sp["hn_c"], w=wte_b,
@@ -596,6 +601,7 @@ class Engine:
         M, Mc = B * T, B * Tc
         pack = sv.get("pack")
         dyn = pack.n_rows if pack is not None else None
+        ops.DYN_HINT = int(getattr(pack, "rows_hint", 0)) if pack is not None else 0
         ws = self.ws_train
         f32, bf16 = torch.float32, torch.bfloat16
         seed, site0 = sv["seed"], sv["site0"]
@@ -629,7 +635,7 @@ class Engine:
             dhn_c.zero_()
             # d hn_c = dlogits_c @ wte: few row tiles, very long K (= V): the kernel splits K itself to fill the GPU
             ops.gemm(dlogits_c, wte_b, dhn_c, M=M, N=H, K=V, a_major=K_MAJOR, b_major=MN_MAJOR, epilogue=L.EPI_ATOMIC,
-                     block_n=2256, dyn_m=cnt)
+                     block_n=2256, dyn_m=cnt, dyn_hint=-1)
             dhn.zero_()
             ops.scatter_rows_dyn(dhn_c, sp["row_idx"], cnt, dhn)
             # d wte += dlogits_c^T @ hn_c (reduction over the run-time row count)
@@ -683,12 +689,12 @@ class Engine:
             has_x = "a2" in r
             # ---- MLP backward ----
             self._wgrad_gemm(r["g"], dxb, self.pg(pfx + "mlp.c_proj.weight"), I, H, M, dyn)
-            if M % 256 == 0 and I % 256 == 0 and pack is None:
-                # GELU' and the c_fc bias gradient ride in the dgrad epilogue (lean FM_GELU_GRAD mode)
+            if M % 256 == 0 and I % 256 == 0:
+                # GELU' and the c_fc bias gradient ride in the dgrad epilogue (lean FM_GELU_GRAD mode; the boundary
+                # slab of a packed batch's run-time row count goes through the generic epilogue, same sums)
                 self._dgrad_gemm(dxb, self.pb(pfx + "mlp.c_proj.weight"), dI, M, I, H, gelu_grad_of=r["u"],
-                                 colsum=self.pg(pfx + "mlp.c_fc.bias"), block_n=2256)
+                                 colsum=self.pg(pfx + "mlp.c_fc.bias"), block_n=2256, dyn_m=dyn)
             else:
-                # (packed batches: the fused epilogue's column sums only exist on whole 32-row slabs)
                 self._dgrad_gemm(dxb, self.pb(pfx + "mlp.c_proj.weight"), dI, M, I, H, dyn_m=dyn)
                 ops.gelu_bwd_colsum(dI, r["u"], self.pg(pfx + "mlp.c_fc.bias"), rows_dyn=dyn)
             self._wgrad_gemm(r["a3"], dI, self.pg(pfx + "mlp.c_fc.weight"), H, I, M, dyn)

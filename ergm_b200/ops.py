@@ -22,7 +22,7 @@ def _ptr(t):
 
 def gemm(a, b, d, *, M, N, K, a_major=L.ERGM_MAJOR_K, b_major=L.ERGM_MAJOR_MN, lda=None, ldb=None,
          ldd=None, bias=None, residual=None, ldr=None, preact=None, gelu_grad_of=None, epilogue=0, split_k=1,
-         block_n=0, dropout_p=0.0, seed=0, offset=0, colsum=None, dyn_m=None, dyn_k=None):
+         block_n=0, dropout_p=0.0, seed=0, offset=0, colsum=None, dyn_m=None, dyn_k=None, dyn_hint=0):
     """D[M,N] = epilogue(A * B).  a/b bf16, d bf16 or fp32.  See include/ergm_b200.h."""
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     args = L.GemmArgs()
@@ -58,6 +58,7 @@ def gemm(a, b, d, *, M, N, K, a_major=L.ERGM_MAJOR_K, b_major=L.ERGM_MAJOR_MN, l
         dyn = dyn_m if dyn_m is not None else dyn_k
         assert dyn.dtype == torch.int32
         args.dyn_count, args.dyn_dim = dyn.data_ptr(), 1 if dyn_m is not None else 2
+        args.dyn_hint = int(dyn_hint or DYN_HINT)
     global _launch_count
     _launch_count += 1
     if PROFILE is not None:
@@ -75,6 +76,7 @@ def gemm(a, b, d, *, M, N, K, a_major=L.ERGM_MAJOR_K, b_major=L.ERGM_MAJOR_MN, l
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim)
 _LAUNCHES = {"ergm_attn_bwd": 2, "ergm_decode_layers": 1, "ergm_decode_stack_pack": 4}
 _launch_count = 0
+DYN_HINT = 0    # expected run-time row count of the packed batch being processed (engine sets it; steers tile shapes)
 PROFILE = None  # set to a list to collect (name, info, start_event, end_event) per call
 
 

@@ -42,6 +42,7 @@ class GraphedTrainStep:
         self.rng_step = torch.zeros(1, dtype=torch.int64, device=eng.device)
         eng.set_rng_step_tensor(self.rng_step)
         self.one = torch.ones(1, dtype=torch.float32, device=eng.device)
+        self.rows_hint = 0   # typical packed row count (from the first packed batch): steers GEMM tile shapes only
         self.loss_host = torch.zeros(5, dtype=torch.float32).pin_memory()
         self.err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.h2d_bytes = 0
@@ -55,6 +56,7 @@ class GraphedTrainStep:
         if b.get("seq_lens") is not None:
             Bq, Tq = b["input_ids"].shape
             pack = eng.get_pack(Bq, Tq).plan(b["seq_lens"])   # one small kernel: part of the captured step
+            pack.rows_hint = self.rows_hint
         out = eng.forward(b["input_ids"], b.get("token_type_ids"), b.get("labels"), b.get("emotion_labels"),
                           b.get("imgs"), b.get("auds"), b.get("caption_ids"), None, training=model.training,
                           save=True, want_logits=False, logits_fp32=model.fp32_logits, pack=pack)
@@ -157,6 +159,10 @@ class GraphedTrainStep:
             pass
 
     def __call__(self, batch):
+        if batch.get("seq_lens") is not None and not self.rows_hint:
+            lens = batch["seq_lens"].to(torch.int64)
+            T = batch["input_ids"].shape[1]
+            self.rows_hint = int(lens.clamp(max=T).sum() + (lens < T).sum())
         key, st = self.copy_in(batch)
         self.run_device(key, st)
         self.loss_host.copy_(self.losses, non_blocking=True)

@@ -86,6 +86,9 @@ typedef struct ergm_gemm_args {
   int32_t dyn_dim;     /* 1: dyn_count bounds M (rows beyond it are not stored; with ERGM_EPI_ATOMIC the kernel picks
                           the K split itself); 2: dyn_count bounds K (ERGM_EPI_ATOMIC only; operand rows in
                           [count, roundup(count, 128)) must be zero) */
+  int32_t dyn_hint;    /* expected value of *dyn_count (0 = unknown).  Only steers the host-side tile-shape choice
+                          (wave quantisation is decided by the rows that really exist, not by the capacity); any
+                          value is correct */
 } ergm_gemm_args;
 
 int ergm_gemm_bf16(const ergm_gemm_args* args, void* stream);
