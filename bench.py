@@ -442,11 +442,13 @@ def main():
     model_tf = value / world * fl_tok / 1e12
 
     gen = None
-    if not args.no_gen and not medium:
+    if not args.no_gen:
         # batched inference sharded per GPU: every rank decodes its own 64 requests with its own paged-KV pool
-        # (no communication); whole-job tokens/s = world x batch x new / max-over-ranks time
+        # (no communication); whole-job tokens/s = world x batch x new / max-over-ranks time.  Config 5 (medium): long
+        # context - ragged prompts 256..512 (the model's imgs / auds here are feature SEQUENCES: generation runs
+        # without fusion, like main.py's sampling loop, which passes neither)
         try:
-            gen = bench_generation(model, device)
+            gen = bench_generation(model, device, prompt=512 if medium else 128)
             if world > 1:
                 modes = ("nocaption", "caption", "nocaption_topk50")
                 steps_k = ("decode_step", "decode_step_caption")
