@@ -13,7 +13,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 WORKER = r'''
-import os, sys, torch, torch.distributed as dist
+import os, sys, faulthandler, torch, torch.distributed as dist
+faulthandler.dump_traceback_later(150, exit=True)   # a deadlocked collective must not eat the GPU lease: dump the stacks and die
 sys.path.insert(0, %(root)r)
 from transformers import GPT2Config
 from ergm_b200.model import GPT2LMHeadModel
@@ -107,6 +108,13 @@ def test_dp_step_equals_single_gpu_step(world, proj, grad, tmp_path):
     script.write_text(WORKER % {"root": ROOT, "proj": proj, "grad": grad})
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    print(r.stdout[-3000:], r.stderr[-3000:])
-    assert r.returncode == 0
+    p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True)
+    try:
+        out, err = p.communicate(timeout=240)
+    except subprocess.TimeoutExpired:
+        os.killpg(p.pid, 9)
+        out, err = p.communicate()
+        print(out[-3000:], err[-6000:])
+        raise AssertionError("data-parallel worker timed out (see the stack dumps above)")
+    print(out[-3000:], err[-3000:])
+    assert p.returncode == 0
