@@ -61,13 +61,23 @@ ok = abs(o.loss.item() - ref_loss) < 1e-5
 ok_oracle = abs(o.loss.item() - oo["loss"].item()) < 2.5e-3
 worst = 0.0
 worst_oracle = 0.0
+worst_name = ""
+oracle_ok = True
 for n, p in m.named_parameters():
     r = ((p.grad - ref_grads[n]).norm() / (ref_grads[n].norm() + 1e-20)).item()
     worst = max(worst, r)
     go = sdo[n].grad.cuda()
-    worst_oracle = max(worst_oracle, ((p.grad - go).norm() / (go.norm() + 1e-20)).item())
+    ro = ((p.grad - go).norm() / (go.norm() + 1e-20)).item()
+    if ro > worst_oracle:
+        worst_oracle, worst_name = ro, n
+    # bias-heavy fixture: the cross-attention tensors carry more bf16 rounding noise (tests/test_model_gpu.py)
+    oracle_ok = oracle_ok and ro < (8e-2 if ("crossattention" in n or "ln_cross_attn" in n) else 4e-2)
 FusedAdamW(m, lr=1e-3).step()
-wdiff = max((p.detach() - q.detach()).abs().max().item() for p, q in zip(m.parameters(), ref.parameters()))
+# post-step weights: AdamW moves every element by ~lr * sign(g); an element whose gradient is below the fp32 rounding
+# noise of the two summation orders (2 partial sums + all-reduce vs one sum) may move the other way: at most 2 lr, and rare
+dw = torch.cat([(p.detach() - q.detach()).abs().reshape(-1) for p, q in zip(m.parameters(), ref.parameters())])
+wdiff = dw.max().item()
+wfrac = (dw > 1e-5).float().mean().item()
 # graph-captured DP train step (the bench path) runs and agrees with itself across ranks
 m2 = build(); dp2 = DataParallel(m2, bucket_mb=0.25, grad_dtype=GRAD)
 step = GraphedTrainStep(m2, FusedAdamW(m2, lr=1e-3), dp=dp2)
@@ -79,14 +89,16 @@ w0 = m2.transformer.h[1].mlp.c_fc.weight.detach().clone(); w1 = w0.clone(); dist
 # replicas must stay bit-identical in EVERY parameter (incl. the late-gradient projections) after graphed steps
 flat = m2.engine.store.flat.detach().clone(); flat0 = flat.clone(); dist.broadcast(flat0, 0)
 allsync = bool(torch.equal(flat, flat0))
-print("RANK%%d loss_ok=%%s oracle_loss_ok=%%s worst_grad_rel=%%.2e worst_grad_rel_vs_oracle=%%.2e wdiff=%%.2e graph_losses=%%s same=%%s wsync=%%s allsync=%%s" %% (rank, ok, ok_oracle, worst, worst_oracle, wdiff, ["%%.4f" %% x for x in losses], same, bool(torch.equal(w0, w1)), allsync), flush=True)
-# fp32 buckets: the N-rank step IS the single-GPU step (fp32 rounding); bf16 buckets: gradients carry one bf16 rounding
-# (2^-9 relative) and AdamW at lr 1e-3 turns a flipped noise-level gradient sign into at most ~2 lr of weight difference
-gtol, wtol = (2e-3, 1e-5) if GRAD == "fp32" else (1.5e-2, 2.5e-3)
-assert ok and ok_oracle and worst < gtol and worst_oracle < 6e-2 and wdiff < wtol and same and torch.equal(w0, w1) and allsync and losses[2] < losses[0]
-step.close()
+print("RANK%%d loss_ok=%%s oracle_loss_ok=%%s worst_grad_rel=%%.2e worst_grad_rel_vs_oracle=%%.2e (%%s) wdiff=%%.2e wfrac=%%.2e graph_losses=%%s same=%%s wsync=%%s allsync=%%s" %% (rank, ok, ok_oracle, worst, worst_oracle, worst_name, wdiff, wfrac, ["%%.4f" %% x for x in losses], same, bool(torch.equal(w0, w1)), allsync), flush=True)
+# fp32 buckets: the N-rank gradients are the single-GPU gradients up to the summation order; bf16 buckets: they carry one
+# bf16 rounding (2^-9 relative), so more noise-level elements change sign under AdamW
+gtol, ftol = (2e-3, 2e-3) if GRAD == "fp32" else (1.5e-2, 5e-2)
+good = (ok and ok_oracle and worst < gtol and oracle_ok and wdiff < 2.5e-3 and wfrac < ftol and same
+        and torch.equal(w0, w1) and allsync and losses[2] < losses[0])
+step.close()          # always tear down (a live graph pins NCCL resources and would hang the interpreter exit)
 dist.barrier()
 dist.destroy_process_group()
+sys.exit(0 if good else 1)
 '''
 
 
