@@ -93,6 +93,8 @@ print("RANK%%d loss_ok=%%s oracle_loss_ok=%%s worst_grad_rel=%%.2e worst_grad_re
 # fp32 buckets: the N-rank gradients are the single-GPU gradients up to the summation order; bf16 buckets: they carry one
 # bf16 rounding (2^-9 relative), so more noise-level elements change sign under AdamW
 gtol, ftol = (2e-3, 2e-3) if GRAD == "fp32" else (1.5e-2, 5e-2)
+if PROJ:
+    gtol = max(gtol, 6e-3)   # the projection weight gradient is a K = B (4 vs 8 samples) bf16 GEMM: one bf16 rounding of noise
 good = (ok and ok_oracle and worst < gtol and oracle_ok and wdiff < 2.5e-3 and wfrac < ftol and same
         and torch.equal(w0, w1) and allsync and losses[2] < losses[0])
 step.close()          # always tear down (a live graph pins NCCL resources and would hang the interpreter exit)
