@@ -19,18 +19,67 @@ from .engine import K_MAJOR
 PAGE = 16
 
 
+class KVPageAllocator:
+    """Page pool of the self-attention K/V cache of one engine: per layer one tensor [pages][k|v][head][16 tokens][64]
+    (bf16), a host-side free list, pages handed out page-index-major (page j of every sequence of a batch before
+    page j+1: the order in which sequences that grow together claim them), so a sequence's pages are NOT
+    contiguous and the kernels' block-table indirection is what finds them.  The pool only grows; pages of a
+    finished batch go back on the free list (most recently freed first)."""
+
+    def __init__(self, eng):
+        self.eng = eng
+        self.pools = None
+        self.n_pages = 0
+        self.free = []
+
+    def _grow(self, need):
+        """Not enough free pages: first the cached (idle) generation states give theirs back; if that is still not
+        enough a larger pool replaces this one.  States that are still in use (handed out with return_state) keep
+        the old tensors alive and go on working in them; their page ids stay reserved in the new pool."""
+        eng = self.eng
+        for _, st in eng.__dict__.get("_gen_states", []):
+            st.graph = None
+            st.release()
+        eng.__dict__["_gen_states"] = []
+        if len(self.free) >= need:
+            return
+        new_total = self.n_pages + need - len(self.free)
+        self.pools = [torch.empty(new_total, 2, eng.nh, PAGE, 64, dtype=torch.bfloat16, device=eng.device)
+                      for _ in range(eng.L)]   # never read before written: every slot < seq_len was stored first
+        self.free = list(range(new_total - 1, self.n_pages - 1, -1)) + self.free
+        self.n_pages = new_total
+
+    def alloc_table(self, B, pages_per_seq):
+        need = B * pages_per_seq
+        if len(self.free) < need:
+            self._grow(need)
+        ids = [self.free.pop() for _ in range(need)]
+        table = torch.tensor(ids, dtype=torch.int32).view(pages_per_seq, B).t().contiguous()   # page j of all sequences first
+        return table.to(self.eng.device), ids
+
+    def release(self, ids):
+        self.free.extend(reversed(ids))
+
+
+def page_allocator(eng):
+    a = eng.__dict__.get("_kv_pages")
+    if a is None:
+        a = eng.__dict__["_kv_pages"] = KVPageAllocator(eng)
+    return a
+
+
 class GenState:
-    """Device state of one generation batch: paged K/V pool + block table per layer, cached
-    cross-attention K/V, per-sequence lengths / finished flags, output ids."""
+    """Device state of one generation batch: its pages of the engine's K/V page pool + block table, cached
+    cross-attention K/V, per-sequence lengths / finished flags, output ids, and the captured decode graph."""
 
     def __init__(self, eng, B, max_ctx, Tc, max_new):
         dev = eng.device
         H, nh, Lyr = eng.H, eng.nh, eng.L
         self.B, self.max_ctx, self.Tc, self.max_new = B, max_ctx, Tc, max_new
         self.pages_per_seq = (max_ctx + PAGE - 1) // PAGE
-        n_pages = B * self.pages_per_seq
-        self.pool = [torch.zeros(n_pages, 2, nh, PAGE, 64, dtype=torch.bfloat16, device=dev) for _ in range(Lyr)]
-        self.block_table = torch.arange(n_pages, dtype=torch.int32, device=dev).view(B, self.pages_per_seq).contiguous()
+        self.alloc = page_allocator(eng)
+        self.block_table, self.page_ids = self.alloc.alloc_table(B, self.pages_per_seq)
+        self.pool = self.alloc.pools
         self.kv2 = [torch.empty(B * Tc, 2 * H, dtype=torch.bfloat16, device=dev) for _ in range(Lyr)] if Tc else None
         self.seq_lens = torch.zeros(B, dtype=torch.int32, device=dev)
         self.finished = torch.zeros(B, dtype=torch.int32, device=dev)
@@ -42,7 +91,47 @@ class GenState:
         self.graph = None
 
     def kv_bytes(self):
-        return sum(p.numel() * 2 for p in self.pool) + (sum(k.numel() * 2 for k in self.kv2) if self.kv2 else 0)
+        page = self.pool[0][0].numel() * 2
+        return (page * self.B * self.pages_per_seq * len(self.pool)
+                + (sum(k.numel() * 2 for k in self.kv2) if self.kv2 else 0))
+
+    def release(self):
+        """Hands the pages back (the state must not be used afterwards)."""
+        if self.page_ids is not None:
+            self.alloc.release(self.page_ids)
+            self.page_ids = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    def reset(self):
+        self.finished.zero_()
+        self.step.zero_()
+        self.out_ids.zero_()
+
+
+STATE_CACHE_SIZE = 2   # generation states (pages + captured decode graph) kept per engine, least recently used evicted
+
+
+def _cached_state(eng, key):
+    cache = eng.__dict__.setdefault("_gen_states", [])
+    for i, (k, st) in enumerate(cache):
+        if k == key and st.pool is page_allocator(eng).pools:
+            cache.append(cache.pop(i))
+            return st
+    return None
+
+
+def _store_state(eng, key, st):
+    cache = eng.__dict__.setdefault("_gen_states", [])
+    cache.append((key, st))
+    while len(cache) > STATE_CACHE_SIZE:
+        _, old = cache.pop(0)
+        old.graph = None
+        old.release()
 
 
 def _head_on_rows(eng, x, row_idx, logits):
@@ -249,12 +338,33 @@ def generate(model, input_ids, token_type_ids=None, max_new_tokens=64, do_sample
     max_ctx = T + max_new_tokens
     if max_ctx > eng.n_pos:
         raise ValueError("prompt + max_new_tokens = %d exceeds n_positions = %d" % (max_ctx, eng.n_pos))
+    k = int(top_k) if do_sample else 0
+    if do_sample and k == 0 and top_p >= 1.0:
+        k = -1  # plain multinomial sampling over the whole distribution (ERGM_SAMPLE_ALL), never silently greedy
+    sample_kw = dict(top_k=k, top_p=float(top_p) if do_sample else 1.0, temperature=float(temperature), seed=int(seed),
+                     eos_id=int(eos_token_id) if eos_token_id is not None else -1)
     with torch.cuda.device(dev):
-        st = GenState(eng, B, max_ctx, Tc, max_new_tokens)
-        st.packed = packed_weights(eng)
-        st.mega = None
-        st.stack = None
-        if stack_supported(eng, B, Tc):
+        packed = packed_weights(eng)
+        # A request batch of the same geometry / sampling setup as an earlier one reuses that batch's state: its pages,
+        # its static buffers and its CAPTURED decode graph (the first version re-allocated a zeroed pool and re-captured
+        # the graph on every generate() call).  Keyed on the weight version: packed weights are part of the graph.
+        key = (B, T, max_ctx, Tc, max_new_tokens, sp2_id, tuple(sorted(sample_kw.items())), bool(use_cuda_graph),
+               eng.store.weights_epoch, os.environ.get("ERGM_DEC_STACK", "0"), os.environ.get("ERGM_DEC_MEGA", "0"),
+               os.environ.get("ERGM_DS_TRACE", "0"))
+        st = None if return_state else _cached_state(eng, key)   # a state handed to the caller is the caller's alone
+        fresh = st is None
+        if fresh:
+            st = GenState(eng, B, max_ctx, Tc, max_new_tokens)
+            if not return_state:
+                _store_state(eng, key, st)
+        else:
+            st.reset()
+        st.packed = packed
+    with torch.cuda.device(dev):
+        if not fresh:
+            pass
+        elif stack_supported(eng, B, Tc):
+            st.mega = None
             st.stack_w = stack_weights(eng)
             st.xring = [torch.zeros(B, eng.H, dtype=torch.float32, device=dev) for _ in range(3)]
             st.sync_ctr = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -263,15 +373,13 @@ def generate(model, input_ids, token_type_ids=None, max_new_tokens=64, do_sample
             st.trace = (torch.zeros(16 * eng.L, dtype=torch.int64, device=dev)
                         if os.environ.get("ERGM_DS_TRACE") == "1" else None)
         elif mega_supported(eng, B):
+            st.stack = None
             st.sync_ctr = torch.zeros(1, dtype=torch.int32, device=dev)
             st.mega = mega_table(eng, st)
-        if sp2_id is not None:
+        else:
+            st.mega = st.stack = None
+        if fresh and sp2_id is not None:
             st.tt = torch.full((B, 1), int(sp2_id), dtype=torch.int64, device=dev)
-        k = int(top_k) if do_sample else 0
-        if do_sample and k == 0 and top_p >= 1.0:
-            k = -1  # plain multinomial sampling over the whole distribution (ERGM_SAMPLE_ALL), never silently greedy
-        sample_kw = dict(top_k=k, top_p=float(top_p) if do_sample else 1.0, temperature=float(temperature), seed=int(seed),
-                         eos_id=int(eos_token_id) if eos_token_id is not None else -1)
         # ---- prefill: fused attention over the padded prompts, K/V -> pages, cross K/V cached ----
         out = eng.forward(input_ids, token_type_ids, None, None, imgs, auds, cap, None, kv_lens=lens,
                           training=False, save=False, heads=False, gen_state=st)
@@ -295,18 +403,19 @@ def generate(model, input_ids, token_type_ids=None, max_new_tokens=64, do_sample
                     st.launches_per_step = ops.launch_count() - n0
                 torch.cuda.current_stream().wait_stream(s)
                 if n_steps > 1:
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
-                        decode_step(eng, st, sample_kw)
-                    st.graph = g
+                    if st.graph is None:
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            decode_step(eng, st, sample_kw)
+                        st.graph = g
                     for _ in range(n_steps - 1):  # capture itself executes nothing
-                        g.replay()
+                        st.graph.replay()
             else:
                 for _ in range(n_steps):
                     decode_step(eng, st, sample_kw)
     if return_state:
         return st.out_ids, st
-    return st.out_ids
+    return st.out_ids.clone()   # the state (and its output buffer) is reused by the next batch of the same geometry
 
 
 def _generate_fp32(model, input_ids, token_type_ids, max_new_tokens, eos_token_id, sp2_id, imgs, auds, caption_ids,

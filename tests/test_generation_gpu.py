@@ -372,3 +372,60 @@ def test_plain_multinomial_sampling_is_not_greedy(cuda_device):
     cold = m.generate(ids, tt, max_new_tokens=12, sp2_id=cfg.vocab_size - 1, do_sample=True, top_k=0, top_p=1.0,
                       temperature=1e-3, seed=3).cpu()
     assert (cold[:, 0] == greedy[:, 0]).all()   # T -> 0 concentrates the whole distribution on the arg-max
+
+
+def test_page_allocator_and_state_reuse(cuda_device):
+    """The K/V cache lives in an engine-wide page pool handed out through a free list: block tables are NOT the
+    identity (page j of every sequence before page j+1), pages of evicted states are reused, and a second batch of
+    the same geometry reuses the cached state AND its captured decode graph - with the same tokens as a fresh one."""
+    from ergm_b200 import generation
+    cfg = tiny_cfg()
+    sd = O.init_state_dict(cfg, seed=15, perturb=True)
+    m = build_model(cfg, sd)
+    eng = m.engine
+    kw = dict(max_new_tokens=10, sp2_id=cfg.vocab_size - 1)
+    b1 = synthetic.make_batch(3, 40, seed=31, vocab=cfg.vocab_size, feat_dim=cfg.n_embd, ragged=False)
+    b2 = synthetic.make_batch(3, 40, seed=32, vocab=cfg.vocab_size, feat_dim=cfg.n_embd, ragged=False)
+    # garbage in the pool first (a larger earlier batch): pages are torch.empty and never cleared between batches
+    big = synthetic.make_batch(5, 64, seed=30, vocab=cfg.vocab_size, feat_dim=cfg.n_embd, ragged=False)
+    generation.generate(m, big["input_ids"].cuda(), big["token_type_ids"].cuda(), **kw)
+    alloc = generation.page_allocator(eng)
+    for p in alloc.pools:
+        p.fill_(float("nan"))
+    first1 = generation.generate(m, b1["input_ids"].cuda(), b1["token_type_ids"].cuda(), **kw)
+    states = eng.__dict__["_gen_states"]
+    st = states[-1][1]
+    bt = st.block_table.cpu()
+    assert bt.shape == (3, 4) and len(set(bt.view(-1).tolist())) == 12
+    assert bt.tolist() != torch.arange(12).view(3, 4).tolist()          # not the identity table
+    assert (bt[1] - bt[0]).abs().max().item() == 1                       # page j of neighbours adjacent: interleaved
+    graph = st.graph
+    assert graph is not None
+    first2 = generation.generate(m, b2["input_ids"].cuda(), b2["token_type_ids"].cuda(), **kw)
+    assert states[-1][1] is st and st.graph is graph                    # same state, same captured graph
+    again1 = generation.generate(m, b1["input_ids"].cuda(), b1["token_type_ids"].cuda(), **kw)
+    assert torch.equal(first1, again1) and not torch.equal(first1, first2)
+    # against the launch chain without graph / cache hit (a different key: use_cuda_graph=False)
+    chain1 = generation.generate(m, b1["input_ids"].cuda(), b1["token_type_ids"].cuda(), use_cuda_graph=False, **kw)
+    assert torch.equal(first1, chain1)
+    with torch.no_grad():
+        want = O.greedy_generate_cached(sd, cfg, b1["input_ids"], b1["token_type_ids"], 10, sp2_id=cfg.vocab_size - 1, eos_id=-1)
+    assert _agreement(first1, want, sd, cfg, b1) >= 0.6
+    # eviction (cache of 2 states) gives pages back; total pool never exceeded the largest concurrent demand
+    used = alloc.n_pages - len(alloc.free)
+    assert used == sum(s.B * s.pages_per_seq for _, s in states)
+    # a weight update invalidates the cached graph's packed weights: new key, new state
+    with torch.no_grad():
+        m.transformer.wte.weight.add_(0.05 * torch.randn_like(m.transformer.wte.weight))
+    after = generation.generate(m, b1["input_ids"].cuda(), b1["token_type_ids"].cuda(), **kw)
+    assert eng.__dict__["_gen_states"][-1][1] is not st
+    assert not torch.equal(after, first1)
+    # a state handed to the caller is not cached and returns its pages when dropped
+    _, own = generation.generate(m, b2["input_ids"].cuda(), b2["token_type_ids"].cuda(), return_state=True, **kw)
+    assert all(s is not own for _, s in eng.__dict__["_gen_states"])
+    cached = sum(s.B * s.pages_per_seq for _, s in eng.__dict__["_gen_states"])
+    assert alloc.n_pages - len(alloc.free) == cached + own.B * own.pages_per_seq
+    del own
+    import gc
+    gc.collect()
+    assert alloc.n_pages - len(alloc.free) == cached
