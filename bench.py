@@ -390,6 +390,11 @@ def main():
                                                          "(operands + output of an average launch)",
                     "gemm_launches_per_step": n_gemm, "gemm_ms_per_step": g_ms, "gemm_flops_per_step": g_fl,
                     "avg_launch_us": 1e3 * g_ms / max(n_gemm, 1), "gemm_by_shape": by_shape,
+                    # the LM-head GEMMs run inside ergm_lmhead_ce_{fwd,bwd} (plan + gather + GEMM + CE in one call):
+                    # timed as those entry points, not part of gemm_ms / gemm_flops above
+                    "lm_head_ce": {"scored_rows": n_scored, "fwd_ms": round(by.get("ergm_lmhead_ce_fwd", 0.0), 3),
+                                   "bwd_ms": round(by.get("ergm_lmhead_ce_bwd", 0.0), 3),
+                                   "gemm_flops": 6.0 * n_scored * 50260 * model.config.n_embd},
                     "eager_ms_by_entry_point": {k: round(v, 3) for k, v in sorted(by.items(), key=lambda kv: -kv[1])}}
             step.eng.set_rng_step_tensor(step.rng_step)
     # ---- secondary: the mode main.py asks for (no caption_ids -> no cross-attention), SURVEY §8d ----

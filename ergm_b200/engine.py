@@ -378,21 +378,11 @@ class Engine:
         lse = row_loss = None
         sp = None
         if sparse:
-            i32 = torch.int32
-            sp = dict(row_idx=ws.get("lm_row_idx", (M,), i32), labels_c=ws.get("lm_labels_c", (M,), torch.int64),
-                      count=ws.get("lm_count", (1,), i32), hn_c=ws.get("lm_hn_c", (M, H), bf16),
-                      logits_c=ws.get("lm_logits_c", (M, ldl), bf16))
-            wte_b = self.pb("transformer.wte.weight")
-            ops.lm_rows_plan(labels, sp["row_idx"], sp["labels_c"], sp["count"], T=T, pack=pack)
-            ops.gather_rows_dyn(hn, sp["row_idx"], sp["count"], sp["hn_c"])
-            hint, ops.DYN_HINT = ops.DYN_HINT, 0   # (the packed-batch row hint does not describe the scored-row count)
-            ops.gemm(sp["hn_c"], wte_b, sp["logits_c"], M=M, N=V, K=H, a_major=K_MAJOR, b_major=K_MAJOR,
-                     dyn_m=sp["count"])
-            ops.DYN_HINT = hint
-            lse = ws.get("ce_lse", (M,), f32)
-            row_loss = ws.get("ce_row_loss", (M,), f32)
-            ops.ce_fwd(sp["logits_c"], sp["labels_c"], lse, row_loss, sums, T=0, V=V, hn=sp["hn_c"], w=wte_b,
-                       rows_dyn=sp["count"])
+            # plan -> gather -> GEMM (run-time M) -> CE: ergm_lmhead_ce_fwd, scratch + backward state in one workspace
+            nbytes = ops.lmhead_ce_layout(M, H, V, save)[-1]
+            sp = ops.lmhead_ce_views(ws.get("lm_head_ws", (nbytes,), torch.uint8), M, H, V, save)
+            ops.lmhead_ce_fwd(hn, self.pb("transformer.wte.weight"), labels, sums, sp["ws"], T=T, V=V, pack=pack)
+            lse = sp["lse"]
         elif labels is not None:
             lse = ws.get("ce_lse", (M,), f32)
             row_loss = ws.get("ce_row_loss", (M,), f32)
@@ -626,21 +616,9 @@ class Engine:
         sp = sv.get("sparse")
         if sp is not None:
             # label-sparse head backward on the compacted rows (run-time count sp["count"])
-            ldl = sv["ldl"]
-            cnt = sp["count"]
-            dlogits_c = ws.get("lm_dlogits_c", (M, ldl), bf16)
-            ops.ce_bwd(sp["logits_c"], sp["labels_c"], sv["ce_lse"], scales[0:1], dlogits_c, T=0, V=V, rows_dyn=cnt)
-            wte_b = self.pb("transformer.wte.weight")
-            dhn_c = ws.get("lm_dhn_c", (M, H), f32)
-            dhn_c.zero_()
-            # d hn_c = dlogits_c @ wte: few row tiles, very long K (= V): the kernel splits K itself to fill the GPU
-            ops.gemm(dlogits_c, wte_b, dhn_c, M=M, N=H, K=V, a_major=K_MAJOR, b_major=MN_MAJOR, epilogue=L.EPI_ATOMIC,
-                     block_n=2256, dyn_m=cnt, dyn_hint=-1)
-            dhn.zero_()
-            ops.scatter_rows_dyn(dhn_c, sp["row_idx"], cnt, dhn)
-            # d wte += dlogits_c^T @ hn_c (reduction over the run-time row count)
-            ops.gemm(dlogits_c, sp["hn_c"], self.pg("transformer.wte.weight"), M=V, N=H, K=M, a_major=MN_MAJOR,
-                     b_major=MN_MAJOR, epilogue=L.EPI_ATOMIC, block_n=2256, dyn_k=cnt)
+            # dlogits, d hn (overwritten), d wte (accumulated) from the forward's workspace: ergm_lmhead_ce_bwd
+            ops.lmhead_ce_bwd(self.pb("transformer.wte.weight"), scales[0:1], dhn, self.pg("transformer.wte.weight"),
+                              sp["ws"], V=V)
         elif sv["labels"] is not None:
             ldl = sv["ldl"]
             dlogits = ws.get("dlogits", (M, ldl), bf16)

@@ -6,6 +6,7 @@ Every call counts its kernel launches (bench.py's gpu_launches) and, when ops.PR
 itself with CUDA events on the current stream.
 """
 import ctypes
+import functools
 
 import torch
 
@@ -74,7 +75,8 @@ def gemm(a, b, d, *, M, N, K, a_major=L.ERGM_MAJOR_K, b_major=L.ERGM_MAJOR_MN, l
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim)
-_LAUNCHES = {"ergm_attn_bwd": 2, "ergm_decode_layers": 1, "ergm_decode_stack_pack": 4}
+_LAUNCHES = {"ergm_attn_bwd": 2, "ergm_decode_layers": 1, "ergm_decode_stack_pack": 4, "ergm_lmhead_ce_fwd": 4,
+             "ergm_lmhead_ce_bwd": 4}
 _launch_count = 0
 DYN_HINT = 0    # expected run-time row count of the packed batch being processed (engine sets it; steers tile shapes)
 PROFILE = None  # set to a list to collect (name, info, start_event, end_event) per call
@@ -316,6 +318,54 @@ def gather_rows_dyn(src, row_idx, count, dst):
 
 def scatter_rows_dyn(src, row_idx, count, dst):
     _call("ergm_scatter_rows_dyn", src.data_ptr(), row_idx.data_ptr(), count.data_ptr(), dst.data_ptr(), src.shape[1])
+
+
+_LMHEAD_WS = ("count", "row_idx", "labels_c", "hn_c", "logits_c", "lse", "row_loss", "dlogits_c", "dhn_c")
+_LMHEAD_DT = (torch.int32, torch.int32, torch.int64, torch.bfloat16, torch.bfloat16, torch.float32, torch.float32,
+              torch.bfloat16, torch.float32)
+
+
+@functools.lru_cache(maxsize=64)
+def lmhead_ce_layout(rows, H, V, with_backward=True):
+    """Byte offsets of the sub-buffers of the ergm_lmhead_ce_* workspace (last entry = total bytes)."""
+    import ctypes as C
+    off = (C.c_int64 * (len(_LMHEAD_WS) + 1))()
+    L.check(L.lib().ergm_lmhead_ce_workspace_layout(rows, H, V, int(with_backward), off), "ergm_lmhead_ce_workspace_layout")
+    total = C.c_int64()
+    L.check(L.lib().ergm_lmhead_ce_workspace_bytes(rows, H, V, int(with_backward), C.byref(total)),
+            "ergm_lmhead_ce_workspace_bytes")
+    assert total.value == off[len(_LMHEAD_WS)]
+    return list(off)
+
+
+def lmhead_ce_views(buf, rows, H, V, with_backward=True):
+    """Typed views into a uint8 workspace tensor: {count, row_idx, labels_c, hn_c, logits_c, lse, row_loss, ...}."""
+    off = lmhead_ce_layout(rows, H, V, with_backward)
+    ldl = (V + 63) // 64 * 64
+    shapes = ((1,), (rows,), (rows,), (rows, H), (rows, ldl), (rows,), (rows,), (rows, ldl), (rows, H))
+    views = {"ws": buf}
+    for i, name in enumerate(_LMHEAD_WS):
+        if i >= 7 and not with_backward:
+            break
+        n = 1
+        for s in shapes[i]:
+            n *= s
+        nbytes = n * torch.empty(0, dtype=_LMHEAD_DT[i]).element_size()
+        views[name] = buf[off[i]:off[i] + nbytes].view(_LMHEAD_DT[i]).view(shapes[i])
+    return views
+
+
+def lmhead_ce_fwd(hn, wte_b, labels, sums, ws_buf, *, T, V, pack=None):
+    """LM head + shifted CE on the scored rows, one C-ABI call (include/ergm_b200.h; model.py:698-708)."""
+    rows, H = hn.shape
+    _call("ergm_lmhead_ce_fwd", hn.data_ptr(), wte_b.data_ptr(), labels.data_ptr(), rows, T, H, V, sums.data_ptr(),
+          err_flag(hn.device).data_ptr(), _pk(pack), ws_buf.data_ptr(), ws_buf.numel())
+
+
+def lmhead_ce_bwd(wte_b, scale, dhn, dwte, ws_buf, *, V):
+    rows, H = dhn.shape
+    _call("ergm_lmhead_ce_bwd", wte_b.data_ptr(), scale.data_ptr(), rows, H, V, dhn.data_ptr(), dwte.data_ptr(),
+          ws_buf.data_ptr(), ws_buf.numel())
 
 
 def emotion_head_fwd(x_final, mean, rstd, gamma, beta, w_emo, emo_labels, hlast, logits, dlogits, sums, *, B, T, cu_rows=None):

@@ -233,6 +233,34 @@ int ergm_gather_rows_dyn(const void* src_bf16, const int* row_idx, const int* co
 /* dst[row_idx[i]] = src[i] (fp32 [.., H]) for i < *count */
 int ergm_scatter_rows_dyn(const float* src, const int* row_idx, const int* count, float* dst, int H,
                           void* stream);
+/* LM head + CE as one call each way (replaces model.py:698 lm_head + :705-708 shift / CrossEntropyLoss and what
+ * autograd derives from them): plan -> gather -> tcgen05 GEMM over the scored rows -> CE; backward: dlogits,
+ * d hn (fp32 [rows, H], OVERWRITTEN: zero for rows that are not scored), d wte (fp32 [V, H], ACCUMULATED).
+ * hn: bf16 [rows, H] ln_f output; wte: bf16 [V, H] (the tied head weight); labels: int64 [B, T] as given to the model
+ * (rows = B * T, or the packed rows of `pack`); sums as ergm_ce_fwd.  Never allocates: scratch and the forward state
+ * the backward reads live in `workspace` (256-byte aligned, >= ergm_lmhead_ce_workspace_bytes(rows, H, V, 1) when
+ * the backward follows; the backward must get the SAME workspace, untouched in between).  The layout query returns
+ * the byte offsets of the sub-buffers (ERGM_LMHEAD_WS_*; [END] = total) so that a caller can read the device row
+ * count, the compacted logits or the per-row losses.                                              */
+enum {
+  ERGM_LMHEAD_WS_COUNT = 0,    /* int32 [1]: scored rows of this batch (device) */
+  ERGM_LMHEAD_WS_ROW_IDX = 1,  /* int32 [rows]: source row of compacted row i */
+  ERGM_LMHEAD_WS_LABELS = 2,   /* int64 [rows]: its target */
+  ERGM_LMHEAD_WS_HN = 3,       /* bf16 [rows, H]: gathered ln_f rows */
+  ERGM_LMHEAD_WS_LOGITS = 4,   /* bf16 [rows, roundup(V, 64)]: logits of the scored rows */
+  ERGM_LMHEAD_WS_LSE = 5,      /* fp32 [rows] */
+  ERGM_LMHEAD_WS_ROW_LOSS = 6, /* fp32 [rows] */
+  ERGM_LMHEAD_WS_DLOGITS = 7,  /* bf16 [rows, roundup(V, 64)] (backward) */
+  ERGM_LMHEAD_WS_DHN = 8,      /* fp32 [rows, H] (backward) */
+  ERGM_LMHEAD_WS_END = 9
+};
+int ergm_lmhead_ce_workspace_bytes(int rows, int H, int V, int with_backward, int64_t* bytes);
+int ergm_lmhead_ce_workspace_layout(int rows, int H, int V, int with_backward, int64_t* offsets /* [END + 1] */);
+int ergm_lmhead_ce_fwd(const void* hn_bf16, const void* wte_bf16, const int64_t* labels, int rows, int T, int H,
+                       int V, float* sums, int* err_flag, const ergm_pack* pack /* nullable */, void* workspace,
+                       int64_t workspace_bytes, void* stream);
+int ergm_lmhead_ce_bwd(const void* wte_bf16, const float* scale_ptr /* device: d loss / d row loss */, int rows, int H,
+                       int V, float* dhn, float* dwte, void* workspace, int64_t workspace_bytes, void* stream);
 /* Emotion head on the last position + 7-way CE (model.py:700-701,710-711).   */
 /* sums[2] += sum of sample losses, sums[3] += samples.                       */
 int ergm_emotion_head_fwd(const float* x_final, const float* mean, const float* rstd,

@@ -120,3 +120,15 @@ def test_reference_compat_shim_exports():
     spec.loader.exec_module(mod)
     for name in ("GPT2LMHeadModel", "GPT2Model", "CausalLMOutputWithEmotionClassification", "torch", "nn", "F"):
         assert hasattr(mod, name)
+
+
+def test_lmhead_ce_workspace_query_without_gpu():
+    """The workspace queries of the composed LM-head + CE entry points are pure host arithmetic."""
+    from ergm_b200 import ops
+    fwd = ops.lmhead_ce_layout(8192, 768, 50260, False)
+    both = ops.lmhead_ce_layout(8192, 768, 50260, True)
+    assert fwd[:8] == both[:8] and all(o % 256 == 0 for o in both)
+    assert all(b > a for a, b in zip(both[:7], both[1:8])) and both[-1] > fwd[-1]
+    ldl = (50260 + 63) // 64 * 64
+    assert both[5] - both[4] == 8192 * ldl * 2            # bf16 logits of the scored rows (capacity = all rows)
+    assert both[-1] - both[8] == 8192 * 768 * 4

@@ -158,3 +158,50 @@ def test_sparse_head_edge_label_patterns(cuda_device):
     m(input_ids=b["input_ids"].cuda(), token_type_ids=b["token_type_ids"].cuda(), labels=lab.cuda())
     with pytest.raises(L.ErgmError):
         stale.logits
+
+
+def test_lmhead_ce_c_abi_vs_torch(cuda_device):
+    """ergm_lmhead_ce_fwd / _bwd called directly (one workspace, no other state) against fp32 torch on the same
+    bf16-rounded operands: loss sums, compacted rows, d hn (zero on unscored rows), d wte accumulated."""
+    from ergm_b200 import _lib as L
+    from ergm_b200 import ops
+    B, T, H, V = 4, 50, 128, 1000           # 200 rows: not a multiple of the 128-row tile; V not a multiple of 64
+    g = torch.Generator().manual_seed(3)
+    hn = torch.randn(B * T, H, generator=g).cuda().bfloat16()
+    wte = (0.2 * torch.randn(V, H, generator=g)).cuda().bfloat16()
+    labels = torch.randint(0, V, (B, T), generator=g)
+    labels[torch.rand(B, T, generator=g) < 0.6] = -100
+    lab = labels.cuda()
+    off = ops.lmhead_ce_layout(B * T, H, V, True)
+    assert off[-1] > ops.lmhead_ce_layout(B * T, H, V, False)[-1]
+    buf = torch.zeros(off[-1], dtype=torch.uint8, device="cuda")
+    sums = torch.zeros(4, device="cuda")
+    ops.lmhead_ce_fwd(hn, wte, lab, sums, buf, T=T, V=V)
+    v = ops.lmhead_ce_views(buf, B * T, H, V, True)
+    # reference: shifted labels, ignore_index = -100 (model.py:705-708)
+    hn32 = hn.float().requires_grad_(True)
+    w32 = wte.float().requires_grad_(True)
+    logits = (hn32 @ w32.t()).view(B, T, V)
+    loss_sum = torch.nn.functional.cross_entropy(logits[:, :-1].reshape(-1, V), lab[:, 1:].reshape(-1), ignore_index=-100,
+                                                 reduction="sum")
+    n_valid = int((labels[:, 1:] != -100).sum())
+    assert int(v["count"].item()) == n_valid and sums[1].item() == n_valid
+    assert abs(sums[0].item() - loss_sum.item()) / loss_sum.item() < 2e-3
+    rows = [b * T + t for b in range(B) for t in range(T - 1) if labels[b, t + 1] != -100]
+    assert v["row_idx"][:n_valid].cpu().tolist() == rows
+    assert rel(v["logits_c"][:n_valid, :V], logits.detach().view(B * T, V)[rows]) < 1e-2
+    scale = torch.tensor([0.5], device="cuda")
+    (0.5 * loss_sum).backward()
+    dhn = torch.full((B * T, H), float("nan"), device="cuda")
+    dwte = torch.ones(V, H, device="cuda")
+    ops.lmhead_ce_bwd(wte, scale, dhn, dwte, buf, V=V)
+    assert rel(dhn, hn32.grad) < 2e-2
+    unscored = torch.ones(B * T, dtype=torch.bool)
+    unscored[rows] = False
+    assert (dhn[unscored.cuda()] == 0).all()
+    assert rel(dwte - 1.0, w32.grad) < 2e-2
+    # argument checks: workspace too small / misaligned -> ERGM_ERR_ARG, nothing launched
+    with pytest.raises(L.ErgmError):
+        ops.lmhead_ce_fwd(hn, wte, lab, sums, buf[: off[-1] // 2], T=T, V=V)
+    with pytest.raises(L.ErgmError):
+        ops.lmhead_ce_fwd(hn, wte, lab, sums, buf[8:], T=T, V=V)
