@@ -20,7 +20,7 @@ OBJDIR = os.path.join(HERE, "build")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
-]
+] + os.environ.get("ERGM_NVCC_EXTRA", "").split()   # e.g. -DERGM_ATTN_TRACE for scripts/trace_attn_bwd.py (never shipped)
 
 
 def _sources():

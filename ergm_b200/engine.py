@@ -650,7 +650,9 @@ class Engine:
                    self.pg("transformer.ln_f.weight"), self.pg("transformer.ln_f.bias"),
                    self.pg(last + "mlp.c_proj.bias"), dropout_p=pd_res, seed=seed,
                    offset=site0 + 8 * (Lyr - 1) + 5, rows_dyn=dyn)
-        dq_acc = ws.get("dq_acc", (M, H), f32)
+        # fp32 scratch of the attention backward (0 bytes up to T = 256: dQ stays in TMEM there)
+        ab_bytes = ops.attn_bwd_workspace_bytes(B, nh, T)
+        ab_ws = ws.get("attn_bwd_ws", (ab_bytes,), torch.uint8) if ab_bytes else None
         delta = ws.get("delta", (B, nh, T), f32)
         denc = None
         if sv["enc"] is not None:
@@ -687,14 +689,13 @@ class Engine:
             if has_x:
                 self._wgrad_gemm(r["ctx2"], dxb, self.pg(pfx + "crossattention.c_proj.weight"), H, H, M, dyn)
                 self._dgrad_gemm(dxb, self.pb(pfx + "crossattention.c_proj.weight"), dH, M, H, H, dyn_m=dyn)
-                dq_acc.zero_()
                 self._side_join()  # dkv2 is about to be overwritten
-                gbx = self.pg(pfx + "crossattention.c_attn.bias")  # K / V bias gradients come out of attn_bwd
-                ops.attn_bwd(r["q2"], r["kv2"], r["kv2"], r["ctx2"], dH, r["lse2"], delta, dq_acc, dkv2, dkv2,
+                gbx = self.pg(pfx + "crossattention.c_attn.bias")  # Q / K / V bias gradients come out of attn_bwd
+                ops.attn_bwd(r["q2"], r["kv2"], r["kv2"], r["ctx2"], dH, r["lse2"], delta, dq2, dkv2, dkv2,
                              B=B, nh=nh, Tq=T, Tk=Tc, q_col0=0, k_col0=0, v_col0=H, dk_col0=0, dv_col0=H,
                              causal=False, dropout_p=pd_attn, seed=seed, offset=s_xattn, out_f32=r["ctx2_32"],
-                             dk_colsum=gbx[:H], dv_colsum=gbx[H:], pack=pack)
-                ops.cast_f32_bf16_2d(dq_acc, dq2, self.pg(pfx + "crossattention.q_attn.bias"), rows_dyn=dyn)
+                             dq_colsum=self.pg(pfx + "crossattention.q_attn.bias"), dk_colsum=gbx[:H],
+                             dv_colsum=gbx[H:], pack=pack, workspace=ab_ws)
                 self._wgrad_gemm(r["a2"], dq2, self.pg(pfx + "crossattention.q_attn.weight"), H, H, M, dyn)
                 self._wgrad_gemm(sv["enc"], dkv2, self.pg(pfx + "crossattention.c_attn.weight"), H, 2 * H, Mc)
                 self._dgrad_gemm(dq2, self.pb(pfx + "crossattention.q_attn.weight"), dH, M, H, H, dyn_m=dyn)
@@ -709,15 +710,14 @@ class Engine:
             # ---- self attention backward ----
             self._wgrad_gemm(r["ctx"], dxb, self.pg(pfx + "attn.c_proj.weight"), H, H, M, dyn)
             self._dgrad_gemm(dxb, self.pb(pfx + "attn.c_proj.weight"), dH, M, H, H, dyn_m=dyn)
-            dq_acc.zero_()
             self._side_join()  # dqkv is about to be overwritten
             qkv = r["qkv"]
             gb = self.pg(pfx + "attn.c_attn.bias")
-            ops.attn_bwd(qkv, qkv, qkv, r["ctx"], dH, r["lse1"], delta, dq_acc, dqkv, dqkv, B=B, nh=nh, Tq=T, Tk=T,
-                         q_col0=0, k_col0=H, v_col0=2 * H, dk_col0=H, dv_col0=2 * H, causal=True,
+            ops.attn_bwd(qkv, qkv, qkv, r["ctx"], dH, r["lse1"], delta, dqkv, dqkv, dqkv, B=B, nh=nh, Tq=T, Tk=T,
+                         q_col0=0, k_col0=H, v_col0=2 * H, dq_col0=0, dk_col0=H, dv_col0=2 * H, causal=True,
                          kv_lens=sv["kv_lens"], dropout_p=pd_attn, seed=seed, offset=s_attn, out_f32=r["ctx32"],
-                         dk_colsum=gb[H:2 * H], dv_colsum=gb[2 * H:], pack=pack, pack_kv=pack is not None)
-            ops.cast_f32_bf16_2d(dq_acc, dqkv[:, :H], gb[:H], rows_dyn=dyn)
+                         dq_colsum=gb[:H], dk_colsum=gb[H:2 * H], dv_colsum=gb[2 * H:], pack=pack,
+                         pack_kv=pack is not None, workspace=ab_ws)
             self._wgrad_gemm(r["a1"], dqkv, self.pg(pfx + "attn.c_attn.weight"), H, 3 * H, M, dyn)
             self._dgrad_gemm(dqkv, self.pb(pfx + "attn.c_attn.weight"), dH, M, H, 3 * H, dyn_m=dyn)
             self._side_join()

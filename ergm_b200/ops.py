@@ -75,7 +75,7 @@ def gemm(a, b, d, *, M, N, K, a_major=L.ERGM_MAJOR_K, b_major=L.ERGM_MAJOR_MN, l
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim)
-_LAUNCHES = {"ergm_attn_bwd": 2, "ergm_decode_layers": 1, "ergm_decode_stack_pack": 4, "ergm_lmhead_ce_fwd": 4,
+_LAUNCHES = {"ergm_attn_bwd": 2,   # (+ memset and cast for Tq > 256) "ergm_decode_layers": 1, "ergm_decode_stack_pack": 4, "ergm_lmhead_ce_fwd": 4,
              "ergm_lmhead_ce_bwd": 4}
 _launch_count = 0
 DYN_HINT = 0    # expected run-time row count of the packed batch being processed (engine sets it; steers tile shapes)
@@ -279,17 +279,32 @@ def attn_fwd(q, k, v, out, lse, *, B, nh, Tq, Tk, q_col0=0, k_col0=0, v_col0=0, 
           causal_off, dropout_p, seed, offset, _pk(pack), int(pack_kv))
 
 
-def attn_bwd(q, k, v, out, dout, lse, delta, dq_accum, dk, dv, *, B, nh, Tq, Tk, q_col0=0, k_col0=0, v_col0=0,
-             dk_col0=0, dv_col0=0, causal=True, causal_off=None, kv_lens=None, dropout_p=0.0, seed=0, offset=0,
-             out_f32=None, dk_colsum=None, dv_colsum=None, pack=None, pack_kv=False):
+@functools.lru_cache(maxsize=64)
+def attn_bwd_workspace_bytes(B, nh, Tq):
+    import ctypes as C
+    n = C.c_int64()
+    L.check(L.lib().ergm_attn_bwd_workspace_bytes(B, nh, Tq, C.byref(n)), "ergm_attn_bwd_workspace_bytes")
+    return n.value
+
+
+def attn_bwd(q, k, v, out, dout, lse, delta, dq, dk, dv, *, B, nh, Tq, Tk, q_col0=0, k_col0=0, v_col0=0,
+             dq_col0=0, dk_col0=0, dv_col0=0, causal=True, causal_off=None, kv_lens=None, dropout_p=0.0, seed=0,
+             offset=0, out_f32=None, dq_colsum=None, dk_colsum=None, dv_colsum=None, pack=None, pack_kv=False,
+             workspace=None):
+    """dq / dk / dv: bf16 outputs.  workspace: uint8 / fp32 tensor of attn_bwd_workspace_bytes(B, nh, Tq) bytes (0 for
+    Tq <= 256); allocated here when not given (tests) - the engine passes a cached one."""
     if causal_off is None:
         causal_off = Tk - Tq
+    assert dq.dtype == torch.bfloat16
+    need = attn_bwd_workspace_bytes(B, nh, Tq)
+    if need and (workspace is None or workspace.numel() * workspace.element_size() < need):
+        workspace = torch.empty(need, dtype=torch.uint8, device=q.device)
     _call("ergm_attn_bwd", q.data_ptr(), q.stride(0), q_col0, k.data_ptr(), k.stride(0), k_col0, v.data_ptr(),
           v.stride(0), v_col0, out.data_ptr(), out.stride(0), _p(out_f32), dout.data_ptr(), dout.stride(0), lse.data_ptr(),
-          delta.data_ptr(), dq_accum.data_ptr(), dq_accum.stride(0), dk.data_ptr(), dk.stride(0), dk_col0,
-          dv.data_ptr(), dv.stride(0), dv_col0, _p(dk_colsum), _p(dv_colsum), _p(kv_lens), B, nh, Tq, Tk, 64, int(causal),
-          causal_off,
-          dropout_p, seed, offset, _pk(pack), int(pack_kv))
+          delta.data_ptr(), dq.data_ptr(), dq.stride(0), dq_col0, dk.data_ptr(), dk.stride(0), dk_col0,
+          dv.data_ptr(), dv.stride(0), dv_col0, _p(dq_colsum), _p(dk_colsum), _p(dv_colsum), _p(kv_lens), B, nh, Tq, Tk,
+          64, int(causal), causal_off, dropout_p, seed, offset, _pk(pack), int(pack_kv),
+          workspace.data_ptr() if need else None, need)
 
 
 def ce_fwd(logits, labels, lse, row_loss, sums, *, T, V, hn=None, w=None, rows_dyn=None):

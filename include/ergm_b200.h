@@ -192,19 +192,23 @@ int ergm_attn_fwd(const void* q, int64_t ld_q, int q_col0, const void* k, int64_
                   int pack_kv /* 1: k / v are packed the same way and kv_lens = pack->kv_lens (self attention) */,
                   void* stream);
 
-/* Backward of ergm_attn_fwd: recomputes P from lse; dq_accum (fp32, pre-zeroed,
- * [B*Tq, ld_dq]) is accumulated with red.add across key blocks; dk / dv are
- * written (bf16) at [B*Tk, ld] column offsets dk_col0 / dv_col0 (+64h);
- * delta ([B,nh,Tq] scratch) receives rowsum(dO * O).  dk_colsum / dv_colsum
- * (nullable fp32 [nh*64]) are incremented by the column sums of dK / dV as
- * stored, i.e. the bias gradients of the K / V projections.                   */
+/* Backward of ergm_attn_fwd: recomputes P from lse; dq / dk / dv are written (bf16) at [B*Tq | B*Tk, ld] column
+ * offsets dq_col0 / dk_col0 / dv_col0 (+64h); delta ([B,nh,Tq] scratch) receives rowsum(dO * O).  dq_colsum /
+ * dk_colsum / dv_colsum (nullable fp32 [nh*64]) are incremented by the column sums of dQ / dK / dV as stored, i.e.
+ * the bias gradients of the Q / K / V projections.  Persistent kernel, one CTA per SM.  Tq <= 256: a CTA owns whole
+ * (batch, head) items, dQ accumulates in TMEM and no workspace is needed; longer sequences: one item per 128-key
+ * block, dQ contributions meet in an fp32 workspace (ergm_attn_bwd_workspace_bytes; zeroed, cast and column-summed by
+ * this call).  Never allocates.                                               */
+int ergm_attn_bwd_workspace_bytes(int B, int nh, int Tq, int64_t* bytes);
 int ergm_attn_bwd(const void* q, int64_t ld_q, int q_col0, const void* k, int64_t ld_k,
                   int k_col0, const void* v, int64_t ld_v, int v_col0, const void* out,
                   int64_t ld_out, const float* out_f32 /* nullable */, const void* dout, int64_t ld_do, const float* lse, float* delta,
-                  float* dq_accum, int64_t ld_dq, void* dk, int64_t ld_dk, int dk_col0, void* dv,
-                  int64_t ld_dv, int dv_col0, float* dk_colsum, float* dv_colsum, const int* kv_lens, int B, int nh, int Tq, int Tk,
-                  int head_dim, int causal, int causal_off, float dropout_p, uint64_t seed,
-                  uint64_t offset, const ergm_pack* pack, int pack_kv, void* stream);
+                  void* dq, int64_t ld_dq, int dq_col0, void* dk, int64_t ld_dk, int dk_col0, void* dv,
+                  int64_t ld_dv, int dv_col0, float* dq_colsum, float* dk_colsum, float* dv_colsum, const int* kv_lens,
+                  int B, int nh, int Tq, int Tk, int head_dim, int causal, int causal_off, float dropout_p,
+                  uint64_t seed, uint64_t offset, const ergm_pack* pack, int pack_kv,
+                  void* workspace /* 16-byte aligned; may be NULL when the query returns 0 */, int64_t workspace_bytes,
+                  void* stream);
 
 /* ------------------------------------------------------------------------ */
 /* Token cross-entropy over LM-head logits with the reference's shift and     */

@@ -105,7 +105,7 @@ if want("attn"):
                k_col0=H, v_col0=2 * H, causal=False, dropout_p=pd, seed=1, offset=2, out_f32=o32[i]), nb, flops=2 * fl_c)
     douts = [torch.randn(M, H, device=dev).bfloat16() for _ in range(nb)]
     dqkv = [torch.zeros(M, 3 * H, device=dev, dtype=torch.bfloat16) for _ in range(nb)]
-    dq = torch.zeros(M, H, device=dev)
+    dq = torch.zeros(M, H, device=dev, dtype=torch.bfloat16)
     delta = torch.zeros(B, nh, T, device=dev)
     for pd in (0.0, args.dropout):
         for causal in (True, False):

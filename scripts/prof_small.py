@@ -17,7 +17,7 @@ if which in ("all", "attn"):
             ops.attn_fwd(qkv, qkv, qkv, out, lse, B=B, nh=nh, Tq=T, Tk=T, k_col0=H, v_col0=2 * H, causal=causal, out_f32=o32)
     dout = torch.randn(M, H, device=dev).bfloat16()
     dqkv = torch.zeros(M, 3 * H, device=dev, dtype=torch.bfloat16)
-    dq = torch.zeros(M, H, device=dev)
+    dq = torch.zeros(M, H, device=dev, dtype=torch.bfloat16)
     delta = torch.zeros(B, nh, T, device=dev)
     for causal in (True, False):
         for _ in range(2):

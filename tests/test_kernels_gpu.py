@@ -305,11 +305,14 @@ def test_attn_bwd(cuda_device, B, nh, Tq, Tk, causal):
     ops.attn_fwd(qm, km, vm, out, lse, B=B, nh=nh, Tq=Tq, Tk=Tk, q_col0=qc, k_col0=kc, v_col0=vc, causal=causal)
     dout = torch.randn(B * Tq, H, device="cuda", generator=g).bfloat16()
     delta = torch.empty(B, nh, Tq, device="cuda")
-    dq = torch.zeros(B * Tq, H, device="cuda")
-    cs = torch.full((2, H), 0.5, device="cuda")  # fused K / V bias gradients accumulate onto existing values
-    ops.attn_bwd(qm, km, vm, out, dout, lse, delta, dq, dkm, dvm, B=B, nh=nh, Tq=Tq, Tk=Tk, q_col0=qc, k_col0=kc,
-                 v_col0=vc, dk_col0=dkc, dv_col0=dvc, causal=causal, dk_colsum=cs[0], dv_colsum=cs[1])
-    for i, (mat, c0) in enumerate(((dkm, dkc), (dvm, dvc))):
+    dqb = torch.full((B * Tq, H + 8), float("nan"), device="cuda", dtype=torch.bfloat16)  # every dQ row must be written
+    cs = torch.full((3, H), 0.5, device="cuda")  # fused Q / K / V bias gradients accumulate onto existing values
+    ops.attn_bwd(qm, km, vm, out, dout, lse, delta, dqb, dkm, dvm, B=B, nh=nh, Tq=Tq, Tk=Tk, q_col0=qc, k_col0=kc,
+                 v_col0=vc, dq_col0=8, dk_col0=dkc, dv_col0=dvc, causal=causal, dq_colsum=cs[2], dk_colsum=cs[0],
+                 dv_colsum=cs[1])
+    assert torch.isnan(dqb[:, :8]).all()    # columns in front of dq_col0 untouched
+    dq = dqb[:, 8:].float()
+    for i, (mat, c0) in enumerate(((dkm, dkc), (dvm, dvc), (dqb, 8))):
         want = 0.5 + mat[:, c0:c0 + H].float().sum(0)  # column sums of the values AS STORED (bf16)
         assert (cs[i] - want).abs().max().item() < 2e-3 * (1 + want.abs().max().item()), (cs[i] - want).abs().max().item()
     q = qm[:, qc:qc + H].float().view(B, Tq, nh, 64).permute(0, 2, 1, 3).clone().requires_grad_(True)
@@ -356,9 +359,8 @@ def test_attn_dropout_fwd_bwd_consistent(cuda_device):
     # the realised mask through linearity: sum_kv dV[kv] == sum_q dO[q] * rowsum(P_drop[q]) = dO . o(V=1)
     dout = torch.randn(B * T, H, device="cuda", generator=g).bfloat16()
     delta = torch.empty(B, nh, T, device="cuda")
-    dq = torch.zeros(B * T, H, device="cuda")
     dqkv = torch.zeros(B * T, 3 * H, device="cuda", dtype=torch.bfloat16)
-    ops.attn_bwd(qkv1, qkv1, qkv1, o1, dout, lse, delta, dq, dqkv, dqkv, dk_col0=H, dv_col0=2 * H,
+    ops.attn_bwd(qkv1, qkv1, qkv1, o1, dout, lse, delta, dqkv, dqkv, dqkv, dk_col0=H, dv_col0=2 * H,
                  dropout_p=0.3, seed=3, offset=4, **kw)
     dv_sum = dqkv[:, 2 * H:].float().view(T, nh, 64).sum(0)
     want = (dout.float().view(T, nh, 64) * o1.float().view(T, nh, 64)[:, :, :1]).sum(0)

@@ -75,7 +75,7 @@ def test_attention_packed_equals_padded(cuda_device, causal):
         o32 = torch.zeros(B * T, H, device="cuda")
         lse = torch.zeros(B, nh, T, device="cuda")
         delta = torch.zeros(B, nh, T, device="cuda")
-        dq = torch.zeros(B * T, H, device="cuda")
+        dq = torch.zeros(B * T, H, device="cuda", dtype=torch.bfloat16)
         if causal:
             dkv = torch.zeros(B * T, 3 * H, device="cuda", dtype=torch.bfloat16)
             kw = dict(B=B, nh=nh, Tq=T, Tk=T, q_col0=0, k_col0=H, v_col0=2 * H, causal=True,
