@@ -229,7 +229,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 const __grid_constant__ CUtensorMap tm_dv, const AttnBwdParams p_in) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   AttnBwdParams p = p_in;
-  p.drop = p_in.drop.resolved();
   const uint32_t base = smem_u32(smem_raw);
   const uint32_t sK = base, sV = base + 2 * AB_TILE;   // 2 item buffers each
   const uint32_t sQ = base + 4 * AB_TILE;    // 2 stages
@@ -299,6 +298,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();               // programmatic dependent launch: no global memory access above this line
+  pdl_launch_dependents();
+  p.drop = p_in.drop.resolved();
   if (threadIdx.x == 0) AB_MARK(61);
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
@@ -627,6 +629,8 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ dout, int64_t ld_do,
                   const int* __restrict__ n_rows) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
+  pdl_wait();
+  pdl_launch_dependents();
   if (row >= rows) return;
   int b = row / Tq, q = row - b * Tq;
   if (cu_q) {   // packed batch: row is a packed row; delta keeps the padded [B, nh, T] indexing
@@ -691,10 +695,10 @@ extern "C" int ergm_attn_bwd(const void* q, int64_t ld_q, int q_col0, const void
   ergm_attn_bwd_workspace_bytes(B, nh, Tq, &need);
   if (need > 0 && (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 15))) return ERGM_ERR_ARG;
   cudaStream_t s = (cudaStream_t)stream;
-  attn_delta_kernel<<<(B * Tq + 7) / 8, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dout), ld_do,
-                                                    reinterpret_cast<const __nv_bfloat16*>(out), ld_out,
-                                                    out_f32, delta, B * Tq, Tq, nh, pack ? pack->cu_rows : nullptr,
-                                                    pack ? pack->row_b : nullptr, pack ? pack->n_rows : nullptr);
+  ERGM_CUDA_TRY(launch_pdl(attn_delta_kernel, dim3((unsigned)((B * Tq + 7) / 8)), dim3(256), 0, s, 1,
+                           reinterpret_cast<const __nv_bfloat16*>(dout), ld_do, reinterpret_cast<const __nv_bfloat16*>(out),
+                           ld_out, (const float*)out_f32, delta, B * Tq, Tq, nh, pack ? pack->cu_rows : (const int*)nullptr,
+                           pack ? pack->row_b : (const int*)nullptr, pack ? pack->n_rows : (const int*)nullptr));
   CUtensorMap tq, tk, tv, tdo, tdq, tdk, tdv;
   int rc;
   if ((rc = encode_tmap_3d(&tq, q, 2, (uint64_t)(q_col0 + nh * 64), q_rows, q_bat,
@@ -741,10 +745,9 @@ extern "C" int ergm_attn_bwd(const void* q, int64_t ld_q, int q_col0, const void
   const int n_items = p.whole_head ? B * nh : B * nh * ((Tk + 127) / 128);
   dim3 grid(n_items < num_sms() ? n_items : num_sms());
   if (causal)
-    attn_bwd_kernel<true><<<grid, AB_THREADS, AB_SMEM, s>>>(tq, tk, tv, tdo, tdq, tdk, tdv, p);
+    ERGM_CUDA_TRY(launch_pdl(attn_bwd_kernel<true>, grid, dim3(AB_THREADS), (size_t)AB_SMEM, s, 1, tq, tk, tv, tdo, tdq, tdk, tdv, p));
   else
-    attn_bwd_kernel<false><<<grid, AB_THREADS, AB_SMEM, s>>>(tq, tk, tv, tdo, tdq, tdk, tdv, p);
-  if ((rc = (int)cudaGetLastError())) return rc;
+    ERGM_CUDA_TRY(launch_pdl(attn_bwd_kernel<false>, grid, dim3(AB_THREADS), (size_t)AB_SMEM, s, 1, tq, tk, tv, tdo, tdq, tdk, tdv, p));
   if (!p.whole_head) {
     // dQ contributions of the key blocks -> bf16 dQ (+ its column sums: the bias gradient of the Q projection)
     return ergm_cast_f32_bf16_2d(reinterpret_cast<const float*>(workspace), (int64_t)nh * 64,

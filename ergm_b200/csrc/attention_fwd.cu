@@ -52,7 +52,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 const __grid_constant__ CUtensorMap tm_v, const AttnFwdParams p_in) {
   extern __shared__ uint8_t smem_raw[];
   AttnFwdParams p = p_in;
-  p.drop = p_in.drop.resolved();
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base, sK = base + AT_TILE, sV = base + 3 * AT_TILE;
   const uint32_t sX = base + 5 * AT_TILE;  // float xch[2 halves][128]
@@ -63,6 +62,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const uint32_t tmem_slot = bars + 64;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_wait();               // programmatic dependent launch: the CTA may be resident before the previous kernel ended
+  pdl_launch_dependents();
+  p.drop = p_in.drop.resolved();
   // heaviest CTAs first: causal query block qb visits qb + 1 key blocks, so the LAST query blocks are scheduled
   // first (blockIdx.z is the slowest-varying index of the block scheduler) and the light ones fill the tail
   const int qb = (int)gridDim.z - 1 - (int)blockIdx.z, h = blockIdx.y, b = blockIdx.x;
@@ -353,8 +355,6 @@ extern "C" int ergm_attn_fwd(const void* q, int64_t ld_q, int q_col0, const void
   }
   dim3 grid(B, nh, (Tq + 127) / 128);
   if (causal)
-    attn_fwd_kernel<true><<<grid, AT_THREADS, AT_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
-  else
-    attn_fwd_kernel<false><<<grid, AT_THREADS, AT_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
-  return (int)cudaGetLastError();
+    return (int)launch_pdl(attn_fwd_kernel<true>, grid, dim3(AT_THREADS), (size_t)AT_SMEM, (cudaStream_t)stream, 1, tq, tk, tv, p);
+  return (int)launch_pdl(attn_fwd_kernel<false>, grid, dim3(AT_THREADS), (size_t)AT_SMEM, (cudaStream_t)stream, 1, tq, tk, tv, p);
 }

@@ -286,6 +286,8 @@ __global__ void __launch_bounds__(LNB_THREADS, 1) ln_bwd_kernel(const LnBwdParam
   constexpr int H = NV * 128;
   extern __shared__ __align__(128) unsigned char lnb_smem[];
   LnBwdParams p = p_in;
+  pdl_wait();               // programmatic dependent launch: nothing is read before the previous kernel completed
+  pdl_launch_dependents();
   p.drop = p_in.drop.resolved();
   if (p.rows_dyn) p.rows = min(p.rows, *p.rows_dyn);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -704,8 +706,7 @@ extern "C" int ergm_ln_bwd(const void* dy, int dy_is_f32, const float* x, const 
   if (smem > 232448) return ERGM_ERR_UNSUPPORTED;
   auto launch = [&](auto kern) -> int {
     ERGM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    kern<<<grid, LNB_THREADS, smem, (cudaStream_t)stream>>>(p, stages);
-    return (int)cudaGetLastError();
+    return (int)launch_pdl(kern, dim3((unsigned)grid), dim3(LNB_THREADS), (size_t)smem, (cudaStream_t)stream, 1, p, stages);
   };
   switch (H / 128) {
     case 1: return launch(ln_bwd_kernel<1>);

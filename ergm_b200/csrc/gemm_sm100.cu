@@ -429,7 +429,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
                  const __grid_constant__ CUtensorMap tmap_b, const GemmParams p_in) {
   using Cfg = GemmCfg<BN>;
   GemmParams p = p_in;
-  apply_dyn(p, BM, (int)gridDim.x);
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle needs 1024-byte aligned tiles
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -466,6 +465,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) touches no
+  // global memory and may overlap the tail of the previous kernel of the stream; nothing below runs before that
+  // kernel has completed.  Our own dependents may be scheduled as soon as every CTA of this grid got here.
+  pdl_wait();
+  pdl_launch_dependents();
+  apply_dyn(p, BM, (int)gridDim.x);
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -608,7 +613,6 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
                   const __grid_constant__ CUtensorMap tmap_b, const GemmParams p_in) {
   using Cfg = Gemm2Cfg<BN>;
   GemmParams p = p_in;
-  apply_dyn(p, 256, (int)(gridDim.x >> 1));
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stage_all = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
@@ -648,6 +652,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
   tc_fence_before();
   cluster_sync();
   tc_fence_after();
+  pdl_wait();               // (see gemm_bf16_kernel) no global memory access above this line
+  pdl_launch_dependents();
+  apply_dyn(p, 256, (int)(gridDim.x >> 1));
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -793,19 +800,8 @@ static int launch_gemm2(const ergm_gemm_args* a, cudaStream_t stream) {
   const int total = p.m_tiles * p.n_tiles * p.split_k;
   const int max_clusters = num_sms() / 2;
   const int clusters = total < max_clusters ? total : max_clusters;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * clusters);
-  cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return (int)cudaLaunchKernelEx(&cfg, gemm2_bf16_kernel<BN, EC, FM>, ta, tb, p);
+  return (int)launch_pdl(gemm2_bf16_kernel<BN, EC, FM>, dim3(2 * clusters), dim3(GEMM_THREADS), (size_t)Cfg::SMEM_BYTES,
+                         stream, 2, ta, tb, p);
 }
 
 template <int BN, int EC, int FM>
@@ -846,8 +842,8 @@ static int launch_gemm(const ergm_gemm_args* a, cudaStream_t stream) {
   ERGM_SET_SMEM_ATTR((gemm_bf16_kernel<BN, EC, FM>), Cfg::SMEM_BYTES);
   const int total = p.m_tiles * p.n_tiles * p.split_k;
   const int grid = total < num_sms() ? total : num_sms();
-  gemm_bf16_kernel<BN, EC, FM><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
-  return (int)cudaGetLastError();
+  return (int)launch_pdl(gemm_bf16_kernel<BN, EC, FM>, dim3(grid), dim3(GEMM_THREADS), (size_t)Cfg::SMEM_BYTES, stream,
+                         1, ta, tb, p);
 }
 
 }  // namespace ergm
