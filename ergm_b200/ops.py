@@ -75,8 +75,8 @@ def gemm(a, b, d, *, M, N, K, a_major=L.ERGM_MAJOR_K, b_major=L.ERGM_MAJOR_MN, l
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim)
-_LAUNCHES = {"ergm_attn_bwd": 2,   # (+ memset and cast for Tq > 256) "ergm_decode_layers": 1, "ergm_decode_stack_pack": 4, "ergm_lmhead_ce_fwd": 4,
-             "ergm_lmhead_ce_bwd": 4}
+_LAUNCHES = {"ergm_attn_bwd": 2,   # delta + the persistent kernel (+ memset and cast for Tq > 256)
+             "ergm_decode_layers": 1, "ergm_decode_stack_pack": 4, "ergm_lmhead_ce_fwd": 4, "ergm_lmhead_ce_bwd": 4}
 _launch_count = 0
 DYN_HINT = 0    # expected run-time row count of the packed batch being processed (engine sets it; steers tile shapes)
 PROFILE = None  # set to a list to collect (name, info, start_event, end_event) per call
