@@ -226,7 +226,8 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
                 const __grid_constant__ CUtensorMap tm_dq, const __grid_constant__ CUtensorMap tm_dk,
-                const __grid_constant__ CUtensorMap tm_dv, const AttnBwdParams p_in) {
+                const __grid_constant__ CUtensorMap tm_dv, const __grid_constant__ CUtensorMap tm_ws,
+                const AttnBwdParams p_in) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   AttnBwdParams p = p_in;
   const uint32_t base = smem_u32(smem_raw);
@@ -480,6 +481,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       if (p.dq_colsum && touched) attn_bwd_colsum16(v, qi < t.Tq, p.dq_colsum + t.h * 64 + 16 * cg, lane);
     };
     bool spt_busy = false;   // a TMA store may still be reading the dQ tiles staged in sPT
+    // key-block items (Tq > 256): dQ of one query block -> fp32 tile in smem ([2 column halves][128 rows][32 fp32],
+    // 128B-swizzled) that ONE TMA reduction adds into the fp32 workspace; the first version issued 4 scattered
+    // red.global.add.v4 per thread (32 half-used sectors per warp instruction: 1.5 - 3 us per block in the LSU)
+    auto stage_dq = [&](int buf, uint32_t tile) {
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(tDQ + 64 * buf + lane_addr + 16 * cg, v);
+      tmem_ld_wait();
+      const uint32_t row = tile + (uint32_t)(cg >> 1) * AB_TILE + (uint32_t)r * 128u;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t ch = (uint32_t)((cg & 1) * 4 + k) ^ (uint32_t)(r & 7);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (ch << 4)), "r"(v[4 * k]), "r"(v[4 * k + 1]),
+                     "r"(v[4 * k + 2]), "r"(v[4 * k + 3]) : "memory");
+      }
+    };
+    auto issue_dq_reduce = [&](const AbItem& t, int q0, uint32_t tile) {   // one thread
+      tma_reduce_add_3d(&tm_ws, tile, t.h * 64, t.q_row0 + q0, t.q_bat);
+      tma_reduce_add_3d(&tm_ws, tile + AB_TILE, t.h * 64 + 32, t.q_row0 + q0, t.q_bat);
+    };
     int n_act = 0, g = 0;
     for (int rr = 0; rr < n_rounds; ++rr) {
       const int w = item_of(rr);
@@ -557,7 +577,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (ct == 0) AB_LOG(2);
         // dQ of the PREVIOUS block (its MMAs completed before this block's S / dP did): off the critical path
         if (!whole && pend_q0 >= 0) {
-          drain_dq(t, pend_q0, (g - 1) & 1);
+          if (pend_q0 + 128 <= t.Tq) {   // CTA-uniform: whole 128-row box inside the sample -> staged TMA reduction
+            if (ct == 0) tma_store_wait_read();          // sOut: its previous tile has been read by the TMA
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            stage_dq((g - 1) & 1, sOut);
+            fence_proxy_async();
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            if (ct == 0) { issue_dq_reduce(t, pend_q0, sOut); tma_store_commit(); }
+          } else {
+            drain_dq(t, pend_q0, (g - 1) & 1);
+          }
           if (ct == 0) AB_LOG(3);
         }
         pend_q0 = q0;
@@ -572,8 +601,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       // staging tiles free again?  (dK / dV of the previous key block were handed to the TMA long ago)
       if (ct == 0) tma_store_wait_read();
       asm volatile("bar.sync 1, 512;" ::: "memory");
+      const bool dq_staged = !whole && pend_q0 + 128 <= t.Tq;   // last dQ of a key-block item goes through sPT
       if (!whole) {
-        drain_dq(t, pend_q0, (g - 1) & 1);
+        if (dq_staged) stage_dq((g - 1) & 1, sPT);
+        else drain_dq(t, pend_q0, (g - 1) & 1);
       } else if (dq_now) {
         store_dq(t, 0, dq_seen & 1u, qfull0);
         if (t.Tq > 128) store_dq(t, 1, (dq_seen >> 1) & 1u, qfull1);
@@ -594,10 +625,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (p.dk_colsum) attn_bwd_colsum16(v, kj < t.Tk, p.dk_colsum + t.h * 64 + 16 * cg, lane);
         if (p.dv_colsum) attn_bwd_colsum16(u, kj < t.Tk, p.dv_colsum + t.h * 64 + 16 * cg, lane);
       }
-      if (kfull || (dq_now && qfull0)) {   // CTA-uniform
+      if (kfull || (dq_now && qfull0) || dq_staged) {   // CTA-uniform
         fence_proxy_async();
         asm volatile("bar.sync 1, 512;" ::: "memory");
         if (ct == 0) {
+          if (dq_staged) issue_dq_reduce(t, pend_q0, sPT);
           if (kfull) {
             tma_store_3d(&tm_dk, sOut, p.dk_col0 + t.h * 64, t.k_row0 + t.k0, t.k_bat);
             tma_store_3d(&tm_dv, sOut + AB_TILE, p.dv_col0 + t.h * 64, t.k_row0 + t.k0, t.k_bat);
@@ -606,7 +638,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           if (dq_now && qfull1) tma_store_3d(&tm_dq, sPT + AB_TILE, p.dq_col0 + t.h * 64, t.q_row0 + 128, t.q_bat);
           tma_store_commit();
         }
-        spt_busy = dq_now && qfull0;
+        spt_busy = (dq_now && qfull0) || dq_staged;
       }
       if (ct == 0) AB_LOG(5);
       ++n_act;
@@ -699,7 +731,7 @@ extern "C" int ergm_attn_bwd(const void* q, int64_t ld_q, int q_col0, const void
                            reinterpret_cast<const __nv_bfloat16*>(dout), ld_do, reinterpret_cast<const __nv_bfloat16*>(out),
                            ld_out, (const float*)out_f32, delta, B * Tq, Tq, nh, pack ? pack->cu_rows : (const int*)nullptr,
                            pack ? pack->row_b : (const int*)nullptr, pack ? pack->n_rows : (const int*)nullptr));
-  CUtensorMap tq, tk, tv, tdo, tdq, tdk, tdv;
+  CUtensorMap tq, tk, tv, tdo, tdq, tdk, tdv, tws;
   int rc;
   if ((rc = encode_tmap_3d(&tq, q, 2, (uint64_t)(q_col0 + nh * 64), q_rows, q_bat,
                            (uint64_t)ld_q * 2, q_rows * ld_q * 2, 64, 128, 1))) return rc;
@@ -716,6 +748,9 @@ extern "C" int ergm_attn_bwd(const void* q, int64_t ld_q, int q_col0, const void
                            (uint64_t)ld_dk * 2, k_rows * ld_dk * 2, 64, 128, 1))) return rc;
   if ((rc = encode_tmap_3d(&tdv, dv, 2, (uint64_t)(dv_col0 + nh * 64), k_rows, k_bat,
                            (uint64_t)ld_dv * 2, k_rows * ld_dv * 2, 64, 128, 1))) return rc;
+  tws = tdq;   // (unused by whole-head items)
+  if (need > 0 && (rc = encode_tmap_3d(&tws, workspace, 4, (uint64_t)(nh * 64), q_rows, q_bat, (uint64_t)nh * 64 * 4,
+                                       q_rows * (uint64_t)nh * 64 * 4, 32, 128, 1))) return rc;
   AttnBwdParams p;
   p.lse = lse; p.delta = delta; p.dq_accum = reinterpret_cast<float*>(workspace);
   p.dq = reinterpret_cast<__nv_bfloat16*>(dq);
@@ -745,9 +780,9 @@ extern "C" int ergm_attn_bwd(const void* q, int64_t ld_q, int q_col0, const void
   const int n_items = p.whole_head ? B * nh : B * nh * ((Tk + 127) / 128);
   dim3 grid(n_items < num_sms() ? n_items : num_sms());
   if (causal)
-    ERGM_CUDA_TRY(launch_pdl(attn_bwd_kernel<true>, grid, dim3(AB_THREADS), (size_t)AB_SMEM, s, 1, tq, tk, tv, tdo, tdq, tdk, tdv, p));
+    ERGM_CUDA_TRY(launch_pdl(attn_bwd_kernel<true>, grid, dim3(AB_THREADS), (size_t)AB_SMEM, s, 1, tq, tk, tv, tdo, tdq, tdk, tdv, tws, p));
   else
-    ERGM_CUDA_TRY(launch_pdl(attn_bwd_kernel<false>, grid, dim3(AB_THREADS), (size_t)AB_SMEM, s, 1, tq, tk, tv, tdo, tdq, tdk, tdv, p));
+    ERGM_CUDA_TRY(launch_pdl(attn_bwd_kernel<false>, grid, dim3(AB_THREADS), (size_t)AB_SMEM, s, 1, tq, tk, tv, tdo, tdq, tdk, tdv, tws, p));
   if (!p.whole_head) {
     // dQ contributions of the key blocks -> bf16 dQ (+ its column sums: the bias gradient of the Q projection)
     return ergm_cast_f32_bf16_2d(reinterpret_cast<const float*>(workspace), (int64_t)nh * 64,

@@ -96,6 +96,13 @@ ERGM_DEVINL void tma_store_3d(const void* tmap, uint32_t src, int c0, int c1, in
                "r"(src), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+// TMA reduction: global[box] += smem tile (element type of the tensor map; fp32 here), same completion mechanism
+ERGM_DEVINL void tma_reduce_add_3d(const void* tmap, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 ERGM_DEVINL void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all bulk groups of this thread have finished READING their smem source (the global writes may still be in flight)
 ERGM_DEVINL void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

@@ -284,7 +284,8 @@ def test_attn_fwd_kv_lens(cuda_device):
 
 @pytest.mark.parametrize("B,nh,Tq,Tk,causal", [(2, 2, 48, 48, True), (2, 12, 256, 256, True), (1, 3, 200, 200, True),
                                                 (2, 2, 48, 40, False), (2, 4, 256, 256, False), (1, 2, 130, 300, False),
-                                                (1, 16, 512, 512, True)])
+                                                (1, 16, 512, 512, True), (1, 2, 300, 300, True),
+                                                (2, 2, 384, 200, False)])
 def test_attn_bwd(cuda_device, B, nh, Tq, Tk, causal):
     from ergm_b200 import ops
     H = nh * 64
