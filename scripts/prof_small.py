@@ -14,7 +14,7 @@ lse = torch.zeros(B, nh, T, device=dev)
 if which in ("all", "attn"):
     for causal in (True, False):
         for _ in range(2):
-            ops.attn_fwd(qkv, qkv, qkv, out, lse, B=B, nh=nh, Tq=T, Tk=T, k_col0=H, v_col0=2 * H, causal=causal, out_f32=o32)
+            ops.attn_fwd(qkv, qkv, qkv, out, lse, B=B, nh=nh, Tq=T, Tk=T, k_col0=H, v_col0=2 * H, causal=causal, out_f32=o32, dropout_p=0.1, seed=1, offset=2)
     dout = torch.randn(M, H, device=dev).bfloat16()
     dqkv = torch.zeros(M, 3 * H, device=dev, dtype=torch.bfloat16)
     dq = torch.zeros(M, H, device=dev, dtype=torch.bfloat16)
@@ -22,7 +22,7 @@ if which in ("all", "attn"):
     for causal in (True, False):
         for _ in range(2):
             ops.attn_bwd(qkv, qkv, qkv, out, dout, lse, delta, dq, dqkv, dqkv, B=B, nh=nh, Tq=T, Tk=T, k_col0=H, v_col0=2 * H,
-                         dk_col0=H, dv_col0=2 * H, causal=causal, out_f32=o32)
+                         dk_col0=H, dv_col0=2 * H, causal=causal, out_f32=o32, dropout_p=0.1, seed=1, offset=2)
 if which in ("all", "gemm"):
     a = torch.randn(M, H, device=dev).bfloat16()
     w = torch.randn(H, 3 * H, device=dev).bfloat16()
