@@ -44,7 +44,13 @@ struct AttnFwdParams {
   float scale;         // 1/sqrt(hd)
   DropoutSite drop;
   int do_drop;
+#ifdef ERGM_ATTN_TRACE
+  long long* trace;    // [ctas][64]: (event, %globaltimer) pairs of softmax thread 0 (profiling builds only)
+#endif
 };
+#ifdef ERGM_ATTN_TRACE
+long long* g_attn_fwd_trace = nullptr;
+#endif
 
 // One work item = one (batch, head, 128-query block).
 struct AfItem {
@@ -109,6 +115,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const uint32_t tmem_slot = bars + 112;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef ERGM_ATTN_TRACE
+  int n_log = 0;
+#define AF_LOG(ev)                                                                     \
+  do {                                                                                 \
+    if (p.trace && threadIdx.x == 128 && n_log < 31) {                                 \
+      long long t_;                                                                    \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                           \
+      p.trace[blockIdx.x * 64 + 2 * n_log] = (ev);                                     \
+      p.trace[blockIdx.x * 64 + 2 * n_log + 1] = t_;                                   \
+      ++n_log;                                                                         \
+    }                                                                                  \
+  } while (0)
+#else
+#define AF_LOG(ev) do {} while (0)
+#endif
   const int n_items = p.B * p.nh * ((p.Tq + 127) / 128);
   const int G = gridDim.x, cta = blockIdx.x;
   auto item_of = [&](int r) { return r * G + ((r & 1) ? G - 1 - cta : cta); };
@@ -247,7 +268,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t tP_mine = tP + lane_addr + 32 * hf;
     const uint32_t tO_mine = tO + lane_addr + 32 * hf;
     const float c = p.scale * 1.4426950408889634f;  // exp(x*scale) = exp2(x*c)
-    const uint32_t thr16 = p.drop.thr16();
+    const uint32_t thr_hi = p.drop.thr16() << 16;   // 16-bit lane >= thr16  <=>  (lane << 16) >= thr_hi
     const float keep_scale = p.do_drop ? p.drop.keep_scale() : 1.f;
     const uint32_t xch_mine = sX + (hf * 128 + r) * 4;
     const uint32_t xch_other = sX + ((hf ^ 1) * 128 + r) * 4;
@@ -270,8 +291,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       // warp-uniform: does any row of this warp need masking in this block?
       const bool need_mask = (j * 128 + 127 > t.kv_len - 1) ||
                              (CAUSAL && (j * 128 + 127 > t.q0 + (warp & 3) * 32 + p.causal_off));
+      AF_LOG(1);
       mbar_wait(bar_s, gb & 1);
       tc_fence_after();
+      AF_LOG(2);
       float mx = -INFINITY;
 #pragma unroll
       for (int cc = 0; cc < 64; cc += 16) {  // 16-column chunks: half the live registers of a 32-column one
@@ -289,8 +312,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
       }
+      AF_LOG(3);
       asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch_mine), "f"(mx) : "memory");
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      AF_LOG(4);
       float mo;
       asm volatile("ld.shared.f32 %0, [%1];" : "=f"(mo) : "r"(xch_other) : "memory");
       const float m_new = fmaxf(m, fmaxf(mx, mo));
@@ -322,8 +347,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
             const uint32_t hsh = p.drop.hash2(drop_row, (uint32_t)(k0 + cc + i) >> 1);
-            pr[i] = ((hsh & 0xffffu) >= thr16) ? pr[i] * keep_scale : 0.f;
-            pr[i + 1] = ((hsh >> 16) >= thr16) ? pr[i + 1] * keep_scale : 0.f;
+            // (the 1 / (1 - p) rescale of the kept probabilities is applied once per row, on the normalised output)
+            pr[i] = ((hsh << 16) >= thr_hi) ? pr[i] : 0.f;
+            pr[i + 1] = (hsh >= thr_hi) ? pr[i + 1] : 0.f;
           }
         }
         uint32_t pk[8];
@@ -337,7 +363,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_p);
+      AF_LOG(5);
       mbar_wait(bar_o, gb & 1);
+      AF_LOG(6);
       tc_fence_after();
       {
         uint32_t v[32];
@@ -347,6 +375,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], alpha, __uint_as_float(v[i]));
       }
       tc_fence_before();
+      AF_LOG(7);
       }
       // combine the two half-row sums
       asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch_mine), "f"(l) : "memory");
@@ -354,7 +383,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       float lo;
       asm volatile("ld.shared.f32 %0, [%1];" : "=f"(lo) : "r"(xch_other) : "memory");
       l += lo;
-      const float inv = l > 0.f ? 1.f / l : 0.f;
+      const float inv = l > 0.f ? keep_scale / l : 0.f;   // l sums the un-dropped probabilities; kept ones carry 1 / (1 - p)
       const bool full = t.q0 + 128 <= t.Tq;   // CTA-uniform
       const int qs = n & 1;
       if (full) {
@@ -383,13 +412,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       if (qi < t.Tq) {
         if (p.out_f32) {
           float* of = p.out_f32 + (t.out_row0 + qi) * (p.nh * AT_D) + h * AT_D + 32 * hf;
+          // 256-bit stores: a warp instruction fills 32 whole sectors (the float4 version touched 32 half sectors per
+          // instruction and twice as many instructions: 3.3 us per item in the LSU, profiles/r2_attn_fwd_timeline.txt)
 #pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            *reinterpret_cast<float4*>(of + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
+          for (int i = 0; i < 32; i += 8)
+            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(of + i), "f"(o[i] * inv),
+                         "f"(o[i + 1] * inv), "f"(o[i + 2] * inv), "f"(o[i + 3] * inv), "f"(o[i + 4] * inv),
+                         "f"(o[i + 5] * inv), "f"(o[i + 6] * inv), "f"(o[i + 7] * inv)
+                         : "memory");
         }
         if (p.lse && hf == 0)
           p.lse[t.stat_row0 + qi] = (m == -INFINITY ? 0.f : m) * p.scale + logf(l);
       }
+      AF_LOG(8);
       ++n;
     }
   }
@@ -444,6 +479,9 @@ extern "C" int ergm_attn_fwd(const void* q, int64_t ld_q, int q_col0, const void
   p.scale = 1.0f / sqrtf((float)head_dim);
   p.drop = make_site(seed, offset, dropout_p, (uint32_t)Tk);
   p.do_drop = dropout_p > 0.f;
+#ifdef ERGM_ATTN_TRACE
+  p.trace = g_attn_fwd_trace;
+#endif
   {
     static std::atomic<uint64_t> done_mask{0};
     int dev = 0;
@@ -466,3 +504,7 @@ extern "C" int ergm_attn_fwd(const void* q, int64_t ld_q, int q_col0, const void
     return (int)launch_pdl(attn_fwd_kernel<true>, grid, dim3(AT_THREADS), (size_t)AT_SMEM, (cudaStream_t)stream, 1, tq, tk, tv, tout, p);
   return (int)launch_pdl(attn_fwd_kernel<false>, grid, dim3(AT_THREADS), (size_t)AT_SMEM, (cudaStream_t)stream, 1, tq, tk, tv, tout, p);
 }
+
+#ifdef ERGM_ATTN_TRACE
+extern "C" int ergm_attn_fwd_set_trace(long long* dev_ptr) { ergm::g_attn_fwd_trace = dev_ptr; return ERGM_OK; }
+#endif
