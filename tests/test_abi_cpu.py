@@ -132,3 +132,26 @@ def test_lmhead_ce_workspace_query_without_gpu():
     ldl = (50260 + 63) // 64 * 64
     assert both[5] - both[4] == 8192 * ldl * 2            # bf16 logits of the scored rows (capacity = all rows)
     assert both[-1] - both[8] == 8192 * 768 * 4
+
+
+def test_kv_page_allocator_host_logic():
+    """Free-list page allocator of the generation K/V pool (no kernels involved: runs on the CPU device)."""
+    import types
+    import torch
+    from ergm_b200 import generation
+    eng = types.SimpleNamespace(nh=2, L=3, device=torch.device("cpu"))
+    alloc = generation.page_allocator(eng)
+    assert generation.page_allocator(eng) is alloc
+    t1, ids1 = alloc.alloc_table(3, 4)
+    assert t1.shape == (3, 4) and sorted(ids1) == list(range(12)) and alloc.n_pages == 12
+    assert t1[:, 0].tolist() == [0, 1, 2] and t1[0].tolist() == [0, 3, 6, 9]       # page j of every sequence first
+    assert len(alloc.pools) == 3 and alloc.pools[0].shape == (12, 2, 2, generation.PAGE, 64)
+    t2, ids2 = alloc.alloc_table(2, 2)                                             # grows: 4 more pages, ids1 stay reserved
+    assert alloc.n_pages == 16 and sorted(ids2) == [12, 13, 14, 15] and not set(ids1) & set(ids2)
+    alloc.release(ids1)
+    t3, ids3 = alloc.alloc_table(4, 3)                                             # reuses the released pages, no growth
+    assert alloc.n_pages == 16 and sorted(ids3) == sorted(ids1)
+    assert len(alloc.free) == 0
+    alloc.release(ids2)
+    alloc.release(ids3)
+    assert sorted(alloc.free) == list(range(16))
