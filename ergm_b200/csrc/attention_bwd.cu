@@ -4,9 +4,10 @@
 // dO, recomputing the probabilities from the saved log-sum-exp instead of storing the
 // [B,nh,T,T] score / probability tensors the reference keeps for autograd.
 //
-// One CTA = one (batch, head, 128-key block j); it loops over the query blocks i that can see
-// those keys.  Everything is computed TRANSPOSED (keys on TMEM lanes, queries on columns) so
-// that P^T and dS^T come out of the softmax warps exactly in the layout the next MMAs need:
+// Persistent kernel: one CTA per SM walks a list of work items.  An item is a whole (batch, head) - all its 128-key
+// blocks j, each against the query blocks i that can see those keys - when the sequence has at most two query blocks
+// (dQ then stays in TMEM), otherwise a single key block.  Everything is computed TRANSPOSED (keys on TMEM lanes,
+// queries on columns) so that P^T and dS^T come out of the element-wise warps exactly in the layout the next MMAs need:
 //   S^T  = K_j Q_i^T                      SS MMA  M128(kv) N128(q) K64      -> TMEM [0,128)
 //   dP^T = V_j dO_i^T                     SS MMA                            -> TMEM [128,256)
 //   P^T  = exp2(S^T c - lse_i log2e),  dS^T = P^T (dP^T - delta_i) scale    (8 compute warps)
@@ -16,7 +17,8 @@
 // The smem tile holding dS^T ([kv rows][q contiguous], 128B swizzle) is at the same time the
 // K-major A operand of the dK product and the MN-major A operand of the dQ product, and the
 // TMA tiles of Q_i / dO_i / K_j serve as K-major and MN-major B operands without any copy.
-// dQ is accumulated across key blocks with red.global.add.v4.f32 into an fp32 buffer.
+// dQ / dK / dV leave through smem tiles and TMA stores (whole-head items) or, for dQ of key-block items, one TMA
+// reduction into an fp32 workspace; blocks that end inside a sample are stored by the threads.
 #include "../../include/ergm_b200.h"
 #include "common.cuh"
 #include "dropout.cuh"

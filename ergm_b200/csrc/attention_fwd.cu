@@ -6,10 +6,10 @@
 // [rows, ld] projection outputs with 3-D TMA maps (col, row-in-sequence, batch) and the
 // context is written merged as [B*Tq, nh*64].
 //
-// One CTA = one (batch, head, 128-query block); TWO CTAs are resident per SM (82 KB smem, 256 TMEM
-// columns, <= 80 registers x 384 threads each) so that one CTA's exp phase (MUFU-bound) overlaps
-// the other's load / MMA / barrier latencies.  Warp roles: 0 = TMA, 1 = MMA issuer, 2 = TMEM
-// allocator, 4..11 = softmax.  Two softmax threads share a query row (TMEM lane): each owns 64 of
+// Persistent kernel: TWO CTAs are resident per SM (97 KB smem, 256 TMEM columns, <= 80 registers x 384 threads each),
+// each walks a static list of (batch, head, 128-query block) work items, so that one CTA's exp phase overlaps the
+// other's load / MMA / barrier latencies.  Warp roles: 0 = TMA producer (runs ahead across items), 1 = MMA issuer,
+// 2 = TMEM allocator, 3 = output TMA store, 4..11 = softmax.  Two softmax threads share a query row (TMEM lane): each owns 64 of
 // the 128 key columns of the current block and 32 of the 64 output columns; the row maximum is
 // exchanged through shared memory once per key block, the row sum once at the end.
 //   S   = Q K_j^T           SS MMA M128 N128 K64    -> TMEM cols [0,128)
