@@ -55,6 +55,8 @@ struct GemmParams {
   DropoutSite site;
   const int* dyn;  // nullable device int: the run-time extent of M (dyn_dim 1) or K (dyn_dim 2), <= the static one
   int dyn_dim;
+  int pdl_trigger;  // release the stream's next kernel early (training-size problems; the M <= 128 decode-step
+                    // GEMMs keep the implicit trigger at exit: an early-resident top-k sampler cost 110 us per step)
 };
 
 // Run-time problem extent (label-sparse LM head, packed batches): the host sizes the launch, the tensor maps and
@@ -469,7 +471,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
   // global memory and may overlap the tail of the previous kernel of the stream; nothing below runs before that
   // kernel has completed.  Our own dependents may be scheduled as soon as every CTA of this grid got here.
   pdl_wait();
-  pdl_launch_dependents();
+  if (p.pdl_trigger) pdl_launch_dependents();
   apply_dyn(p, BM, (int)gridDim.x);
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -653,7 +655,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
   cluster_sync();
   tc_fence_after();
   pdl_wait();               // (see gemm_bf16_kernel) no global memory access above this line
-  pdl_launch_dependents();
+  if (p.pdl_trigger) pdl_launch_dependents();
   apply_dyn(p, 256, (int)(gridDim.x >> 1));
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -796,6 +798,7 @@ static int launch_gemm2(const ergm_gemm_args* a, cudaStream_t stream) {
   p.dropout_p = a->dropout_p;
   p.site = make_site(a->seed, a->offset, a->dropout_p, (uint32_t)a->N);
   p.dyn = a->dyn_count; p.dyn_dim = a->dyn_count ? a->dyn_dim : 0;
+  p.pdl_trigger = a->M > 128;
   ERGM_SET_SMEM_ATTR((gemm2_bf16_kernel<BN, EC, FM>), Cfg::SMEM_BYTES);
   const int total = p.m_tiles * p.n_tiles * p.split_k;
   const int max_clusters = num_sms() / 2;
@@ -838,6 +841,7 @@ static int launch_gemm(const ergm_gemm_args* a, cudaStream_t stream) {
   p.dropout_p = a->dropout_p;
   p.site = make_site(a->seed, a->offset, a->dropout_p, (uint32_t)a->N);
   p.dyn = a->dyn_count; p.dyn_dim = a->dyn_count ? a->dyn_dim : 0;
+  p.pdl_trigger = a->M > 128;
 
   ERGM_SET_SMEM_ATTR((gemm_bf16_kernel<BN, EC, FM>), Cfg::SMEM_BYTES);
   const int total = p.m_tiles * p.n_tiles * p.split_k;
