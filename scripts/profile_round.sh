@@ -1,3 +1,7 @@
+#!/bin/bash
+# End-of-round evidence on one B200 (run through gpurun): ncu metrics of the hot kernels at config-2 shapes, an ncu launch
+# list of bench.py without the CUDA graph (cut ONE training step out of it: profiles/README.md), then the default bench line.
+# Each command runs plainly first; ncu only after it exited 0.  The launch list takes ~10 minutes under ncu.
 mkdir -p gpurun_out/logs gpurun_out/ncu
 M=gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,dram__bytes_read.sum,dram__bytes_write.sum,dram__throughput.avg.pct_of_peak_sustained_elapsed,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,sm__inst_executed_pipe_tensor.sum
 timeout 120 python scripts/prof_small.py > gpurun_out/logs/prof_small_plain.log 2>&1 && \
